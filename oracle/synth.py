@@ -1,0 +1,129 @@
+"""Deterministic synthetic weights / pileup inputs shared by the oracle, tests and bench.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py): nothing under ``medaka_b200/`` imports this.
+
+Everything here uses ``numpy.random.RandomState`` (frozen bit-stream guarantee) so
+that fixtures made in the build container (tests/golden/make_golden.py, which runs
+the real reference classes) can be regenerated bit-for-bit on the GPU box where
+/root/reference does not exist.
+
+State-dict key names and shapes follow torch.nn.GRU / Linear exactly as the
+reference's GRUModel uses them (medaka/architectures/gru.py:46-55): gate order
+r,z,n; ``gru.weight_ih_l{k}[_reverse]`` [3H,in], ``gru.weight_hh_l{k}[_reverse]``
+[3H,H], ``gru.bias_ih/bias_hh`` [3H], ``linear.weight`` [5,2H], ``linear.bias`` [5].
+"""
+import numpy as np
+
+GATES = 3
+
+
+def state_dict_keys(n_layers=2, bidirectional=True):
+    keys = []
+    for layer in range(n_layers):
+        for sfx in ([""] + (["_reverse"] if bidirectional else [])):
+            for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                keys.append("gru.{}_l{}{}".format(name, layer, sfx))
+    keys += ["linear.weight", "linear.bias"]
+    return keys
+
+
+def synth_state_dict(seed=0, num_features=10, gru_size=128, n_layers=2,
+                     bidirectional=True, head_gain=8.0, rec_gain=1.0):
+    """Seeded float32 weights, torch-default scale U(-1/sqrt(H), 1/sqrt(H)).
+
+    ``head_gain`` widens the Linear so logits have a realistic spread (random
+    default-init heads give near-uniform softmax, i.e. nothing but near-ties;
+    SURVEY.md section 7, "Precision vs parity").
+    Returns {key: np.ndarray(float32)} with torch's state-dict key names.
+    """
+    rs = np.random.RandomState(seed)
+    H = gru_size
+    ndir = 2 if bidirectional else 1
+    bound = 1.0 / np.sqrt(H)
+    sd = {}
+    for layer in range(n_layers):
+        n_in = num_features if layer == 0 else H * ndir
+        for sfx in ([""] + (["_reverse"] if bidirectional else [])):
+            sd["gru.weight_ih_l{}{}".format(layer, sfx)] = rs.uniform(
+                -bound, bound, (GATES * H, n_in)).astype(np.float32)
+            sd["gru.weight_hh_l{}{}".format(layer, sfx)] = (rec_gain * rs.uniform(
+                -bound, bound, (GATES * H, H))).astype(np.float32)
+            sd["gru.bias_ih_l{}{}".format(layer, sfx)] = rs.uniform(
+                -bound, bound, (GATES * H,)).astype(np.float32)
+            sd["gru.bias_hh_l{}{}".format(layer, sfx)] = rs.uniform(
+                -bound, bound, (GATES * H,)).astype(np.float32)
+    lb = 1.0 / np.sqrt(H * ndir)
+    sd["linear.weight"] = (head_gain * rs.uniform(-lb, lb, (5, H * ndir))).astype(np.float32)
+    sd["linear.bias"] = (head_gain * rs.uniform(-lb, lb, (5,))).astype(np.float32)
+    return sd
+
+
+def synth_counts(n_cols, seed=20240923, num_dtypes=1, mean_depth=30, max_depth=120,
+                 minor_frac=0.15, start_major=0, start_on_minor=False):
+    """Synthetic raw pileup counts the way BASELINE.md section 4 describes them.
+
+    Returns (counts uint64[n_cols, 10*num_dtypes], positions structured
+    [('major', i8), ('minor', i8)]) laid out as medaka_counts.c emits them
+    (src/medaka_counts.c:274-357): feature order 'acgtACGTdD' per dtype, lower
+    case = reverse strand; a major column followed by its minor (insertion)
+    columns which only carry the reads that have the insertion.
+    """
+    rs = np.random.RandomState(seed)
+    F = 10 * num_dtypes
+    is_minor = rs.uniform(size=n_cols) < minor_frac
+    is_minor[0] = bool(start_on_minor)
+    major = start_major + np.cumsum(~is_minor) - (0 if start_on_minor else 1)
+    major = major.astype(np.int64)
+    # minor index = run length since last major
+    idx = np.arange(n_cols)
+    last_major_idx = np.maximum.accumulate(np.where(~is_minor, idx, -1))
+    minor = (idx - last_major_idx).astype(np.int64)
+    if start_on_minor:
+        # chunk cut in the middle of an insertion run: first column is minor 1..
+        minor = np.where(last_major_idx < 0, idx + 1, minor).astype(np.int64)
+    depth = np.clip(rs.poisson(mean_depth, n_cols), 1, max_depth)
+    counts = np.zeros((n_cols, F), dtype=np.uint64)
+    true_base = rs.randint(0, 4, n_cols)
+    for dt in range(num_dtypes):
+        d_dt = depth if num_dtypes == 1 else rs.binomial(depth, 1.0 / num_dtypes)
+        fwd = rs.binomial(d_dt, 0.5)
+        rev = d_dt - fwd
+        for strand_n, base_off, del_idx in ((rev, 0, 8), (fwd, 4, 9)):
+            # 5 outcomes: 4 bases + deletion; 0.94 on the true base
+            p = np.full((n_cols, 5), 0.015)
+            p[idx, true_base] = 0.94
+            p /= p.sum(axis=1, keepdims=True)
+            # vectorised multinomial by sequential binomials
+            remaining = strand_n.copy()
+            rem_p = np.ones(n_cols)
+            outs = []
+            for k in range(5):
+                pk = np.clip(p[:, k] / np.maximum(rem_p, 1e-12), 0, 1)
+                x = rs.binomial(remaining, pk) if k < 4 else remaining
+                outs.append(x)
+                remaining = remaining - x
+                rem_p = rem_p - p[:, k]
+            for b in range(4):
+                counts[:, dt * 10 + base_off + b] = outs[b]
+            counts[:, dt * 10 + del_idx] = outs[4]
+    # minor columns: only ~15% of the parent's reads carry the insertion, no deletions
+    keep = rs.uniform(size=(n_cols, F)) < 0.15
+    minor_counts = np.where(keep, counts, 0).astype(np.uint64)
+    for dt in range(num_dtypes):
+        minor_counts[:, dt * 10 + 8] = 0
+        minor_counts[:, dt * 10 + 9] = 0
+    counts = np.where(is_minor[:, None] | (minor[:, None] > 0), minor_counts, counts)
+    positions = np.empty(n_cols, dtype=[("major", "<i8"), ("minor", "<i8")])
+    positions["major"] = major
+    positions["minor"] = minor
+    return counts, positions
+
+
+def synth_features(B, T, F=10, seed=1234):
+    """Normalised-count-like float32 features [B, T, F] in [0, 1] (sum per dtype <= 1)."""
+    rs = np.random.RandomState(seed)
+    x = rs.dirichlet(np.full(F, 0.35), size=(B, T)).astype(np.float32)
+    # some all-zero columns and sparse insertion-like columns, as real pileups have
+    mask = rs.uniform(size=(B, T, 1)) < 0.02
+    x = np.where(mask, 0.0, x).astype(np.float32)
+    return x
