@@ -1,0 +1,169 @@
+/*
+ * medaka_b200.h - C ABI of libmedaka_b200.so, the sm_100a engine behind medaka's
+ * inference hot path (medaka/prediction.py:44-52).
+ *
+ * Plain C: opaque handles, pointers + sizes, int return codes (0 = MDK_OK).  No torch
+ * types, no exit(): every failure returns a negative code and leaves a message in
+ * mdk_last_error() (the reference's C layer calls exit(1) on error,
+ * src/medaka_common.c:19-26; a drop-in library must not).
+ *
+ * Each entry point cites the reference interface it replaces.  The cffi binding a
+ * medaka maintainer would add is in INTEGRATION.md; medaka_b200/libmedaka.py is
+ * that binding (it cdef()s this file minus the '#' lines, like the reference's
+ * build.py:71-82 does for libmedaka).
+ *
+ * Conventions
+ *   - "host" pointers are ordinary host memory (pinned memory from mdk_host_alloc makes
+ *     the copies asynchronous); "dev" pointers are CUDA device pointers on the engine's
+ *     device (e.g. torch tensor .data_ptr()).
+ *   - feats   float32 [B][T][F] row-major (torch_ext.Batch.counts_matrix, torch_ext.py:155)
+ *   - probs   float32 [B][T][5]  (GRUModel.forward output, gru.py:58-72)
+ *   - logits  float32 [B][T][5]  (pre-softmax, gru.py:67)            - optional (NULL)
+ *   - labels  uint8   [B][T]     (argmax, first max wins, labels.py:1063) - optional
+ *   - weights: torch state-dict layout (gate order r,z,n): w_ih [3H][in], w_hh [3H][H],
+ *     b_ih [3H], b_hh [3H]; linear w [5][2H], b [5]   
+ */
+#ifndef MEDAKA_B200_H
+#define MEDAKA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDK_OK 0
+#define MDK_ERR_ARG -1
+#define MDK_ERR_CUDA -2
+#define MDK_ERR_STATE -3
+#define MDK_ERR_UNSUPPORTED -4
+#define MDK_ERR_NOMEM -5
+
+/* precision modes of the GRU gate matmuls */
+#define MDK_PREC_TC 0    /* tcgen05 tensor cores, fp16 hi/lo split operands (3 MMAs), fp32 accumulate */
+#define MDK_PREC_FP32 1  /* CUDA-core fp32 FFMA path: validation / --full_precision */
+
+/* count normalisation modes: CountsFeatureEncoder._norm_modes_ (medaka/features.py:816) */
+#define MDK_NORM_TOTAL 0
+#define MDK_NORM_FWD_REV 1
+#define MDK_NORM_NONE 2
+
+typedef struct mdk_engine mdk_engine;
+
+/* GRUModel constructor arguments (medaka/architectures/gru.py:13-21). */
+typedef struct mdk_model_desc {
+    int32_t num_features;   /* F = 10 * len(dtypes) */
+    int32_t gru_size;       /* H; this build supports 128 (every shipped counts-matrix model) */
+    int32_t n_layers;       /* 2 */
+    int32_t bidirectional;  /* 1 */
+    int32_t num_classes;    /* linear head is hard-coded to 5 outputs (gru.py:53-55) */
+} mdk_model_desc;
+
+/* per-stage device timings of the last mdk_engine_forward* call, milliseconds (CUDA events) */
+typedef struct mdk_timings {
+    float h2d_ms;
+    float inproj0_ms;   /* layer-0 input projection */
+    float rec0_ms;      /* layer-0 recurrence (both directions) */
+    float inproj1_ms;   /* layer-1 input projection GEMM */
+    float rec1_ms;      /* layer-1 recurrence */
+    float head_ms;      /* linear + softmax + argmax */
+    float d2h_ms;
+    float total_ms;
+    int32_t launches;   /* kernels launched by the call */
+} mdk_timings;
+
+/* constants the Python layer reads from the library, like libmedaka.lib.plp_bases etc.
+ * (src/medaka_counts.h:19-22; read at medaka/common.py:29-35, medaka/features.py:860,902-904) */
+const char *mdk_plp_bases(void);   /* "acgtACGTdD" */
+size_t mdk_featlen(void);          /* 10 */
+size_t mdk_fwd_del(void);          /* 9 */
+size_t mdk_rev_del(void);          /* 8 */
+
+const char *mdk_last_error(void);  /* thread-local message of the last failing call */
+const char *mdk_version(void);
+int mdk_device_count(int *count);
+/* sm major*10+minor of `device`, SM count, bytes of global memory */
+int mdk_device_info(int device, int *sm_arch, int *sm_count, size_t *total_mem);
+
+/* pinned host memory for batch staging (replaces the pageable .to(device) / .cpu() copies of
+ * TorchModel.predict_on_batch, medaka/models.py:309,312) */
+int mdk_host_alloc(size_t bytes, void **out);
+int mdk_host_free(void *p);
+/* raw device memory + copies, for callers that keep inputs resident in HBM (bench, tests) */
+int mdk_dev_alloc(int device, size_t bytes, void **out);
+int mdk_dev_free(int device, void *p);
+int mdk_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes);
+int mdk_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes);
+int mdk_dev_memset(int device, void *dst_dev, int value, size_t bytes);
+int mdk_device_synchronize(int device);
+
+/* ---- model seam: replaces ModelStoreTGZ.load_model + TorchModel.predict_on_batch --------------
+ * (medaka/datastore.py:135-157, medaka/models.py:303-313) */
+int mdk_engine_create(int device, const mdk_model_desc *desc, mdk_engine **out);
+int mdk_engine_destroy(mdk_engine *e);
+/* load_state_dict for one (layer, direction) of gru.* ; direction 1 = "_reverse" */
+int mdk_engine_load_gru(mdk_engine *e, int layer, int direction, const float *w_ih,
+                        const float *w_hh, const float *b_ih, const float *b_hh);
+int mdk_engine_load_linear(mdk_engine *e, const float *w, const float *b);
+/* TorchModel.half() / --full_precision (medaka/prediction.py:164-168): MDK_PREC_* */
+int mdk_engine_set_precision(mdk_engine *e, int mode);
+int mdk_engine_get_precision(mdk_engine *e, int *mode);
+/* pre-size the device workspace for up to B windows of T columns (otherwise grown on demand) */
+int mdk_engine_reserve(mdk_engine *e, int64_t B, int64_t T);
+/* predict_on_batch with HOST buffers: H2D feats, forward, D2H probs (+logits, +labels when
+ * non-NULL); returns when outputs are in host memory. */
+int mdk_engine_forward(mdk_engine *e, const float *feats_host, int64_t B, int64_t T,
+                       float *probs_host, float *logits_host, uint8_t *labels_host);
+/* same forward with DEVICE buffers (inputs resident in HBM); asynchronous on the engine stream,
+ * complete after mdk_engine_sync(). */
+int mdk_engine_forward_dev(mdk_engine *e, const float *feats_dev, int64_t B, int64_t T,
+                           float *probs_dev, float *logits_dev, uint8_t *labels_dev);
+int mdk_engine_sync(mdk_engine *e);
+int mdk_engine_last_timings(mdk_engine *e, mdk_timings *out);
+/* mean per-stage device times over the last n_last (<= 32) forward calls */
+int mdk_engine_mean_timings(mdk_engine *e, int n_last, mdk_timings *out);
+/* bracket a timed region on the engine stream with CUDA events (bench.py) */
+int mdk_engine_timer_start(mdk_engine *e);
+int mdk_engine_timer_stop(mdk_engine *e, float *elapsed_ms);
+/* debugging / layer-wise parity: copy an internal activation of the last forward to host.
+ * which: 0 = layer-0 output [B][T][2H] fp32, 1 = layer-1 output [B][T][2H] fp32 */
+int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_t n_floats);
+/* number of kernels launched by this engine since creation (bench.py "gpu_launches") */
+int64_t mdk_engine_launch_count(mdk_engine *e);
+
+/* ---- featuriser seam: replaces CountsFeatureEncoder._post_process_pileup --------------------
+ * (medaka/features.py:871-935): depth = sum of counts, minor columns take the depth of their
+ * major column (np.searchsorted side='left'), optional sym_indels fill, normalisation by
+ * `mode`, float64 divide then cast to float32.  counts is what calculate_pileup returns
+ * (size_t matrix, src/medaka_counts.h:5-14): uint64 [n][F], F = 10 * num_dtypes.
+ * feats_out float32 [n][F]; depth_out int64 [n] (may be NULL).
+ * Host-buffer version stages through the device; *_dev works on device pointers. */
+int mdk_normalise_counts(int device, const uint64_t *counts, const int64_t *major,
+                         const int64_t *minor, int64_t n, int32_t num_dtypes, int32_t mode,
+                         int32_t sym_indels, float *feats_out, int64_t *depth_out);
+int mdk_normalise_counts_dev(int device, const uint64_t *counts_dev, const int64_t *major_dev,
+                             const int64_t *minor_dev, int64_t n, int32_t num_dtypes,
+                             int32_t mode, int32_t sym_indels, float *feats_out_dev,
+                             int64_t *depth_out_dev);
+
+/* ---- decode seam: replaces the array part of HaploidLabelScheme.decode_consensus ------------
+ * (medaka/labels.py:1053-1085 with _phred :387-401): labels = argmax (first max wins),
+ * quals = uint8(min(70, -10*log10(clip(1-p_max, 1e-7, 1)))) + 33.  probs float32 [n][5].
+ * Gap removal / string building stays on the host.  quals may be NULL. */
+int mdk_decode_consensus(int device, const float *probs, int64_t n, uint8_t *labels_out,
+                         uint8_t *quals_out);
+int mdk_decode_consensus_dev(int device, const float *probs_dev, int64_t n,
+                             uint8_t *labels_out_dev, uint8_t *quals_out_dev);
+
+/* ---- self test of the tcgen05 building block (one 128xN tile GEMM), used by tests ----------
+ * Computes D[128][N] = A[128][K] * B[N][K]^T with the same smem layouts, descriptors and
+ * fp16 hi/lo split the GRU kernels use.  A, B, D are host fp32.  variant selects descriptor
+ * hypotheses (0 = production encoding). */
+int mdk_selftest_umma(int device, const float *A, const float *B, float *D, int N, int K,
+                      int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDAKA_B200_H */

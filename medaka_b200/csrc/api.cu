@@ -1,0 +1,525 @@
+// C ABI of libmedaka_b200 (include/medaka_b200.h): engine life-cycle, weight loading, the forward
+// pipeline, and the featuriser / decode entry points.  Host orchestration only - kernels live in
+// misc.cu, gru_fp32.cu and gru_tc.cu.
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mdk {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t err, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d: %s", (int)err, cudaGetErrorString(err), file, line, what);
+    g_last_error = buf;
+    if (err == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return MDK_ERR_NOMEM;
+    }
+    return MDK_ERR_CUDA;
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t n_elems) {
+    MDK_CUDA(cudaMalloc(reinterpret_cast<void **>(p), n_elems * sizeof(T)));
+    return MDK_OK;
+}
+template <typename T>
+static void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static int upload(float **dst, const float *src, size_t n) {
+    if (!*dst) {
+        int rc = dev_alloc(dst, n);
+        if (rc) return rc;
+    }
+    MDK_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return MDK_OK;
+}
+
+static int in_features(const mdk_engine *e, int layer) { return layer == 0 ? e->desc.num_features : H2; }
+
+static int prepare_weights(mdk_engine *e) {
+    if (e->prepared) return MDK_OK;
+    for (int l = 0; l < 2; ++l) {
+        MDK_REQUIRE(e->layer[l].loaded[0] && e->layer[l].loaded[1], MDK_ERR_STATE,
+                    "engine: GRU weights not loaded for every (layer, direction)");
+    }
+    MDK_REQUIRE(e->lin_loaded, MDK_ERR_STATE, "engine: linear head weights not loaded");
+    for (int l = 0; l < 2; ++l) {
+        LayerWeights &lw = e->layer[l];
+        const int in = in_features(e, l);
+        int rc;
+        if (!lw.w_in_packed && (rc = dev_alloc(&lw.w_in_packed, (size_t)GI_COLS * in))) return rc;
+        if (!lw.bias_gi && (rc = dev_alloc(&lw.bias_gi, (size_t)GI_COLS))) return rc;
+        if (!lw.b_hn && (rc = dev_alloc(&lw.b_hn, (size_t)NDIR * H))) return rc;
+        if (!lw.w_hh_t && (rc = dev_alloc(&lw.w_hh_t, (size_t)NDIR * H * G3))) return rc;
+        if (!lw.w_hh_tc && (rc = dev_alloc(&lw.w_hh_tc, (size_t)NDIR * 2 * G3 * H))) return rc;
+        if (l == 1 && !lw.w_in_tc && (rc = dev_alloc(&lw.w_in_tc, (size_t)2 * GI_COLS * H2))) return rc;
+        MDK_CUDA(launch_prepare_layer(lw, in, l == 1, e->stream));
+        e->launches++;
+    }
+    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    e->prepared = true;
+    return MDK_OK;
+}
+
+static int ensure_workspace(mdk_engine *e, int64_t B, int64_t T) {
+    const int64_t P = B * T;
+    const int64_t need = ((P + XT_ROWS - 1) / XT_ROWS) * XT_ROWS;
+    if (need <= e->cap_pos) return MDK_OK;
+    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    dev_free(e->gi);
+    if (e->h0) { cudaFree(e->h0); e->h0 = nullptr; }
+    dev_free(e->h1);
+    e->cap_pos = 0;
+    int rc;
+    if ((rc = dev_alloc(&e->gi, (size_t)need * GI_COLS))) return rc;
+    MDK_CUDA(cudaMalloc(&e->h0, (size_t)need * H2 * sizeof(float)));
+    if ((rc = dev_alloc(&e->h1, (size_t)need * H2))) return rc;
+    e->cap_pos = need;
+    return MDK_OK;
+}
+
+static int ensure_io(mdk_engine *e, int64_t B, int64_t T) {
+    const int64_t P = B * T;
+    const int64_t feats = P * e->desc.num_features;
+    if (P <= e->cap_io && feats <= e->cap_feats_floats) return MDK_OK;
+    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    dev_free(e->d_feats); dev_free(e->d_probs); dev_free(e->d_logits); dev_free(e->d_labels);
+    e->cap_io = 0; e->cap_feats_floats = 0;
+    int rc;
+    if ((rc = dev_alloc(&e->d_feats, (size_t)feats))) return rc;
+    if ((rc = dev_alloc(&e->d_probs, (size_t)P * NCLS))) return rc;
+    if ((rc = dev_alloc(&e->d_logits, (size_t)P * NCLS))) return rc;
+    if ((rc = dev_alloc(&e->d_labels, (size_t)P))) return rc;
+    e->cap_io = P; e->cap_feats_floats = feats;
+    return MDK_OK;
+}
+
+// The forward pipeline on e->stream.  ev[1..6] bracket the stages for mdk_timings.
+static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t T, float *probs_dev,
+                       float *logits_dev, uint8_t *labels_dev) {
+    int rc;
+    if ((rc = prepare_weights(e))) return rc;
+    if ((rc = ensure_workspace(e, B, T))) return rc;
+    const int64_t P = B * T;
+    cudaStream_t s = e->stream;
+    const bool tc = e->precision == MDK_PREC_TC;
+    int launches = 0;
+    MDK_CUDA(cudaEventRecord(e->ev[1], s));
+    MDK_CUDA(launch_inproj0(feats_dev, e->layer[0].w_in_packed, e->layer[0].bias_gi, e->gi, P,
+                            e->desc.num_features, s));
+    launches++;
+    MDK_CUDA(cudaEventRecord(e->ev[2], s));
+    if (tc) MDK_CUDA(launch_rec_tc(e->gi, e->layer[0].w_hh_tc, e->layer[0].b_hn, e->h0, 1, B, T, e->sm_count, s));
+    else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[0].w_hh_t, e->layer[0].b_hn, (float *)e->h0, B, T, s));
+    launches++;
+    MDK_CUDA(cudaEventRecord(e->ev[3], s));
+    if (tc) MDK_CUDA(launch_gemm_tc(e->h0, e->layer[1].w_in_tc, e->layer[1].bias_gi, e->gi, P, e->sm_count, s));
+    else MDK_CUDA(launch_gemm_fp32((const float *)e->h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, e->gi, P, s));
+    launches++;
+    MDK_CUDA(cudaEventRecord(e->ev[4], s));
+    if (tc) MDK_CUDA(launch_rec_tc(e->gi, e->layer[1].w_hh_tc, e->layer[1].b_hn, e->h1, 0, B, T, e->sm_count, s));
+    else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[1].w_hh_t, e->layer[1].b_hn, e->h1, B, T, s));
+    launches++;
+    MDK_CUDA(cudaEventRecord(e->ev[5], s));
+    MDK_CUDA(launch_head(e->h1, e->lin_w, e->lin_b, P, probs_dev, logits_dev, labels_dev, s));
+    launches++;
+    MDK_CUDA(cudaEventRecord(e->ev[6], s));
+    e->launches += launches;
+    e->last.launches = launches;
+    e->last_B = B; e->last_T = T; e->last_precision = e->precision;
+    return MDK_OK;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+    return ms;
+}
+
+static int check_shapes(const mdk_engine *e, const void *feats, int64_t B, int64_t T, const void *probs) {
+    MDK_REQUIRE(e != nullptr, MDK_ERR_ARG, "engine is NULL");
+    MDK_REQUIRE(feats != nullptr && probs != nullptr, MDK_ERR_ARG, "forward: feats/probs must not be NULL");
+    MDK_REQUIRE(B >= 1 && T >= 1, MDK_ERR_ARG, "forward: need B >= 1 and T >= 1");
+    MDK_REQUIRE(B * T < (int64_t)1 << 40, MDK_ERR_ARG, "forward: B*T too large");
+    return MDK_OK;
+}
+
+}  // namespace mdk
+
+using namespace mdk;
+
+extern "C" {
+
+const char *mdk_plp_bases(void) { return "acgtACGTdD"; }
+size_t mdk_featlen(void) { return 10; }
+size_t mdk_fwd_del(void) { return 9; }
+size_t mdk_rev_del(void) { return 8; }
+const char *mdk_last_error(void) { return g_last_error.c_str(); }
+const char *mdk_version(void) { return "medaka_b200 0.1.0 (sm_100a)"; }
+
+int mdk_device_count(int *count) {
+    MDK_REQUIRE(count, MDK_ERR_ARG, "count is NULL");
+    cudaError_t err = cudaGetDeviceCount(count);
+    if (err != cudaSuccess) { *count = 0; return cuda_fail(err, "cudaGetDeviceCount", __FILE__, __LINE__); }
+    return MDK_OK;
+}
+
+int mdk_device_info(int device, int *sm_arch, int *sm_count, size_t *total_mem) {
+    cudaDeviceProp prop;
+    MDK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (sm_arch) *sm_arch = prop.major * 10 + prop.minor;
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (total_mem) *total_mem = prop.totalGlobalMem;
+    return MDK_OK;
+}
+
+int mdk_host_alloc(size_t bytes, void **out) {
+    MDK_REQUIRE(out, MDK_ERR_ARG, "out is NULL");
+    MDK_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return MDK_OK;
+}
+int mdk_host_free(void *p) {
+    if (p) MDK_CUDA(cudaFreeHost(p));
+    return MDK_OK;
+}
+int mdk_dev_alloc(int device, size_t bytes, void **out) {
+    MDK_REQUIRE(out, MDK_ERR_ARG, "out is NULL");
+    MDK_CUDA(cudaSetDevice(device));
+    MDK_CUDA(cudaMalloc(out, bytes ? bytes : 1));
+    return MDK_OK;
+}
+int mdk_dev_free(int device, void *p) {
+    MDK_CUDA(cudaSetDevice(device));
+    if (p) MDK_CUDA(cudaFree(p));
+    return MDK_OK;
+}
+int mdk_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes) {
+    MDK_CUDA(cudaSetDevice(device));
+    MDK_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+    return MDK_OK;
+}
+int mdk_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes) {
+    MDK_CUDA(cudaSetDevice(device));
+    MDK_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+    return MDK_OK;
+}
+int mdk_dev_memset(int device, void *dst_dev, int value, size_t bytes) {
+    MDK_CUDA(cudaSetDevice(device));
+    MDK_CUDA(cudaMemset(dst_dev, value, bytes));
+    return MDK_OK;
+}
+int mdk_device_synchronize(int device) {
+    MDK_CUDA(cudaSetDevice(device));
+    MDK_CUDA(cudaDeviceSynchronize());
+    return MDK_OK;
+}
+
+int mdk_engine_create(int device, const mdk_model_desc *desc, mdk_engine **out) {
+    MDK_REQUIRE(desc && out, MDK_ERR_ARG, "engine_create: NULL argument");
+    MDK_REQUIRE(desc->gru_size == H, MDK_ERR_UNSUPPORTED, "engine_create: only gru_size == 128 is supported");
+    MDK_REQUIRE(desc->n_layers == 2 && desc->bidirectional == 1, MDK_ERR_UNSUPPORTED,
+                "engine_create: only the 2-layer bidirectional GRU is supported");
+    MDK_REQUIRE(desc->num_features >= 1 && desc->num_features <= 1024, MDK_ERR_ARG, "engine_create: bad num_features");
+    int ndev = 0;
+    MDK_CUDA(cudaGetDeviceCount(&ndev));
+    MDK_REQUIRE(device >= 0 && device < ndev, MDK_ERR_ARG, "engine_create: no such CUDA device");
+    cudaDeviceProp prop;
+    MDK_CUDA(cudaGetDeviceProperties(&prop, device));
+    MDK_REQUIRE(prop.major == 10, MDK_ERR_UNSUPPORTED,
+                "engine_create: this library is built for sm_100a (Blackwell B200) only");
+    MDK_CUDA(cudaSetDevice(device));
+    mdk_engine *e = new (std::nothrow) mdk_engine();
+    MDK_REQUIRE(e, MDK_ERR_NOMEM, "engine_create: out of host memory");
+    e->device = device;
+    e->desc = *desc;
+    e->sm_count = prop.multiProcessorCount;
+    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
+    for (auto &set : e->evr) for (auto &ev : set) cudaEventCreate(&ev);
+    for (auto &ev : e->ev_timer) cudaEventCreate(&ev);
+    *out = e;
+    return MDK_OK;
+}
+
+int mdk_engine_destroy(mdk_engine *e) {
+    if (!e) return MDK_OK;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (int l = 0; l < 2; ++l) {
+        LayerWeights &lw = e->layer[l];
+        for (int d = 0; d < NDIR; ++d) { dev_free(lw.w_ih[d]); dev_free(lw.w_hh[d]); dev_free(lw.b_ih[d]); dev_free(lw.b_hh[d]); }
+        dev_free(lw.w_in_packed); dev_free(lw.bias_gi); dev_free(lw.b_hn); dev_free(lw.w_hh_t);
+        dev_free(lw.w_hh_tc); dev_free(lw.w_in_tc);
+    }
+    dev_free(e->lin_w); dev_free(e->lin_b);
+    dev_free(e->gi); dev_free(e->h1);
+    if (e->h0) cudaFree(e->h0);
+    dev_free(e->d_feats); dev_free(e->d_probs); dev_free(e->d_logits); dev_free(e->d_labels);
+    for (auto &set : e->evr) for (auto &ev : set) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->ev_timer) if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(e->stream);
+    delete e;
+    cudaGetLastError();
+    return MDK_OK;
+}
+
+int mdk_engine_load_gru(mdk_engine *e, int layer, int direction, const float *w_ih, const float *w_hh,
+                        const float *b_ih, const float *b_hh) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
+    MDK_REQUIRE(layer >= 0 && layer < 2 && direction >= 0 && direction < 2, MDK_ERR_ARG, "load_gru: bad layer/direction");
+    MDK_REQUIRE(w_ih && w_hh && b_ih && b_hh, MDK_ERR_ARG, "load_gru: NULL weight pointer");
+    MDK_CUDA(cudaSetDevice(e->device));
+    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    LayerWeights &lw = e->layer[layer];
+    const int in = in_features(e, layer);
+    int rc;
+    if ((rc = upload(&lw.w_ih[direction], w_ih, (size_t)G3 * in))) return rc;
+    if ((rc = upload(&lw.w_hh[direction], w_hh, (size_t)G3 * H))) return rc;
+    if ((rc = upload(&lw.b_ih[direction], b_ih, (size_t)G3))) return rc;
+    if ((rc = upload(&lw.b_hh[direction], b_hh, (size_t)G3))) return rc;
+    lw.loaded[direction] = true;
+    e->prepared = false;
+    return MDK_OK;
+}
+
+int mdk_engine_load_linear(mdk_engine *e, const float *w, const float *b) {
+    MDK_REQUIRE(e && w && b, MDK_ERR_ARG, "load_linear: NULL argument");
+    MDK_CUDA(cudaSetDevice(e->device));
+    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    int rc;
+    if ((rc = upload(&e->lin_w, w, (size_t)NCLS * H2))) return rc;
+    if ((rc = upload(&e->lin_b, b, (size_t)NCLS))) return rc;
+    e->lin_loaded = true;
+    return MDK_OK;
+}
+
+int mdk_engine_set_precision(mdk_engine *e, int mode) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
+    MDK_REQUIRE(mode == MDK_PREC_TC || mode == MDK_PREC_FP32, MDK_ERR_ARG, "set_precision: unknown mode");
+    e->precision = mode;
+    return MDK_OK;
+}
+int mdk_engine_get_precision(mdk_engine *e, int *mode) {
+    MDK_REQUIRE(e && mode, MDK_ERR_ARG, "NULL argument");
+    *mode = e->precision;
+    return MDK_OK;
+}
+
+int mdk_engine_reserve(mdk_engine *e, int64_t B, int64_t T) {
+    MDK_REQUIRE(e && B >= 1 && T >= 1, MDK_ERR_ARG, "reserve: bad arguments");
+    MDK_CUDA(cudaSetDevice(e->device));
+    int rc;
+    if ((rc = ensure_workspace(e, B, T))) return rc;
+    return ensure_io(e, B, T);
+}
+
+int mdk_engine_forward_dev(mdk_engine *e, const float *feats_dev, int64_t B, int64_t T, float *probs_dev,
+                           float *logits_dev, uint8_t *labels_dev) {
+    int rc;
+    if ((rc = check_shapes(e, feats_dev, B, T, probs_dev))) return rc;
+    MDK_CUDA(cudaSetDevice(e->device));
+    e->ev = e->evr[e->fwd_count % mdk_engine::EV_RING];
+    e->fwd_count++;
+    MDK_CUDA(cudaEventRecord(e->ev[0], e->stream));
+    if ((rc = run_forward(e, feats_dev, B, T, probs_dev, logits_dev, labels_dev))) return rc;
+    MDK_CUDA(cudaEventRecord(e->ev[7], e->stream));
+    return MDK_OK;
+}
+
+int mdk_engine_forward(mdk_engine *e, const float *feats_host, int64_t B, int64_t T, float *probs_host,
+                       float *logits_host, uint8_t *labels_host) {
+    int rc;
+    if ((rc = check_shapes(e, feats_host, B, T, probs_host))) return rc;
+    MDK_CUDA(cudaSetDevice(e->device));
+    if ((rc = ensure_io(e, B, T))) return rc;
+    const int64_t P = B * T;
+    cudaStream_t s = e->stream;
+    e->ev = e->evr[e->fwd_count % mdk_engine::EV_RING];
+    e->fwd_count++;
+    MDK_CUDA(cudaEventRecord(e->ev[0], s));
+    MDK_CUDA(cudaMemcpyAsync(e->d_feats, feats_host, (size_t)P * e->desc.num_features * sizeof(float),
+                             cudaMemcpyHostToDevice, s));
+    if ((rc = run_forward(e, e->d_feats, B, T, e->d_probs, logits_host ? e->d_logits : nullptr,
+                          labels_host ? e->d_labels : nullptr)))
+        return rc;
+    MDK_CUDA(cudaMemcpyAsync(probs_host, e->d_probs, (size_t)P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (logits_host)
+        MDK_CUDA(cudaMemcpyAsync(logits_host, e->d_logits, (size_t)P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (labels_host) MDK_CUDA(cudaMemcpyAsync(labels_host, e->d_labels, (size_t)P, cudaMemcpyDeviceToHost, s));
+    MDK_CUDA(cudaEventRecord(e->ev[7], s));
+    MDK_CUDA(cudaStreamSynchronize(s));
+    return MDK_OK;
+}
+
+int mdk_engine_sync(mdk_engine *e) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
+    MDK_CUDA(cudaSetDevice(e->device));
+    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    return MDK_OK;
+}
+
+static void stage_times(cudaEvent_t *ev, mdk_timings *t) {
+    t->h2d_ms = ev_ms(ev[0], ev[1]);
+    t->inproj0_ms = ev_ms(ev[1], ev[2]);
+    t->rec0_ms = ev_ms(ev[2], ev[3]);
+    t->inproj1_ms = ev_ms(ev[3], ev[4]);
+    t->rec1_ms = ev_ms(ev[4], ev[5]);
+    t->head_ms = ev_ms(ev[5], ev[6]);
+    t->d2h_ms = ev_ms(ev[6], ev[7]);
+    t->total_ms = ev_ms(ev[0], ev[7]);
+}
+
+int mdk_engine_last_timings(mdk_engine *e, mdk_timings *out) { return mdk_engine_mean_timings(e, 1, out); }
+
+int mdk_engine_mean_timings(mdk_engine *e, int n_last, mdk_timings *out) {
+    MDK_REQUIRE(e && out, MDK_ERR_ARG, "NULL argument");
+    MDK_REQUIRE(n_last >= 1 && n_last <= mdk_engine::EV_RING, MDK_ERR_ARG, "mean_timings: n_last out of range");
+    MDK_REQUIRE(e->fwd_count >= n_last, MDK_ERR_STATE, "mean_timings: fewer forwards recorded than requested");
+    MDK_CUDA(cudaSetDevice(e->device));
+    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    mdk_timings acc{};
+    for (int i = 0; i < n_last; ++i) {
+        mdk_timings t{};
+        stage_times(e->evr[(e->fwd_count - 1 - i) % mdk_engine::EV_RING], &t);
+        acc.h2d_ms += t.h2d_ms; acc.inproj0_ms += t.inproj0_ms; acc.rec0_ms += t.rec0_ms;
+        acc.inproj1_ms += t.inproj1_ms; acc.rec1_ms += t.rec1_ms; acc.head_ms += t.head_ms;
+        acc.d2h_ms += t.d2h_ms; acc.total_ms += t.total_ms;
+    }
+    const float inv = 1.0f / (float)n_last;
+    acc.h2d_ms *= inv; acc.inproj0_ms *= inv; acc.rec0_ms *= inv; acc.inproj1_ms *= inv; acc.rec1_ms *= inv;
+    acc.head_ms *= inv; acc.d2h_ms *= inv; acc.total_ms *= inv;
+    acc.launches = e->last.launches;
+    *out = acc;
+    return MDK_OK;
+}
+
+int mdk_engine_timer_start(mdk_engine *e) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
+    MDK_CUDA(cudaSetDevice(e->device));
+    MDK_CUDA(cudaEventRecord(e->ev_timer[0], e->stream));
+    return MDK_OK;
+}
+int mdk_engine_timer_stop(mdk_engine *e, float *elapsed_ms) {
+    MDK_REQUIRE(e && elapsed_ms, MDK_ERR_ARG, "NULL argument");
+    MDK_CUDA(cudaSetDevice(e->device));
+    MDK_CUDA(cudaEventRecord(e->ev_timer[1], e->stream));
+    MDK_CUDA(cudaEventSynchronize(e->ev_timer[1]));
+    MDK_CUDA(cudaEventElapsedTime(elapsed_ms, e->ev_timer[0], e->ev_timer[1]));
+    return MDK_OK;
+}
+
+int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_t n_floats) {
+    MDK_REQUIRE(e && out_host, MDK_ERR_ARG, "NULL argument");
+    MDK_REQUIRE(which == 0 || which == 1, MDK_ERR_ARG, "read_activation: which must be 0 or 1");
+    const int64_t P = e->last_B * e->last_T;
+    MDK_REQUIRE(P > 0 && n_floats == P * H2, MDK_ERR_ARG, "read_activation: size must be B*T*256 of the last forward");
+    MDK_CUDA(cudaSetDevice(e->device));
+    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    if (which == 1) {
+        MDK_CUDA(cudaMemcpy(out_host, e->h1, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    } else if (e->last_precision == MDK_PREC_FP32) {
+        MDK_CUDA(cudaMemcpy(out_host, e->h0, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    } else {
+        float *tmp = nullptr;
+        MDK_CUDA(cudaMalloc(&tmp, (size_t)n_floats * sizeof(float)));
+        cudaError_t err = launch_unpack_h0(e->h0, tmp, P, e->stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        if (err == cudaSuccess) err = cudaMemcpy(out_host, tmp, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        e->launches++;
+        if (err != cudaSuccess) return cuda_fail(err, "unpack_h0", __FILE__, __LINE__);
+    }
+    return MDK_OK;
+}
+
+int64_t mdk_engine_launch_count(mdk_engine *e) { return e ? e->launches : 0; }
+
+// ---------------------------------------------------------------------------- featuriser seam
+int mdk_normalise_counts_dev(int device, const uint64_t *counts_dev, const int64_t *major_dev,
+                             const int64_t *minor_dev, int64_t n, int32_t num_dtypes, int32_t mode,
+                             int32_t sym_indels, float *feats_out_dev, int64_t *depth_out_dev) {
+    MDK_REQUIRE(n >= 0, MDK_ERR_ARG, "normalise_counts: n < 0");
+    MDK_REQUIRE(num_dtypes >= 1 && num_dtypes <= 4, MDK_ERR_UNSUPPORTED, "normalise_counts: 1..4 dtypes supported");
+    MDK_REQUIRE(mode >= MDK_NORM_TOTAL && mode <= MDK_NORM_NONE, MDK_ERR_ARG, "normalise_counts: unknown mode");
+    if (n == 0) return MDK_OK;
+    MDK_REQUIRE(counts_dev && major_dev && minor_dev && feats_out_dev, MDK_ERR_ARG, "normalise_counts: NULL pointer");
+    MDK_CUDA(cudaSetDevice(device));
+    MDK_CUDA(launch_normalise(counts_dev, major_dev, minor_dev, n, num_dtypes, mode, sym_indels, feats_out_dev,
+                              depth_out_dev, 0));
+    return MDK_OK;
+}
+
+int mdk_normalise_counts(int device, const uint64_t *counts, const int64_t *major, const int64_t *minor, int64_t n,
+                         int32_t num_dtypes, int32_t mode, int32_t sym_indels, float *feats_out,
+                         int64_t *depth_out) {
+    MDK_REQUIRE(n >= 0, MDK_ERR_ARG, "normalise_counts: n < 0");
+    MDK_REQUIRE(num_dtypes >= 1 && num_dtypes <= 4, MDK_ERR_UNSUPPORTED, "normalise_counts: 1..4 dtypes supported");
+    if (n == 0) return MDK_OK;
+    MDK_REQUIRE(counts && major && minor && feats_out, MDK_ERR_ARG, "normalise_counts: NULL pointer");
+    MDK_CUDA(cudaSetDevice(device));
+    const size_t F = 10 * (size_t)num_dtypes;
+    uint8_t *buf = nullptr;
+    const size_t b_counts = (size_t)n * F * 8, b_pos = (size_t)n * 8, b_feats = (size_t)n * F * 4;
+    MDK_CUDA(cudaMalloc(&buf, b_counts + 3 * b_pos + b_feats));
+    uint64_t *d_counts = reinterpret_cast<uint64_t *>(buf);
+    int64_t *d_major = reinterpret_cast<int64_t *>(buf + b_counts);
+    int64_t *d_minor = d_major + n;
+    int64_t *d_depth = d_minor + n;
+    float *d_feats = reinterpret_cast<float *>(buf + b_counts + 3 * b_pos);
+    cudaError_t err = cudaMemcpy(d_counts, counts, b_counts, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(d_major, major, b_pos, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(d_minor, minor, b_pos, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = launch_normalise(d_counts, d_major, d_minor, n, num_dtypes, mode, sym_indels, d_feats, d_depth, 0);
+    if (err == cudaSuccess) err = cudaMemcpy(feats_out, d_feats, b_feats, cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess && depth_out) err = cudaMemcpy(depth_out, d_depth, b_pos, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    if (err != cudaSuccess) return cuda_fail(err, "normalise_counts", __FILE__, __LINE__);
+    return MDK_OK;
+}
+
+// ---------------------------------------------------------------------------- decode seam
+int mdk_decode_consensus_dev(int device, const float *probs_dev, int64_t n, uint8_t *labels_out_dev,
+                             uint8_t *quals_out_dev) {
+    MDK_REQUIRE(n >= 0, MDK_ERR_ARG, "decode_consensus: n < 0");
+    if (n == 0) return MDK_OK;
+    MDK_REQUIRE(probs_dev && labels_out_dev, MDK_ERR_ARG, "decode_consensus: NULL pointer");
+    MDK_CUDA(cudaSetDevice(device));
+    MDK_CUDA(launch_decode(probs_dev, n, labels_out_dev, quals_out_dev, 0));
+    return MDK_OK;
+}
+
+int mdk_decode_consensus(int device, const float *probs, int64_t n, uint8_t *labels_out, uint8_t *quals_out) {
+    MDK_REQUIRE(n >= 0, MDK_ERR_ARG, "decode_consensus: n < 0");
+    if (n == 0) return MDK_OK;
+    MDK_REQUIRE(probs && labels_out, MDK_ERR_ARG, "decode_consensus: NULL pointer");
+    MDK_CUDA(cudaSetDevice(device));
+    uint8_t *buf = nullptr;
+    const size_t b_probs = (size_t)n * NCLS * 4;
+    MDK_CUDA(cudaMalloc(&buf, b_probs + 2 * (size_t)n));
+    float *d_probs = reinterpret_cast<float *>(buf);
+    uint8_t *d_labels = buf + b_probs, *d_quals = d_labels + n;
+    cudaError_t err = cudaMemcpy(d_probs, probs, b_probs, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = launch_decode(d_probs, n, d_labels, quals_out ? d_quals : nullptr, 0);
+    if (err == cudaSuccess) err = cudaMemcpy(labels_out, d_labels, (size_t)n, cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess && quals_out) err = cudaMemcpy(quals_out, d_quals, (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    if (err != cudaSuccess) return cuda_fail(err, "decode_consensus", __FILE__, __LINE__);
+    return MDK_OK;
+}
+
+int mdk_selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant) {
+    MDK_REQUIRE(A && B && D, MDK_ERR_ARG, "selftest_umma: NULL pointer");
+    return selftest_umma(device, A, B, D, N, K, variant);
+}
+
+}  // extern "C"

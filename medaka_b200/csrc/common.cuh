@@ -1,0 +1,120 @@
+// Shared declarations of libmedaka_b200: engine state, error plumbing, kernel launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/medaka_b200.h"
+
+namespace mdk {
+
+constexpr int H = 128;        // gru_size of every shipped counts-matrix model (gru.py:18)
+constexpr int G3 = 3 * H;     // gate rows per direction (r,z,n)
+constexpr int NDIR = 2;
+constexpr int GI_COLS = NDIR * G3;  // 768: input-projection row [fwd r z n | rev r z n]
+constexpr int H2 = NDIR * H;        // 256: layer output width
+constexpr int NCLS = 5;             // gru.py:53-55
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t err, const char *what, const char *file, int line);
+
+#define MDK_CUDA(call)                                                        \
+    do {                                                                      \
+        cudaError_t _e = (call);                                              \
+        if (_e != cudaSuccess) return ::mdk::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define MDK_REQUIRE(cond, code, msg)  \
+    do {                              \
+        if (!(cond)) {                \
+            ::mdk::set_error(msg);    \
+            return (code);            \
+        }                             \
+    } while (0)
+
+// Geometry of the fp16 hi/lo operand tiles the tcgen05 kernels consume (K-major, no swizzle:
+// [k-group][row][8 halfs]; see ptx.cuh make_smem_desc).
+constexpr int XT_ROWS = 128;                       // positions per activation tile
+constexpr int XT_K = H2;                           // 256
+constexpr int XT_PLANE_BYTES = XT_ROWS * XT_K * 2; // one plane (hi or lo) of a tile: 64 KiB
+constexpr int XT_TILE_BYTES = 2 * XT_PLANE_BYTES;  // hi plane then lo plane
+
+struct LayerWeights {
+    // fp32 originals (device), torch layout
+    float *w_ih[NDIR] = {nullptr, nullptr};  // [3H][in]
+    float *w_hh[NDIR] = {nullptr, nullptr};  // [3H][H]
+    float *b_ih[NDIR] = {nullptr, nullptr};
+    float *b_hh[NDIR] = {nullptr, nullptr};
+    bool loaded[NDIR] = {false, false};
+    // derived (built by prepare_weights)
+    float *w_in_packed = nullptr;   // [768][in] fp32: rows = dir*384 + gate*128 + j
+    float *bias_gi = nullptr;       // [768]: r,z: b_ih+b_hh ; n: b_ih
+    float *b_hn = nullptr;          // [2][128]
+    float *w_hh_t = nullptr;        // [2][128(k)][384] fp32 (transposed) for the FFMA path
+    __half *w_hh_tc = nullptr;      // [2][hi/lo][gate][kgroup16][row128][8] fp16 for rec_tc
+    __half *w_in_tc = nullptr;      // layer 1 only: [6 blocks][hi/lo][kgroup32][row128][8] fp16
+};
+
+}  // namespace mdk
+
+struct mdk_engine {
+    int device = 0;
+    mdk_model_desc desc{};
+    int precision = MDK_PREC_TC;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    static constexpr int EV_RING = 32;   // per-forward event sets kept for mdk_engine_mean_timings
+    cudaEvent_t evr[EV_RING][8] = {};
+    cudaEvent_t *ev = evr[0];            // event set of the forward in flight
+    int64_t fwd_count = 0;
+    cudaEvent_t ev_timer[2] = {};
+    mdk::LayerWeights layer[2];
+    float *lin_w = nullptr, *lin_b = nullptr;
+    bool lin_loaded = false;
+    bool prepared = false;
+    // workspace
+    int64_t cap_pos = 0;       // capacity in positions (B*T, rounded up to XT_ROWS)
+    float *gi = nullptr;       // [cap_pos][768]
+    void *h0 = nullptr;        // fp32 [cap_pos][256]  or  fp16 hi/lo tiles (same byte size)
+    float *h1 = nullptr;       // [cap_pos][256]
+    // staging for the host-buffer API
+    int64_t cap_io = 0;
+    float *d_feats = nullptr, *d_probs = nullptr, *d_logits = nullptr;
+    uint8_t *d_labels = nullptr;
+    int64_t cap_feats_floats = 0;
+    mdk_timings last{};
+    int64_t launches = 0;
+    int64_t last_B = 0, last_T = 0;
+    int last_precision = -1;
+};
+
+namespace mdk {
+
+// ---- launchers (each returns cudaGetLastError() of its launch) -------------------------------
+// misc.cu
+cudaError_t launch_inproj0(const float *feats, const float *w_packed, const float *bias, float *gi,
+                           int64_t P, int F, cudaStream_t s);
+cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b, int64_t P, float *probs,
+                        float *logits, uint8_t *labels, cudaStream_t s);
+cudaError_t launch_normalise(const uint64_t *counts, const int64_t *major, const int64_t *minor, int64_t n,
+                             int num_dtypes, int mode, int sym_indels, float *feats, int64_t *depth,
+                             cudaStream_t s);
+cudaError_t launch_decode(const float *probs, int64_t n, uint8_t *labels, uint8_t *quals, cudaStream_t s);
+cudaError_t launch_prepare_layer(const LayerWeights &lw, int in_features, bool build_in_tc, cudaStream_t s);
+cudaError_t launch_unpack_h0(const void *h0_tiles, float *out, int64_t P, cudaStream_t s);
+// gru_fp32.cu
+cudaError_t launch_rec_fp32(const float *gi, const float *w_hh_t, const float *b_hn, float *h_out, int64_t B,
+                            int64_t T, cudaStream_t s);
+cudaError_t launch_gemm_fp32(const float *A, const float *W, const float *bias, float *C, int64_t P,
+                             cudaStream_t s);
+// gru_tc.cu
+cudaError_t launch_rec_tc(const float *gi, const __half *w_hh_tc, const float *b_hn, void *h_out, int out_tiles,
+                          int64_t B, int64_t T, int sm_count, cudaStream_t s);
+cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tc, const float *bias, float *gi, int64_t P,
+                           int sm_count, cudaStream_t s);
+int selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant);
+
+}  // namespace mdk

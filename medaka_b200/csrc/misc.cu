@@ -1,0 +1,405 @@
+// HBM-bound kernels of the hot path: count normalisation, layer-0 input projection,
+// linear head + softmax + argmax, consensus decode (argmax + phred), weight packing.
+// All are coalesced / vectorised streaming kernels; none is GEMM-shaped.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mdk {
+
+// =====================================================================================
+// Count normalisation  (CountsFeatureEncoder._post_process_pileup, medaka/features.py:871-935)
+// One thread per pileup column.  Algorithmic bytes per column (F=10): read 80 (counts) + 16
+// (major, minor), write 40 (features) + 8 (depth) = 144 B.
+// =====================================================================================
+// index helpers for the per-(dtype, strand) groups of medaka/features.py:647-687:
+// feature order per dtype is 'acgtACGTdD' (src/medaka_counts.h:19): reverse = {0,1,2,3,8}, forward = {4,5,6,7,9}
+__device__ __forceinline__ bool feat_is_rev(int f10) { return f10 < 4 || f10 == 8; }
+
+__device__ __forceinline__ int64_t lower_bound_major(const int64_t *__restrict__ major, int64_t n, int64_t key) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (major[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int ND>
+__global__ void __launch_bounds__(256) normalise_kernel(const uint64_t *__restrict__ counts,
+                                                        const int64_t *__restrict__ major,
+                                                        const int64_t *__restrict__ minor, int64_t n, int mode,
+                                                        int sym_indels, float *__restrict__ feats,
+                                                        int64_t *__restrict__ depth_out) {
+    constexpr int F = 10 * ND;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t c[F];
+    {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(counts + i * F);
+#pragma unroll
+        for (int q = 0; q < F / 2; ++q) {
+            ulonglong2 v = src[q];
+            c[2 * q] = v.x;
+            c[2 * q + 1] = v.y;
+        }
+    }
+    const int64_t mn = minor[i];
+    // group sums of this column: gs[dt][0] = reverse strand, gs[dt][1] = forward strand
+    uint64_t gs_i[ND][2];
+#pragma unroll
+    for (int dt = 0; dt < ND; ++dt) {
+        gs_i[dt][0] = c[dt * 10 + 0] + c[dt * 10 + 1] + c[dt * 10 + 2] + c[dt * 10 + 3] + c[dt * 10 + 8];
+        gs_i[dt][1] = c[dt * 10 + 4] + c[dt * 10 + 5] + c[dt * 10 + 6] + c[dt * 10 + 7] + c[dt * 10 + 9];
+    }
+    uint64_t gs_p[ND][2];      // group sums of the parent (major) column, ORIGINAL counts
+    uint64_t del_p[ND][2];     // parent's original deletion counts (needed only if the parent is a minor column)
+    int64_t parent_minor = 0;
+    if (mn > 0) {
+        // np.searchsorted(positions['major'], major, side='left'): first column with this major
+        const int64_t j = lower_bound_major(major, n, major[i]);
+        parent_minor = minor[j];
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(counts + j * F);
+        uint64_t p[F];
+#pragma unroll
+        for (int q = 0; q < F / 2; ++q) {
+            ulonglong2 v = src[q];
+            p[2 * q] = v.x;
+            p[2 * q + 1] = v.y;
+        }
+#pragma unroll
+        for (int dt = 0; dt < ND; ++dt) {
+            gs_p[dt][0] = p[dt * 10 + 0] + p[dt * 10 + 1] + p[dt * 10 + 2] + p[dt * 10 + 3] + p[dt * 10 + 8];
+            gs_p[dt][1] = p[dt * 10 + 4] + p[dt * 10 + 5] + p[dt * 10 + 6] + p[dt * 10 + 7] + p[dt * 10 + 9];
+            del_p[dt][0] = p[dt * 10 + 8];
+            del_p[dt][1] = p[dt * 10 + 9];
+        }
+    } else {
+#pragma unroll
+        for (int dt = 0; dt < ND; ++dt) {
+            gs_p[dt][0] = gs_i[dt][0];
+            gs_p[dt][1] = gs_i[dt][1];
+            del_p[dt][0] = c[dt * 10 + 8];
+            del_p[dt][1] = c[dt * 10 + 9];
+        }
+    }
+    // depth = row sum of the parent column's original counts (features.py:889-890)
+    uint64_t depth = 0;
+#pragma unroll
+    for (int dt = 0; dt < ND; ++dt) depth += gs_p[dt][0] + gs_p[dt][1];
+    if (depth_out) depth_out[i] = (int64_t)depth;
+
+    if (sym_indels && mn > 0) {
+        // features.py:892-908: reads spanning the insertion site without the insertion count as deletions
+#pragma unroll
+        for (int dt = 0; dt < ND; ++dt) {
+            c[dt * 10 + 8] = gs_p[dt][0] - gs_i[dt][0];   // uint64 wrap-around like numpy
+            c[dt * 10 + 9] = gs_p[dt][1] - gs_i[dt][1];
+        }
+    }
+    float out[F];
+    if (mode == MDK_NORM_TOTAL) {
+        const double d = (double)(depth > 1 ? depth : 1);
+#pragma unroll
+        for (int f = 0; f < F; ++f) out[f] = __double2float_rn((double)c[f] / d);   // f64 divide then cast (features.py:914,926)
+    } else if (mode == MDK_NORM_FWD_REV) {
+        // features.py:915-923: per (dtype, strand) depth, recomputed from the (possibly sym_indels-modified)
+        // counts; minor columns take their parent's group depth.
+#pragma unroll
+        for (int dt = 0; dt < ND; ++dt) {
+#pragma unroll
+            for (int st = 0; st < 2; ++st) {
+                uint64_t g;
+                if (mn > 0) {
+                    g = gs_p[dt][st];
+                    // parent itself a minor column (chunk cut inside an insertion run): its own deletion
+                    // slot was overwritten by the sym_indels fill (with gs_p - gs_p = 0)
+                    if (sym_indels && parent_minor > 0) g -= del_p[dt][st];
+                } else {
+                    g = gs_i[dt][st];
+                }
+                const double d = (double)(g > 1 ? g : 1);
+#pragma unroll
+                for (int b = 0; b < 10; ++b) {
+                    if (feat_is_rev(b) == (st == 0)) out[dt * 10 + b] = __double2float_rn((double)c[dt * 10 + b] / d);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int f = 0; f < F; ++f) out[f] = (float)c[f];
+    }
+    float2 *dst = reinterpret_cast<float2 *>(feats + i * F);
+#pragma unroll
+    for (int q = 0; q < F / 2; ++q) dst[q] = make_float2(out[2 * q], out[2 * q + 1]);
+}
+
+cudaError_t launch_normalise(const uint64_t *counts, const int64_t *major, const int64_t *minor, int64_t n,
+                             int num_dtypes, int mode, int sym_indels, float *feats, int64_t *depth,
+                             cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    switch (num_dtypes) {
+        case 1: normalise_kernel<1><<<blocks, threads, 0, s>>>(counts, major, minor, n, mode, sym_indels, feats, depth); break;
+        case 2: normalise_kernel<2><<<blocks, threads, 0, s>>>(counts, major, minor, n, mode, sym_indels, feats, depth); break;
+        case 3: normalise_kernel<3><<<blocks, threads, 0, s>>>(counts, major, minor, n, mode, sym_indels, feats, depth); break;
+        case 4: normalise_kernel<4><<<blocks, threads, 0, s>>>(counts, major, minor, n, mode, sym_indels, feats, depth); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Consensus decode (labels.py:1053-1085, _phred :387-401).  41 B per position.
+// =====================================================================================
+__global__ void __launch_bounds__(256) decode_kernel(const float *__restrict__ probs, int64_t n,
+                                                     uint8_t *__restrict__ labels, uint8_t *__restrict__ quals) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = probs + i * NCLS;
+    float best = p[0];
+    int arg = 0;
+#pragma unroll
+    for (int c = 1; c < NCLS; ++c) {
+        const float v = p[c];
+        if (v > best) { best = v; arg = c; }   // strict '>' : first maximum wins, as np.argmax
+    }
+    labels[i] = (uint8_t)arg;
+    if (quals) {
+        float err = 1.0f - best;                              // float32 arithmetic, like numpy on f32 probs
+        err = fminf(fmaxf(err, 1e-7f), 1.0f);                 // np.clip(err, 10**-7, 1)
+        const float l = __double2float_rn(log10((double)err));  // correctly rounded float32 log10
+        float q = -10.0f * l;
+        q = fminf(q, 70.0f);
+        quals[i] = (uint8_t)((int)q + 33);                    // astype('u1') truncation, +33
+    }
+}
+
+cudaError_t launch_decode(const float *probs, int64_t n, uint8_t *labels, uint8_t *quals, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(probs, n, labels, quals);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Layer-0 input projection: gi[p][c] = sum_f x[p][f] * W[c][f] + bias[c],  c in [0,768)
+// K = F (10 or 20) is far too thin for the tensor cores; the kernel is bound by the 3 KiB/position
+// write of gi.  256 threads, each owns 3 of the 768 columns with its weights in registers.
+// =====================================================================================
+template <int F>
+__global__ void __launch_bounds__(256) inproj0_kernel(const float *__restrict__ feats, const float *__restrict__ w,
+                                                      const float *__restrict__ bias, float *__restrict__ gi,
+                                                      int64_t P) {
+    constexpr int PT = 64;   // positions per block
+    __shared__ float xs[PT * F];
+    const int tid = threadIdx.x;
+    const int64_t p0 = (int64_t)blockIdx.x * PT;
+    const int np = (int)min((int64_t)PT, P - p0);
+    for (int i = tid; i < np * F; i += 256) xs[i] = feats[p0 * F + i];
+    float wr[3][F], b[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int c = tid + 256 * q;
+        b[q] = bias[c];
+#pragma unroll
+        for (int f = 0; f < F; ++f) wr[q][f] = w[c * F + f];
+    }
+    __syncthreads();
+    for (int p = 0; p < np; ++p) {
+        float a0 = b[0], a1 = b[1], a2 = b[2];
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+            const float x = xs[p * F + f];   // smem broadcast
+            a0 = fmaf(x, wr[0][f], a0);
+            a1 = fmaf(x, wr[1][f], a1);
+            a2 = fmaf(x, wr[2][f], a2);
+        }
+        float *row = gi + (p0 + p) * GI_COLS;
+        row[tid] = a0;
+        row[tid + 256] = a1;
+        row[tid + 512] = a2;
+    }
+}
+
+// generic F (weights streamed from L1/L2)
+__global__ void __launch_bounds__(256) inproj0_generic_kernel(const float *__restrict__ feats,
+                                                              const float *__restrict__ w,
+                                                              const float *__restrict__ bias, float *__restrict__ gi,
+                                                              int64_t P, int F) {
+    const int64_t p = blockIdx.x;
+    if (p >= P) return;
+    for (int c = threadIdx.x; c < GI_COLS; c += 256) {
+        float a = bias[c];
+        for (int f = 0; f < F; ++f) a = fmaf(feats[p * F + f], w[c * F + f], a);
+        gi[p * GI_COLS + c] = a;
+    }
+}
+
+cudaError_t launch_inproj0(const float *feats, const float *w_packed, const float *bias, float *gi, int64_t P,
+                           int F, cudaStream_t s) {
+    if (P == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((P + 63) / 64);
+    if (F == 10) inproj0_kernel<10><<<blocks, 256, 0, s>>>(feats, w_packed, bias, gi, P);
+    else if (F == 20) inproj0_kernel<20><<<blocks, 256, 0, s>>>(feats, w_packed, bias, gi, P);
+    else inproj0_generic_kernel<<<(unsigned)P, 256, 0, s>>>(feats, w_packed, bias, gi, P, F);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Head: logits = h1 . W^T + b (gru.py:67), probs = softmax (gru.py:71), label = argmax (labels.py:1063)
+// One warp per position, 8 of the 256 inputs per lane; 1 KiB read + 41 B written per position.
+// =====================================================================================
+__global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1, const float *__restrict__ lin_w,
+                                                   const float *__restrict__ lin_b, int64_t P,
+                                                   float *__restrict__ probs, float *__restrict__ logits,
+                                                   uint8_t *__restrict__ labels) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float w[NCLS][8];
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) {
+        const float4 a = *reinterpret_cast<const float4 *>(lin_w + c * H2 + lane * 8);
+        const float4 b = *reinterpret_cast<const float4 *>(lin_w + c * H2 + lane * 8 + 4);
+        w[c][0] = a.x; w[c][1] = a.y; w[c][2] = a.z; w[c][3] = a.w;
+        w[c][4] = b.x; w[c][5] = b.y; w[c][6] = b.z; w[c][7] = b.w;
+    }
+    float bias[NCLS];
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) bias[c] = lin_b[c];
+    for (int64_t p = warp; p < P; p += nwarps) {
+        const float4 a = *reinterpret_cast<const float4 *>(h1 + p * H2 + lane * 8);
+        const float4 b = *reinterpret_cast<const float4 *>(h1 + p * H2 + lane * 8 + 4);
+        const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float acc[NCLS];
+#pragma unroll
+        for (int c = 0; c < NCLS; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = fmaf(x[i], w[c][i], s);
+            acc[c] = s;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int c = 0; c < NCLS; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+        }
+        float l[NCLS];
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NCLS; ++c) { l[c] = acc[c] + bias[c]; m = fmaxf(m, l[c]); }
+        float e[NCLS], sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCLS; ++c) { e[c] = expf(l[c] - m); sum += e[c]; }
+        float pr[NCLS];
+#pragma unroll
+        for (int c = 0; c < NCLS; ++c) pr[c] = e[c] / sum;
+        if (lane < NCLS) {
+            float lv = l[0], pv = pr[0];
+#pragma unroll
+            for (int c = 1; c < NCLS; ++c) if (lane == c) { lv = l[c]; pv = pr[c]; }
+            probs[p * NCLS + lane] = pv;
+            if (logits) logits[p * NCLS + lane] = lv;
+        }
+        if (labels && lane == 0) {
+            float best = pr[0]; int arg = 0;
+#pragma unroll
+            for (int c = 1; c < NCLS; ++c) if (pr[c] > best) { best = pr[c]; arg = c; }
+            labels[p] = (uint8_t)arg;
+        }
+    }
+}
+
+cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b, int64_t P, float *probs,
+                        float *logits, uint8_t *labels, cudaStream_t s) {
+    if (P == 0) return cudaSuccess;
+    int64_t blocks = (P + 7) / 8;              // 8 warps per block, 1 position per warp per iteration
+    if (blocks > 148 * 8) blocks = 148 * 8;    // persistent-ish grid: multiple of the SM count
+    head_kernel<<<(unsigned)blocks, 256, 0, s>>>(h1, lin_w, lin_b, P, probs, logits, labels);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// Weight packing (runs once per load_state_dict)
+// =====================================================================================
+__global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const float *w_hh0, const float *w_hh1,
+                                  const float *b_ih0, const float *b_ih1, const float *b_hh0, const float *b_hh1,
+                                  int in_features, float *w_in_packed, float *bias_gi, float *b_hn, float *w_hh_t,
+                                  __half *w_hh_tc, __half *w_in_tc) {
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float *w_ih[2] = {w_ih0, w_ih1}, *w_hh[2] = {w_hh0, w_hh1};
+    const float *b_ih[2] = {b_ih0, b_ih1}, *b_hh[2] = {b_hh0, b_hh1};
+    // input weights packed [768][in]
+    for (int64_t i = tid; i < (int64_t)GI_COLS * in_features; i += stride) {
+        const int row = (int)(i / in_features), k = (int)(i % in_features);
+        const int d = row / G3, r = row % G3;
+        w_in_packed[i] = w_ih[d][(int64_t)r * in_features + k];
+    }
+    for (int64_t i = tid; i < GI_COLS; i += stride) {
+        const int d = (int)i / G3, r = (int)i % G3;
+        bias_gi[i] = (r < 2 * H) ? (b_ih[d][r] + b_hh[d][r]) : b_ih[d][r];
+    }
+    for (int64_t i = tid; i < NDIR * H; i += stride) {
+        const int d = (int)i / H, j = (int)i % H;
+        b_hn[i] = b_hh[d][2 * H + j];
+    }
+    // recurrent weights, transposed fp32 [d][k][384] and fp16 hi/lo blocks [d][part][gate][kg][row][8]
+    for (int64_t i = tid; i < (int64_t)NDIR * G3 * H; i += stride) {
+        const int d = (int)(i / (G3 * H));
+        const int rem = (int)(i % (G3 * H));
+        const int c = rem / H, k = rem % H;          // c = gate row, k = input unit
+        const float v = w_hh[d][c * H + k];
+        w_hh_t[((int64_t)d * H + k) * G3 + c] = v;
+        __half hi, lo;
+        split_f16(v, hi, lo);
+        const int g = c / H, j = c % H;
+        const int64_t blk_halfs = (int64_t)H * H;   // 128x128 block
+        const int64_t off = (int64_t)(k / 8) * (H * 8) + j * 8 + (k % 8);
+        w_hh_tc[(((int64_t)d * 2 + 0) * 3 + g) * blk_halfs + off] = hi;
+        w_hh_tc[(((int64_t)d * 2 + 1) * 3 + g) * blk_halfs + off] = lo;
+    }
+    if (w_in_tc) {   // layer 1: [blk = d*3+g][part][kg 32][row 128][8]
+        for (int64_t i = tid; i < (int64_t)GI_COLS * H2; i += stride) {
+            const int row = (int)(i / H2), k = (int)(i % H2);
+            const int d = row / G3, r = row % G3;
+            const float v = w_ih[d][(int64_t)r * H2 + k];
+            __half hi, lo;
+            split_f16(v, hi, lo);
+            const int blk = row / H, j = row % H;
+            const int64_t plane = (int64_t)H * H2;   // 128 x 256 halfs
+            const int64_t off = (int64_t)(k / 8) * (H * 8) + j * 8 + (k % 8);
+            w_in_tc[((int64_t)blk * 2 + 0) * plane + off] = hi;
+            w_in_tc[((int64_t)blk * 2 + 1) * plane + off] = lo;
+        }
+    }
+}
+
+cudaError_t launch_prepare_layer(const LayerWeights &lw, int in_features, bool build_in_tc, cudaStream_t s) {
+    pack_layer_kernel<<<296, 256, 0, s>>>(lw.w_ih[0], lw.w_ih[1], lw.w_hh[0], lw.w_hh[1], lw.b_ih[0], lw.b_ih[1],
+                                          lw.b_hh[0], lw.b_hh[1], in_features, lw.w_in_packed, lw.bias_gi,
+                                          lw.b_hn, lw.w_hh_t, lw.w_hh_tc, build_in_tc ? lw.w_in_tc : nullptr);
+    return cudaGetLastError();
+}
+
+// fp16 hi/lo activation tiles -> fp32 [P][256]  (debug / layer-wise parity only)
+__global__ void unpack_h0_kernel(const __half *__restrict__ tiles, float *__restrict__ out, int64_t P) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= P * H2) return;
+    const int64_t p = i / H2;
+    const int k = (int)(i % H2);
+    const int64_t tile = p / XT_ROWS;
+    const int r = (int)(p % XT_ROWS);
+    const __half *base = tiles + tile * (XT_TILE_BYTES / 2);
+    const int64_t off = (int64_t)(k / 8) * (XT_ROWS * 8) + r * 8 + (k % 8);
+    out[i] = __half2float(base[off]) + __half2float(base[XT_PLANE_BYTES / 2 + off]);
+}
+
+cudaError_t launch_unpack_h0(const void *h0_tiles, float *out, int64_t P, cudaStream_t s) {
+    if (P == 0) return cudaSuccess;
+    const int64_t n = P * H2;
+    unpack_h0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __half *>(h0_tiles), out, P);
+    return cudaGetLastError();
+}
+
+}  // namespace mdk

@@ -1,0 +1,160 @@
+"""Featuriser seam: counts post-processing / normalisation on the GPU, and window generation.
+
+Mirrors the inference half of medaka/features.py: ``pileup_counts_norm_indices`` (:647-687),
+``CountsFeatureEncoder`` (:813-935; ``_post_process_pileup`` is the part that runs on the
+device through mdk_normalise_counts) and ``SampleGenerator`` (:1208-1313).  Raw pileup
+counts come from ``_pileup_function`` - in the reference that is htslib's multi-pileup walked
+by src/medaka_counts.c; here it is pluggable (``pileup_source``) because no BAM decoder is
+part of this engine; the synthetic source used by the benchmark and tests
+produces counts in exactly the layout calculate_pileup returns.
+"""
+import inspect
+from collections import defaultdict
+from timeit import default_timer as now
+
+import numpy as np
+
+from medaka_b200 import common
+from medaka_b200 import libmedaka as _lm
+
+_NORM_MODES = {'total': 0, 'fwd_rev': 1, None: 2}
+
+
+def pileup_counts_norm_indices(dtypes, num_qstrat=1):
+    """Per (datatype, is_rev) column indices of the counts matrix (medaka/features.py:647-687)."""
+    lib = _lm.load()
+    codes = _lm.ffi.string(lib.mdk_plp_bases()).decode()
+    featlen = int(lib.mdk_featlen())
+    assert len(codes) == featlen
+    indices = defaultdict(list)
+    for dti, dt in enumerate(dtypes):
+        for qindex in range(num_qstrat):
+            for base_i, code in enumerate(codes):
+                indices[dt, code.islower()].append(base_i + featlen * (dti * num_qstrat + qindex))
+    return dict(indices)
+
+
+class CountsFeatureEncoder(object):
+    """Create a pileup array of counts of observed bases (medaka/features.py:813-935)."""
+
+    _norm_modes_ = ['total', 'fwd_rev', None]
+    feature_dtype = np.float32
+
+    def __init__(self, normalise='total', dtypes=('',), tag_name=None, tag_value=None,
+                 tag_keep_missing=False, read_group=None, min_mapq=1, sym_indels=False,
+                 pileup_source=None, device=0):
+        self.normalise = normalise
+        self.dtypes = dtypes
+        self.feature_indices = pileup_counts_norm_indices(self.dtypes)
+        self.tag_name = tag_name
+        self.tag_value = tag_value
+        self.tag_keep_missing = tag_keep_missing
+        self.read_group = read_group
+        self.min_mapq = min_mapq
+        self.sym_indels = sym_indels
+        self.pileup_source = pileup_source
+        self.device = device
+        if self.normalise not in self._norm_modes_:
+            raise ValueError('normalise={} is not one of {}'.format(self.normalise, self._norm_modes_))
+        self.logger = common.get_named_logger('Feature')
+
+    def to_dict(self):
+        """Return dictionary of keyword arguments."""
+        opts = inspect.signature(self.__class__.__init__).parameters
+        kwargs = {k: getattr(self, k) for k in opts if k not in ('self', 'pileup_source', 'device')}
+        return {'type': self.__class__.__name__, 'kwargs': kwargs}
+
+    @property
+    def feature_vector_length(self):
+        """Length of a neural network input at a single time point."""
+        return len(self.dtypes) * int(_lm.load().mdk_featlen())
+
+    def _pileup_function(self, region, bam):
+        """Raw counts for a region: list of (counts uint64 [n,F], positions) chunks (features.py:863-869)."""
+        if self.pileup_source is None:
+            raise NotImplementedError(
+                "no pileup source configured: BAM decoding (htslib in the reference) is outside this "
+                "engine; pass pileup_source=callable(region, bam, encoder) -> [(counts, positions), ...]")
+        return self.pileup_source(region, bam, self)
+
+    def _post_process_pileup(self, counts, positions, region):
+        """Normalise counts on the GPU (features.py:871-935) and wrap them in a Sample."""
+        start, end = positions['major'][0], positions['major'][-1]
+        if start != region.start or end + 1 != region.end:
+            self.logger.warning(
+                'Pileup counts do not span requested region, requested {}, '
+                'received {}-{}.'.format(region, start, end))
+        lib, ffi = _lm.load(), _lm.ffi
+        n, F = counts.shape
+        num_dtypes = len(self.dtypes)
+        if F != 10 * num_dtypes:
+            raise ValueError("counts have {} columns, encoder expects {}".format(F, 10 * num_dtypes))
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        major = np.ascontiguousarray(positions['major'], dtype=np.int64)
+        minor = np.ascontiguousarray(positions['minor'], dtype=np.int64)
+        feats = np.empty((n, F), dtype=np.float32)
+        depth = np.empty(n, dtype=np.int64)
+        _lm.check(lib.mdk_normalise_counts(
+            self.device, ffi.cast("const uint64_t *", ffi.from_buffer(counts)),
+            ffi.cast("const int64_t *", ffi.from_buffer(major)),
+            ffi.cast("const int64_t *", ffi.from_buffer(minor)), n, num_dtypes,
+            _NORM_MODES[self.normalise], 1 if self.sym_indels else 0,
+            ffi.cast("float *", ffi.from_buffer(feats)), ffi.cast("int64_t *", ffi.from_buffer(depth))))
+        return common.Sample(
+            ref_name=region.ref_name, features=feats, labels=None, ref_seq=None,
+            positions=positions, label_probs=None, depth=depth)
+
+    def bam_to_sample(self, reads_bam, region):
+        """Convert a section of an alignment pileup to samples (features.py:770-798)."""
+        samples = []
+        for counts, positions in self._pileup_function(region, reads_bam):
+            if len(counts) == 0:
+                self.logger.warning(
+                    'Pileup-feature is zero-length for {} indicating no reads in this region.'.format(region))
+                samples.append(common.Sample(
+                    ref_name=region.ref_name, features=None, labels=None, ref_seq=None,
+                    positions=positions, label_probs=None, depth=None))
+                continue
+            samples.append(self._post_process_pileup(counts, positions, region))
+        return samples
+
+
+class SampleGenerator(object):
+    """Chunked inference samples for one region (medaka/features.py:1208-1313, inference half)."""
+
+    def __init__(self, bam, region, feature_encoder, chunk_len=1000, chunk_overlap=200,
+                 enable_chunking=True):
+        self.logger = common.get_named_logger("Sampler")
+        self.fencoder = feature_encoder
+        self.bam = bam
+        self.region = region
+        self.chunk_len = chunk_len
+        self.chunk_overlap = chunk_overlap
+        self.enable_chunking = enable_chunking
+        self._source = None
+        self._quarantined = list()     # (Region, pileup width) of sources narrower than chunk_len
+
+    def _fill_features(self):
+        if self._source is None:
+            t0 = now()
+            self._source = self.fencoder.bam_to_sample(self.bam, self.region)
+            self.logger.debug("Took {:.2f}s to make features.".format(now() - t0))
+
+    @property
+    def samples(self):
+        """List of (possibly) chunked samples; short sources are quarantined (features.py:1283-1313)."""
+        self._fill_features()
+        self._quarantined = list()
+        out = []
+        for source in self._source:
+            if source.is_empty:
+                continue
+            if not self.enable_chunking:
+                out.append(source)
+                continue
+            if source.size < self.chunk_len:
+                start, end = source.first_pos[0], source.last_pos[0] + 1
+                self._quarantined.append((common.Region(source.ref_name, start, end), source.size))
+                continue
+            out.extend(source.chunks(chunk_len=self.chunk_len, overlap=self.chunk_overlap))
+        return out

@@ -1,0 +1,70 @@
+"""Decode seam: per-position label decode on the GPU.
+
+Mirrors ``HaploidLabelScheme.decode_consensus`` (medaka/labels.py:1053-1085) and ``_phred``
+(:387-401).  The array work - argmax (first maximum wins), probability of the chosen class,
+``uint8(min(70, -10*log10(clip(1-p, 1e-7, 1)))) + 33`` - runs in libmedaka_b200
+(mdk_decode_consensus); gap removal and string building, which are O(n) byte shuffles on
+the result, stay on the host.
+"""
+import numpy as np
+
+from medaka_b200 import libmedaka as _lm
+
+
+def decode_arrays(label_probs, device=0, with_qualities=True):
+    """float32 probabilities [..., 5] -> (labels uint8 [...], quals uint8 [...] or None)."""
+    lib = _lm.load()
+    p = np.ascontiguousarray(label_probs, dtype=np.float32)
+    if p.shape[-1] != 5:
+        raise ValueError("expected label probabilities with 5 classes, got shape {}".format(p.shape))
+    n = int(np.prod(p.shape[:-1]))
+    labels = np.empty(p.shape[:-1], dtype=np.uint8)
+    quals = np.empty(p.shape[:-1], dtype=np.uint8) if with_qualities else None
+    ffi = _lm.ffi
+    _lm.check(lib.mdk_decode_consensus(
+        device, ffi.cast("const float *", ffi.from_buffer(p)), n,
+        ffi.cast("uint8_t *", ffi.from_buffer(labels)),
+        ffi.cast("uint8_t *", ffi.from_buffer(quals)) if with_qualities else ffi.NULL))
+    return labels, quals
+
+
+class HaploidLabelScheme(object):
+    """The decode half of the reference's HaploidLabelScheme (labels.py:703-1085)."""
+
+    symbols = '*ACGT'     # labels.py:342
+    n_elements = 1
+
+    def __init__(self, device=0):
+        self.device = device
+
+    @property
+    def num_classes(self):
+        return len(self.symbols)
+
+    @staticmethod
+    def _phred(err, cap=70.0):
+        """Host restatement kept for API compatibility (labels.py:387-401); not used on the hot path."""
+        err = np.clip(err, 10 ** (-cap / 10.0), 1)
+        return np.minimum(-10 * np.log10(err), cap)
+
+    def decode_consensus(self, sample, with_gaps=False, dtype=None, with_qualities=False):
+        """Convert network output to consensus sequence by argmax decoding.
+
+        :param sample: object with a ``label_probs`` array [n, 5].
+        :param with_gaps: include gap ("*") characters in output.
+        :returns: str, consensus sequence, optionally: qualities
+        """
+        mp, quals = decode_arrays(sample.label_probs, self.device, with_qualities=with_qualities)
+        if not with_gaps:
+            keep = mp != self.symbols.index('*')
+            mp = mp[keep]
+            if with_qualities:
+                quals = quals[keep]
+        if dtype is None:
+            table = np.frombuffer(self.symbols.encode(), dtype=np.uint8)
+            seq = table[mp].tobytes().decode()
+        else:
+            seq = np.fromiter(self.symbols, dtype=dtype)[mp]
+        if with_qualities:
+            return seq, quals.tobytes().decode()
+        return seq

@@ -1,0 +1,59 @@
+"""Batch container for inference: the part of medaka/torch_ext.py the hot path uses (:102-173).
+
+``Batch.collate`` stacks the per-window feature matrices into one float32 [B,T,F] tensor
+(reference: ``torch.stack([...]).float()``, torch_ext.py:155).  Here the stack is written
+straight into page-locked host memory when a pinned staging pool is supplied, so the
+engine's H2D copy is a single asynchronous DMA instead of the reference's pageable
+``.to(device)`` (medaka/models.py:309).
+"""
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+
+@dataclass
+class Batch:
+    """Batch of samples (inference fields only)."""
+
+    read_level_features: torch.Tensor = None
+    counts_matrix: torch.Tensor = None
+    labels: torch.Tensor = None
+    majority_vote_probs: torch.Tensor = None
+
+    @classmethod
+    def collate(cls, samples, counts_matrix=False, out=None):
+        """Construct a batch from a list of `Sample` objects with 2-D (counts-matrix) features.
+
+        :param out: optional float32 array [len(samples), T, F] to fill (e.g. pinned memory).
+        """
+        first = samples[0].features
+        if first.ndim == 3:
+            raise NotImplementedError(
+                "read-level (3-D) features belong to the rl_ models, outside this engine's hot path")
+        if first.ndim != 2:
+            raise ValueError(
+                f"Unknown feature dimension {first.ndim}. Expect 3 for"
+                "read level features or 2 for counts matrices.")
+        shape = (len(samples),) + tuple(first.shape)
+        for s in samples:
+            if tuple(s.features.shape) != tuple(first.shape):
+                raise RuntimeError("stack expects each tensor to be equal size, but got {} and {}".format(
+                    list(first.shape), list(s.features.shape)))
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        elif tuple(out.shape) != shape or out.dtype != np.float32:
+            raise ValueError("out must be float32 of shape {}".format(shape))
+        for i, s in enumerate(samples):
+            out[i] = s.features          # converts to float32 like .float()
+        fields = {"counts_matrix": torch.from_numpy(out)}
+        if samples[0].labels is not None:
+            fields["labels"] = torch.stack([torch.from_numpy(np.asarray(s.labels)) for s in samples])
+        return cls(**fields)
+
+    @property
+    def features(self):
+        """Return the features tensor."""
+        if self.read_level_features is None:
+            return self.counts_matrix
+        return self.read_level_features

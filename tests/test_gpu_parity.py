@@ -1,0 +1,246 @@
+"""GPU parity tests (run with `pytest -m gpu` on a B200): the CUDA path, called through the C ABI
+(medaka_b200.libmedaka -> libmedaka_b200.so), against the CPU oracle and the committed golden
+vectors produced by the real reference classes.
+
+Parity bar (BASELINE.md section 4 / SURVEY.md section 7):
+  * argmax labels identical to the fp32 CPU reference;
+  * logits within 1e-3 "relative fp32", scale-aware:  |d| <= 1e-3 * max_c |logit_c| per position
+    (an element-wise relative test is ill-posed for logits that happen to be ~0; the raw
+    element-wise figure is printed alongside);
+  * integer / byte outputs (labels, qualities, depth) and normalised features bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import features_oracle, gru_oracle, labels_oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def lm():
+    from medaka_b200 import libmedaka
+    libmedaka.load()
+    libmedaka.require_gpu(0)
+    return libmedaka
+
+
+def _scaled_err(got, ref):
+    scale = np.abs(ref).max(axis=-1, keepdims=True)
+    return float((np.abs(got - ref) / scale).max())
+
+
+def _make_model(sd, F=10, precision="tc"):
+    from medaka_b200 import models
+    m = models.GRUModel(num_features=F)
+    m.load_state_dict(sd)
+    m.set_precision(precision)
+    return m
+
+
+# ------------------------------------------------------------------ tcgen05 building block
+@pytest.mark.parametrize("N,K", [(16, 128), (128, 64), (128, 256), (32, 16)])
+def test_umma_tile_selftest(lm, N, K):
+    rs = np.random.RandomState(N * 1000 + K)
+    A = rs.uniform(-1, 1, (128, K)).astype(np.float32)
+    B = rs.uniform(-1, 1, (N, K)).astype(np.float32)
+    D = np.zeros((128, N), dtype=np.float32)
+    ffi = lm.ffi
+    lm.check(lm.lib.mdk_selftest_umma(0, ffi.cast("const float *", ffi.from_buffer(A)),
+                                      ffi.cast("const float *", ffi.from_buffer(B)),
+                                      ffi.cast("float *", ffi.from_buffer(D)), N, K, 0))
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    err = np.abs(D - ref).max()
+    print("umma selftest N=%d K=%d max abs err %.3e" % (N, K, err))
+    assert err < 2e-5 * np.sqrt(K)      # fp16 hi/lo split: ~fp32-level agreement
+
+
+# ------------------------------------------------------------------ forward pass
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+@pytest.mark.parametrize("case", ["small", "long", "hot", "f20", "b1"])
+def test_forward_matches_reference_golden(golden_dir, case, precision):
+    g = np.load(os.path.join(golden_dir, "gru_forward.npz"))
+    seed, B, T, F, head_gain, rec_gain = g[case + "_args"]
+    sd = synth.synth_state_dict(int(seed), num_features=int(F), head_gain=head_gain, rec_gain=rec_gain)
+    feats = synth.synth_features(int(B), int(T), int(F), seed=100 + int(seed))
+    m = _make_model(sd, int(F), precision)
+    out = m.forward_arrays(feats, want_logits=True, want_labels=True)
+    ref_logits, ref_probs = g[case + "_logits"], g[case + "_probs"]
+    err = _scaled_err(out.logits, ref_logits)
+    raw = float((np.abs(out.logits - ref_logits) / np.maximum(np.abs(ref_logits), 1e-30)).max())
+    flips = int((out.labels != np.argmax(ref_probs, -1)).sum())
+    print("%s/%s: scaled logit err %.3e (element-wise rel %.3e), prob err %.3e, label mismatches %d/%d" % (
+        case, precision, err, raw, np.abs(out.probs - ref_probs).max(), flips, out.labels.size))
+    assert err <= LOGIT_TOL
+    assert np.abs(out.probs - ref_probs).max() <= 1e-3
+    assert flips == 0
+    assert np.array_equal(out.labels, np.argmax(out.probs, -1))
+    m.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_layerwise_activations_match_oracle(precision):
+    sd = synth.synth_state_dict(21)
+    feats = synth.synth_features(37, 130, 10, seed=5)     # ragged: 37 windows (partial tiles), T not a multiple of 128
+    man = gru_oracle.manual_forward(sd, feats)
+    m = _make_model(sd, 10, precision)
+    out = m.forward_arrays(feats, want_logits=True)
+    h0 = m.read_activation(0)
+    h1 = m.read_activation(1)
+    e0, e1 = np.abs(h0 - man["h0"]).max(), np.abs(h1 - man["h1"]).max()
+    print("layerwise[%s]: |dh0| %.3e |dh1| %.3e |dlogit| %.3e" % (precision, e0, e1, np.abs(out.logits - man["logits"]).max()))
+    assert e0 < 2e-5 and e1 < 5e-5
+    m.close()
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 17), (16, 2), (17, 129), (33, 64), (200, 40), (300, 33)])
+def test_forward_ragged_shapes(B, T):
+    sd = synth.synth_state_dict(3)
+    feats = synth.synth_features(B, T, 10, seed=B * 7 + T)
+    ref_probs, ref_logits = gru_oracle.predict_on_batch(gru_oracle.build(sd), feats)
+    for precision in ("tc", "fp32"):
+        m = _make_model(sd, 10, precision)
+        out = m.forward_arrays(feats, want_logits=True)
+        assert _scaled_err(out.logits, ref_logits) <= LOGIT_TOL
+        assert int((out.labels != np.argmax(ref_probs, -1)).sum()) == 0
+        m.close()
+
+
+def test_predict_on_batch_interface():
+    """TorchModel.predict_on_batch contract (medaka/models.py:303-313): CPU float32 tensor [B,T,5]."""
+    import torch
+    from medaka_b200 import torch_ext, common
+    sd = synth.synth_state_dict(0)
+    feats = synth.synth_features(4, 50, 10, seed=77)
+    samples = [common.Sample("c", feats[i], None, None, None, None, None) for i in range(4)]
+    batch = torch_ext.Batch.collate(samples)
+    m = _make_model(sd)
+    probs = m.predict_on_batch(batch)
+    assert isinstance(probs, torch.Tensor) and probs.device.type == "cpu" and probs.dtype == torch.float32
+    assert tuple(probs.shape) == (4, 50, 5)
+    ref_probs, _ = gru_oracle.predict_on_batch(gru_oracle.build(sd), feats)
+    assert np.abs(probs.numpy() - ref_probs).max() < 1e-4
+    assert np.array_equal(m.last_labels, np.argmax(ref_probs, -1))
+    m.close()
+
+
+def test_near_tie_labels_follow_own_probs():
+    """First-max tie-breaking: labels are argmax of the returned probabilities (np.argmax semantics)."""
+    sd = synth.synth_state_dict(5, head_gain=0.0)      # zero head -> logits all equal the (zero) bias -> exact ties
+    feats = synth.synth_features(3, 20, 10, seed=1)
+    m = _make_model(sd)
+    out = m.forward_arrays(feats)
+    assert np.all(out.labels == 0)
+    assert np.allclose(out.probs, 0.2)
+    m.close()
+
+
+def test_full_size_window_properties():
+    """BASELINE config-2 window length (T=10000) at a reduced batch: size-independent properties.
+
+    (a) windows are independent: a window's output does not depend on its batch mates or slot;
+    (b) time reversal symmetry of the bidirectional net: swapping fwd/_reverse weights and flipping
+        the input in time flips the output; (c) tc vs fp32 paths agree within tolerance."""
+    sd = synth.synth_state_dict(8)
+    T = 10000
+    feats = synth.synth_features(20, T, 10, seed=9)
+    m = _make_model(sd, 10, "tc")
+    out = m.forward_arrays(feats, want_logits=True)
+    sub = m.forward_arrays(feats[[7, 3, 19]], want_logits=True)
+    assert np.array_equal(sub.logits, out.logits[[7, 3, 19]])            # (a) bit-identical
+    sd_sw = dict(sd)
+    for k in list(sd):
+        if k.startswith("gru.") and not k.endswith("_reverse"):
+            sd_sw[k], sd_sw[k + "_reverse"] = sd[k + "_reverse"], sd[k]
+    lw = sd["linear.weight"]
+    sd_sw["linear.weight"] = np.concatenate([lw[:, 128:], lw[:, :128]], axis=1).copy()
+    # layer-1 input weights see [fwd|rev] halves swapped as well
+    for sfx in ("", "_reverse"):
+        w = sd_sw["gru.weight_ih_l1" + sfx]
+        sd_sw["gru.weight_ih_l1" + sfx] = np.concatenate([w[:, 128:], w[:, :128]], axis=1).copy()
+    m2 = _make_model(sd_sw, 10, "tc")
+    out_flip = m2.forward_arrays(feats[:, ::-1].copy(), want_logits=True)
+    assert _scaled_err(out_flip.logits[:, ::-1], out.logits) < 1e-4      # (b)
+    m3 = _make_model(sd, 10, "fp32")
+    out32 = m3.forward_arrays(feats[:8], want_logits=True)
+    assert _scaled_err(out.logits[:8], out32.logits) <= LOGIT_TOL        # (c)
+    mism = int((out.labels[:8] != out32.labels).sum())
+    print("T=10000: tc vs fp32 label mismatches %d / %d" % (mism, out32.labels.size))
+    assert mism == 0
+    for mm in (m, m2, m3):
+        mm.close()
+
+
+# ------------------------------------------------------------------ count normalisation
+NORM_CASES = ["simple", "synth", "synth_minor_start", "synth2dt", "deep"]
+
+
+@pytest.mark.parametrize("name", NORM_CASES)
+@pytest.mark.parametrize("norm", ["total", "fwd_rev", None])
+@pytest.mark.parametrize("sym", [False, True])
+def test_normalise_counts_bit_exact(golden_dir, name, norm, sym):
+    from medaka_b200 import features
+    g = np.load(os.path.join(golden_dir, "post_process.npz"))
+    counts = g[name + "_counts"].copy()
+    pos = np.empty(len(counts), dtype=[("major", "<i8"), ("minor", "<i8")])
+    pos["major"], pos["minor"] = g[name + "_major"], g[name + "_minor"]
+    dtypes = ("r9", "r10") if name == "synth2dt" else ("",)
+    enc = features.CountsFeatureEncoder(normalise=norm, dtypes=dtypes, sym_indels=sym)
+    from medaka_b200 import common
+    s = enc._post_process_pileup(counts, pos, common.Region("ref", int(pos["major"][0]), int(pos["major"][-1]) + 1))
+    key = "%s_%s_%d" % (name, norm, int(sym))
+    assert s.features.dtype == np.float32
+    assert np.array_equal(s.features, g[key + "_features"])
+    assert np.array_equal(np.asarray(s.depth).astype(np.int64), g[key + "_depth"].astype(np.int64))
+
+
+def test_normalise_counts_large_matches_oracle():
+    from medaka_b200 import features, common
+    counts, pos = synth.synth_counts(2000000, seed=123)
+    exp_f, exp_d = features_oracle.post_process_pileup(counts.copy(), pos, "total")
+    enc = features.CountsFeatureEncoder(normalise="total")
+    s = enc._post_process_pileup(counts, pos, common.Region("ref", 0, int(pos["major"][-1]) + 1))
+    assert np.array_equal(s.features, exp_f) and np.array_equal(np.asarray(s.depth), exp_d.astype(np.int64))
+    # property at size: every major column's features sum to 1 (or 0 for empty), minors <= 1
+    sums = s.features.sum(axis=1)
+    assert np.all(np.abs(sums[pos["minor"] == 0] - 1.0) < 1e-5)
+
+
+def test_normalise_empty():
+    from medaka_b200 import libmedaka as lm
+    lm.load()
+    lm.check(lm.lib.mdk_normalise_counts(0, lm.ffi.NULL, lm.ffi.NULL, lm.ffi.NULL, 0, 1, 0, 0, lm.ffi.NULL, lm.ffi.NULL))
+
+
+# ------------------------------------------------------------------ decode
+def test_decode_consensus_bit_exact(golden_dir):
+    from medaka_b200 import labels as mlabels, common
+    g = np.load(os.path.join(golden_dir, "decode.npz"))
+    ls = mlabels.HaploidLabelScheme()
+    s = common.Sample("c", None, None, None, None, g["probs"], None)
+    seq, qual = ls.decode_consensus(s, with_qualities=True)
+    assert seq.encode() == g["seq"].tobytes() and qual.encode() == g["qual"].tobytes()
+    seq, qual = ls.decode_consensus(s, with_gaps=True, with_qualities=True)
+    assert seq.encode() == g["seq_gaps"].tobytes() and qual.encode() == g["qual_gaps"].tobytes()
+    # reference literal (medaka/test/test_labels.py:252-266)
+    p = np.array([[0., 0.991, 0.009, 0., 0.], [0.1, 0., 0.9, 0., 0.], [0.9, 0., 0.02, 0.04, 0.04],
+                  [0, 0, 0, 0, 1], [0, 0.1, 0.1, 0.6, 0.2], [0, 0.01, 0.1, 0.88, 0.01]])
+    s = common.Sample("c", None, None, None, None, p, None)
+    assert ls.decode_consensus(s, with_qualities=True) == ("ACTGG", "5+g$*")
+    assert ls.decode_consensus(s) == "ACTGG"
+
+
+def test_decode_large_matches_oracle():
+    from medaka_b200 import labels as mlabels
+    rs = np.random.RandomState(3)
+    logits = rs.normal(0, 5, (3000000, 5)).astype(np.float32)
+    e = np.exp(logits - logits.max(-1, keepdims=True))
+    p = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    lab, q = mlabels.decode_arrays(p)
+    exp_lab, exp_q = labels_oracle.decode_arrays(p)
+    assert np.array_equal(lab, exp_lab)
+    assert np.array_equal(q, exp_q)

@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""GPU bring-up diagnostics: each check runs in its own process (a trapped kernel poisons the CUDA
+context) under a timeout, and reports into gpurun_out/diag.json.  Not part of the product."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def check_selftest(arg):
+    from medaka_b200 import libmedaka as lm
+    lm.load()
+    ffi = lm.ffi
+    res = {}
+    variant = int(arg)
+    for N, K in [(16, 16), (16, 128), (32, 64), (128, 64), (128, 256)]:
+        rs = np.random.RandomState(N * 1000 + K)
+        A = rs.uniform(-1, 1, (128, K)).astype(np.float32)
+        B = rs.uniform(-1, 1, (N, K)).astype(np.float32)
+        D = np.full((128, N), np.nan, dtype=np.float32)
+        lm.check(lm.lib.mdk_selftest_umma(0, ffi.cast("const float *", ffi.from_buffer(A)),
+                                          ffi.cast("const float *", ffi.from_buffer(B)),
+                                          ffi.cast("float *", ffi.from_buffer(D)), N, K, variant))
+        ref = A.astype(np.float64) @ B.astype(np.float64).T
+        res["N%d_K%d" % (N, K)] = float(np.nanmax(np.abs(D - ref))) if np.isfinite(D).any() else "all-nan"
+    return res
+
+
+def _forward(precision, B, T, seed=0, F=10):
+    from medaka_b200 import models
+    from oracle import gru_oracle, synth
+    sd = synth.synth_state_dict(seed, num_features=F)
+    feats = synth.synth_features(B, T, F, seed=42)
+    man = gru_oracle.manual_forward(sd, feats)
+    m = models.GRUModel(num_features=F)
+    m.load_state_dict(sd)
+    m.set_precision(precision)
+    t0 = time.time()
+    out = m.forward_arrays(feats, want_logits=True)
+    dt = time.time() - t0
+    h0, h1 = m.read_activation(0), m.read_activation(1)
+    scale = np.abs(man["logits"]).max(-1, keepdims=True)
+    res = {
+        "dh0": float(np.abs(h0 - man["h0"]).max()), "dh1": float(np.abs(h1 - man["h1"]).max()),
+        "dh0_fwd": float(np.abs(h0[..., :128] - man["h0"][..., :128]).max()),
+        "dh0_rev": float(np.abs(h0[..., 128:] - man["h0"][..., 128:]).max()),
+        "dh0_t0": float(np.abs(h0[:, 0, :128] - man["h0"][:, 0, :128]).max()),
+        "dh0_t1": float(np.abs(h0[:, min(1, T - 1), :128] - man["h0"][:, min(1, T - 1), :128]).max()),
+        "dlogit_scaled": float((np.abs(out.logits - man["logits"]) / scale).max()),
+        "label_mismatch": int((out.labels != np.argmax(man["probs"], -1)).sum()),
+        "n": int(out.labels.size), "wall_s": dt, "timings": m.last_timings(),
+        "finite": bool(np.isfinite(out.logits).all()),
+    }
+    return res
+
+
+def check_forward(arg):
+    precision, B, T = arg.split(",")
+    return _forward(precision, int(B), int(T))
+
+
+def check_misc(arg):
+    from medaka_b200 import features, labels, common
+    from oracle import features_oracle, labels_oracle, synth
+    res = {}
+    counts, pos = synth.synth_counts(200000, seed=3)
+    for norm in ("total", "fwd_rev", None):
+        for sym in (False, True):
+            ef, ed = features_oracle.post_process_pileup(counts.copy(), pos, norm, ("",), sym)
+            s = features.CountsFeatureEncoder(normalise=norm, sym_indels=sym)._post_process_pileup(
+                counts.copy(), pos, common.Region("r", 0, int(pos["major"][-1]) + 1))
+            res["norm_%s_%d" % (norm, sym)] = [int((s.features != ef).sum()), int((np.asarray(s.depth) != ed.astype(np.int64)).sum())]
+    rs = np.random.RandomState(1)
+    lg = rs.normal(0, 5, (500000, 5)).astype(np.float32)
+    e = np.exp(lg - lg.max(-1, keepdims=True))
+    p = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    lab, q = labels.decode_arrays(p)
+    el, eq = labels_oracle.decode_arrays(p)
+    res["decode"] = [int((lab != el).sum()), int((q != eq).sum())]
+    return res
+
+
+CHECKS = {"selftest": check_selftest, "forward": check_forward, "misc": check_misc}
+
+PLAN = [
+    ("selftest", "0"), ("selftest", "1"), ("selftest", "2"),
+    ("misc", ""),
+    ("forward", "fp32,20,64"), ("forward", "tc,20,64"), ("forward", "tc,37,130"), ("forward", "fp32,37,130"),
+    ("forward", "tc,1200,24"), ("forward", "tc,3,1500"),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check")
+    ap.add_argument("--arg", default="")
+    args = ap.parse_args()
+    if args.check:
+        print("RESULT " + json.dumps(CHECKS[args.check](args.arg)))
+        return
+    os.makedirs(OUT, exist_ok=True)
+    report = {}
+    for name, arg in PLAN:
+        key = "%s[%s]" % (name, arg)
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--check", name, "--arg", arg],
+                               capture_output=True, text=True, timeout=300)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+            if lines:
+                report[key] = json.loads(lines[-1][7:])
+            else:
+                report[key] = {"error": (r.stdout[-1500:] + "\n" + r.stderr[-2500:])}
+        except subprocess.TimeoutExpired:
+            report[key] = {"error": "timeout"}
+        report[key + ".s"] = round(time.time() - t0, 1)
+        print(key, json.dumps(report[key])[:600], flush=True)
+        with open(os.path.join(OUT, "diag.json"), "w") as fh:
+            json.dump(report, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()
