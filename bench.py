@@ -107,33 +107,77 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(threads, sample_windows, cols, feats, steps=1, warmup=0):
+def host_cores():
+    """Host threads this process may really use: scheduler affinity capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+def log(msg):
+    print("[bench %.1fs] %s" % (time.perf_counter() - T_START, msg), file=sys.stderr, flush=True)
+
+
+T_START = time.perf_counter()
+
+
+def fill_features(x, seed):
+    """Fill a float32 [B,T,F] array IN PLACE with normalised-count-like values (rows sum to 1)."""
+    rng = np.random.default_rng(seed)
+    rng.random(out=x.reshape(-1), dtype=np.float32)
+    step = max(1, (1 << 22) // (x.shape[1] * x.shape[2]))
+    for i in range(0, x.shape[0], step):
+        b = x[i:i + step]
+        b *= b * b
+        b /= b.sum(axis=-1, keepdims=True)
+    return x
+
+
+def cpu_reference_rate(threads, sample_windows, cols, feats, steps=1, warmup=0, budget_s=12.0):
     """positions/s of the reference's CPU arithmetic (torch fp32 nn.GRU + Linear + softmax, the
-    oracle restatement of medaka/architectures/gru.py + models.py:303-313) on a bounded sample."""
+    oracle restatement of medaka/architectures/gru.py + models.py:303-313) on a bounded sample.
+
+    ``cols`` <= 0 picks the number of columns so that one pass takes about ``budget_s`` seconds
+    (calibrated on a 20-column probe); per-position cost does not depend on the window length.
+    Returns (positions/s, seconds per step, cols used)."""
     import torch
     from oracle import gru_oracle, synth
     torch.set_num_threads(threads)
     sd = synth.synth_state_dict(0, num_features=feats)
     model = gru_oracle.build(sd, num_features=feats)
-    x = synth.synth_features(sample_windows, cols, feats, seed=1)
+    if cols <= 0:
+        probe = fill_features(np.empty((sample_windows, 20, feats), dtype=np.float32), 2)
+        gru_oracle.predict_on_batch(model, probe)
+        t0 = time.perf_counter()
+        gru_oracle.predict_on_batch(model, probe)
+        r0 = sample_windows * 20 / (time.perf_counter() - t0)
+        cols = int(min(2000, max(40, r0 * budget_s / sample_windows)))
+    x = fill_features(np.empty((sample_windows, cols, feats), dtype=np.float32), 1)
     for _ in range(warmup):
         gru_oracle.predict_on_batch(model, x)
     t0 = time.perf_counter()
     for _ in range(steps):
         gru_oracle.predict_on_batch(model, x)
     dt = time.perf_counter() - t0
-    return steps * sample_windows * cols / dt, dt / steps
+    return steps * sample_windows * cols / dt, dt / steps, cols
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path on this box's host cores (rank 0 only)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     sample_windows = args.cpu_windows
-    rate, sec_per_step = cpu_reference_rate(cores, sample_windows, COLS, FEATS, steps=args.steps,
-                                            warmup=min(args.warmup, 1))
-    sample = "%d windows x %d cols per step (bounded sample of the 1111-window batch)" % (sample_windows, COLS)
+    rate, sec_per_step, cols = cpu_reference_rate(cores, sample_windows, args.cpu_cols, FEATS, steps=args.steps,
+                                                  warmup=min(args.warmup, 1))
+    sample = "%d windows x %d cols per step (the reference's 200-window batch, truncated in time)" % (
+        sample_windows, cols)
     line = {
         "impl": "reference", "metric": "pileup positions/sec (consensus inference)", "value": rate,
         "unit": "positions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -163,7 +207,9 @@ def main():
     ap.add_argument("--windows", type=int, default=WINDOWS, help="windows per step per GPU")
     ap.add_argument("--cols", type=int, default=COLS)
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
-    ap.add_argument("--cpu-windows", type=int, default=24, help="windows in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-windows", type=int, default=200, help="windows in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-cols", type=int, default=0,
+                    help="columns per window in the CPU-baseline sample (0 = sized for ~12 s per pass)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -211,7 +257,9 @@ def main():
 
     B, T, F = args.windows, args.cols, FEATS
     P = B * T
-    feats = synth.synth_features(B, T, F, seed=1000 + rank)
+    log("generating %d x %d x %d synthetic features into pinned host memory" % (B, T, F))
+    feats = fill_features(model.pinned("bench_feats", (B, T, F), np.float32), 1000 + rank)
+    log("reserving workspace")
     lm.check(lib.mdk_engine_reserve(eng, B, T))
 
     # ---- device-resident leg ("value") ----
@@ -235,9 +283,11 @@ def main():
             dist.barrier()
         lm.check(lib.mdk_engine_sync(eng))
 
+    log("device-resident leg: warm-up")
     for _ in range(args.warmup):
         step_dev()
     barrier()
+    log("device-resident leg: timing %d steps" % args.steps)
     launches0 = model.launch_count()
     sampler = ClockSampler(dev)
     sampler.start()
@@ -260,8 +310,7 @@ def main():
     assert np.isfinite(chk).all() and abs(float(chk.sum(-1).mean()) - 1.0) < 1e-4
 
     # ---- host-buffer leg ("e2e"): pinned H2D + forward + D2H of probs and labels per step ----
-    h_feats = model.pinned("bench_feats", (B, T, F), np.float32)
-    np.copyto(h_feats, feats)
+    h_feats = feats
     h_probs = model.pinned("bench_probs", (B, T, 5), np.float32)
     h_labels = model.pinned("bench_labels", (B, T), np.uint8)
 
@@ -270,6 +319,7 @@ def main():
                                         ffi.cast("float *", ffi.from_buffer(h_probs)), ffi.NULL,
                                         ffi.cast("uint8_t *", ffi.from_buffer(h_labels))))
 
+    log("host-buffer leg")
     for _ in range(max(1, min(args.warmup, 2))):
         step_host()
     barrier()
@@ -320,11 +370,13 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        rate, sec = cpu_reference_rate(cores, args.cpu_windows, T, F, steps=1, warmup=0)
+        cores = host_cores()
+        log("cpu baseline on %d threads" % cores)
+        rate, sec, ccols = cpu_reference_rate(cores, args.cpu_windows, args.cpu_cols, F, steps=1, warmup=0)
         cpu_baseline = {"value": rate, "unit": "positions/s", "cores": cores, "kind": "port",
                         "sample": "%d windows x %d cols, 1 pass (%.1f s), torch %s fp32 nn.GRU oracle" % (
-                            args.cpu_windows, T, sec, torch.__version__)}
+                            args.cpu_windows, ccols, sec, torch.__version__)}
+    log("done")
 
     line = {
         "metric": "pileup positions/sec (consensus inference)", "value": value, "unit": "positions/s",

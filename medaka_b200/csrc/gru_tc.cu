@@ -485,6 +485,7 @@ int selftest_umma(int device, const float *A, const float *B, float *D, int N, i
     MDK_CUDA(cudaMemcpy(dA, A, sizeof(float) * 128 * K, cudaMemcpyHostToDevice));
     MDK_CUDA(cudaMemcpy(dB, B, sizeof(float) * N * K, cudaMemcpyHostToDevice));
     const int smem = 2 * 128 * K * 2 + 2 * N * K * 2 + 64;
+    MDK_REQUIRE(smem <= 227 * 1024, MDK_ERR_ARG, "selftest_umma: N*K too large for shared memory");
     MDK_CUDA(cudaFuncSetAttribute(selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     selftest_kernel<<<1, 128, smem>>>(dA, dB, dD, N, K, variant);
     MDK_CUDA(cudaGetLastError());
