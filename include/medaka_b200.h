@@ -155,6 +155,9 @@ int mdk_decode_consensus(int device, const float *probs, int64_t n, uint8_t *lab
                          uint8_t *quals_out);
 int mdk_decode_consensus_dev(int device, const float *probs_dev, int64_t n,
                              uint8_t *labels_out_dev, uint8_t *quals_out_dev);
+/* same for float64 probabilities: all arithmetic in double, as numpy does for a float64 label_probs array */
+int mdk_decode_consensus_f64(int device, const double *probs, int64_t n, uint8_t *labels_out,
+                             uint8_t *quals_out);
 
 /* ---- self test of the tcgen05 building block (one 128xN tile GEMM), used by tests ----------
  * Computes D[128][N] = A[128][K] * B[N][K]^T with the same smem layouts, descriptors and

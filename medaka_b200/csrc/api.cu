@@ -1,6 +1,7 @@
 // C ABI of libmedaka_b200 (include/medaka_b200.h): engine life-cycle, weight loading, the forward
 // pipeline, and the featuriser / decode entry points.  Host orchestration only - kernels live in
 // misc.cu, gru_fp32.cu and gru_tc.cu.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -35,12 +36,17 @@ static void dev_free(T *&p) {
     p = nullptr;
 }
 
-static int upload(float **dst, const float *src, size_t n) {
+// Host -> device upload ordered on the ENGINE stream.  A plain cudaMemcpy from pageable memory returns once the
+// data is staged, possibly before the DMA lands, and the engine stream is non-blocking (it does not synchronise
+// with the legacy default stream): the packing kernels could then read stale weights (seen as run-to-run
+// 3e-6 differences in layer-0 outputs).  cudaMemcpyAsync + stream sync closes that window.
+static int upload(cudaStream_t stream, float **dst, const float *src, size_t n) {
     if (!*dst) {
         int rc = dev_alloc(dst, n);
         if (rc) return rc;
     }
-    MDK_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    MDK_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    MDK_CUDA(cudaStreamSynchronize(stream));
     return MDK_OK;
 }
 
@@ -62,6 +68,7 @@ static int prepare_weights(mdk_engine *e) {
         if (!lw.b_hn && (rc = dev_alloc(&lw.b_hn, (size_t)NDIR * H))) return rc;
         if (!lw.w_hh_t && (rc = dev_alloc(&lw.w_hh_t, (size_t)NDIR * H * G3))) return rc;
         if (!lw.w_hh_tc && (rc = dev_alloc(&lw.w_hh_tc, (size_t)NDIR * 2 * G3 * H))) return rc;
+        if (!lw.w_hh_tm && (rc = dev_alloc(&lw.w_hh_tm, (size_t)NDIR * 2 * G3 * H))) return rc;
         if (l == 1 && !lw.w_in_tc && (rc = dev_alloc(&lw.w_in_tc, (size_t)2 * GI_COLS * H2))) return rc;
         MDK_CUDA(launch_prepare_layer(lw, in, l == 1, e->stream));
         e->launches++;
@@ -119,7 +126,8 @@ static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t
                             e->desc.num_features, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[2], s));
-    if (tc) MDK_CUDA(launch_rec_tc(e->gi, e->layer[0].w_hh_tc, e->layer[0].b_hn, e->h0, 1, B, T, e->sm_count, s));
+    if (tc) MDK_CUDA(launch_rec_tc(e->gi, e->layer[0].w_hh_tc, e->layer[0].w_hh_tm, e->layer[0].b_hn, e->h0, 1, B, T,
+                                   e->sm_count, e->rec_w_in_smem, s));
     else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[0].w_hh_t, e->layer[0].b_hn, (float *)e->h0, B, T, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[3], s));
@@ -127,7 +135,8 @@ static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t
     else MDK_CUDA(launch_gemm_fp32((const float *)e->h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, e->gi, P, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[4], s));
-    if (tc) MDK_CUDA(launch_rec_tc(e->gi, e->layer[1].w_hh_tc, e->layer[1].b_hn, e->h1, 0, B, T, e->sm_count, s));
+    if (tc) MDK_CUDA(launch_rec_tc(e->gi, e->layer[1].w_hh_tc, e->layer[1].w_hh_tm, e->layer[1].b_hn, e->h1, 0, B, T,
+                                   e->sm_count, e->rec_w_in_smem, s));
     else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[1].w_hh_t, e->layer[1].b_hn, e->h1, B, T, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[5], s));
@@ -243,6 +252,10 @@ int mdk_engine_create(int device, const mdk_model_desc *desc, mdk_engine **out) 
     e->device = device;
     e->desc = *desc;
     e->sm_count = prop.multiProcessorCount;
+    {
+        const char *v = getenv("MDK_REC_SMEM");
+        e->rec_w_in_smem = v && v[0] == '1';
+    }
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
     for (auto &set : e->evr) for (auto &ev : set) cudaEventCreate(&ev);
@@ -259,7 +272,7 @@ int mdk_engine_destroy(mdk_engine *e) {
         LayerWeights &lw = e->layer[l];
         for (int d = 0; d < NDIR; ++d) { dev_free(lw.w_ih[d]); dev_free(lw.w_hh[d]); dev_free(lw.b_ih[d]); dev_free(lw.b_hh[d]); }
         dev_free(lw.w_in_packed); dev_free(lw.bias_gi); dev_free(lw.b_hn); dev_free(lw.w_hh_t);
-        dev_free(lw.w_hh_tc); dev_free(lw.w_in_tc);
+        dev_free(lw.w_hh_tc); dev_free(lw.w_hh_tm); dev_free(lw.w_in_tc);
     }
     dev_free(e->lin_w); dev_free(e->lin_b);
     dev_free(e->gi); dev_free(e->h1);
@@ -283,10 +296,10 @@ int mdk_engine_load_gru(mdk_engine *e, int layer, int direction, const float *w_
     LayerWeights &lw = e->layer[layer];
     const int in = in_features(e, layer);
     int rc;
-    if ((rc = upload(&lw.w_ih[direction], w_ih, (size_t)G3 * in))) return rc;
-    if ((rc = upload(&lw.w_hh[direction], w_hh, (size_t)G3 * H))) return rc;
-    if ((rc = upload(&lw.b_ih[direction], b_ih, (size_t)G3))) return rc;
-    if ((rc = upload(&lw.b_hh[direction], b_hh, (size_t)G3))) return rc;
+    if ((rc = upload(e->stream, &lw.w_ih[direction], w_ih, (size_t)G3 * in))) return rc;
+    if ((rc = upload(e->stream, &lw.w_hh[direction], w_hh, (size_t)G3 * H))) return rc;
+    if ((rc = upload(e->stream, &lw.b_ih[direction], b_ih, (size_t)G3))) return rc;
+    if ((rc = upload(e->stream, &lw.b_hh[direction], b_hh, (size_t)G3))) return rc;
     lw.loaded[direction] = true;
     e->prepared = false;
     return MDK_OK;
@@ -297,8 +310,8 @@ int mdk_engine_load_linear(mdk_engine *e, const float *w, const float *b) {
     MDK_CUDA(cudaSetDevice(e->device));
     MDK_CUDA(cudaStreamSynchronize(e->stream));
     int rc;
-    if ((rc = upload(&e->lin_w, w, (size_t)NCLS * H2))) return rc;
-    if ((rc = upload(&e->lin_b, b, (size_t)NCLS))) return rc;
+    if ((rc = upload(e->stream, &e->lin_w, w, (size_t)NCLS * H2))) return rc;
+    if ((rc = upload(e->stream, &e->lin_b, b, (size_t)NCLS))) return rc;
     e->lin_loaded = true;
     return MDK_OK;
 }
@@ -514,6 +527,25 @@ int mdk_decode_consensus(int device, const float *probs, int64_t n, uint8_t *lab
     if (err == cudaSuccess && quals_out) err = cudaMemcpy(quals_out, d_quals, (size_t)n, cudaMemcpyDeviceToHost);
     cudaFree(buf);
     if (err != cudaSuccess) return cuda_fail(err, "decode_consensus", __FILE__, __LINE__);
+    return MDK_OK;
+}
+
+int mdk_decode_consensus_f64(int device, const double *probs, int64_t n, uint8_t *labels_out, uint8_t *quals_out) {
+    MDK_REQUIRE(n >= 0, MDK_ERR_ARG, "decode_consensus: n < 0");
+    if (n == 0) return MDK_OK;
+    MDK_REQUIRE(probs && labels_out, MDK_ERR_ARG, "decode_consensus: NULL pointer");
+    MDK_CUDA(cudaSetDevice(device));
+    uint8_t *buf = nullptr;
+    const size_t b_probs = (size_t)n * NCLS * 8;
+    MDK_CUDA(cudaMalloc(&buf, b_probs + 2 * (size_t)n));
+    double *d_probs = reinterpret_cast<double *>(buf);
+    uint8_t *d_labels = buf + b_probs, *d_quals = d_labels + n;
+    cudaError_t err = cudaMemcpy(d_probs, probs, b_probs, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = launch_decode_f64(d_probs, n, d_labels, quals_out ? d_quals : nullptr, 0);
+    if (err == cudaSuccess) err = cudaMemcpy(labels_out, d_labels, (size_t)n, cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess && quals_out) err = cudaMemcpy(quals_out, d_quals, (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    if (err != cudaSuccess) return cuda_fail(err, "decode_consensus_f64", __FILE__, __LINE__);
     return MDK_OK;
 }
 

@@ -19,14 +19,32 @@
 
 namespace mdk {
 
-__device__ __forceinline__ float sigmoid_fast(float x) {
-    // 1/(1+e^-x) with ex2.approx + rcp.approx: ~2 ulp, abs error < 2e-7
-    return __fdividef(1.0f, 1.0f + __expf(-x));
+// ---- activations: ex2.approx / rcp.approx only (MUFU is the gate phase's binding pipe: 5 ops per element) ----
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// r = sigmoid(a), z = sigmoid(b) with ONE reciprocal: 1/((1+e^-a)(1+e^-b)).  Exponents are clamped at 2^60 so the
+// product stays finite (sigmoid(-41.6) = 9e-19: the clamp changes nothing at fp32 resolution).  ~2 ulp.
+__device__ __forceinline__ void sigmoid2_fast(float a, float b, float &r, float &z) {
+    constexpr float kNegLog2e = -1.4426950408889634f;
+    const float ea = 1.0f + ex2_approx(fminf(a * kNegLog2e, 60.0f));
+    const float eb = 1.0f + ex2_approx(fminf(b * kNegLog2e, 60.0f));
+    const float inv = rcp_approx(ea * eb);
+    r = eb * inv;
+    z = ea * inv;
+}
+// tanh(x) = 1 - 2/(1+e^{2x}); absolute error ~1e-7, saturates cleanly at +-1
 __device__ __forceinline__ float tanh_fast(float x) {
-    // 1 - 2/(1+e^{2x}); abs error ~1e-7 (no cancellation blow-up in absolute terms); saturates cleanly
-    const float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, 1.0f + e);
+    constexpr float k2Log2e = 2.8853900817779268f;
+    const float e = ex2_approx(fminf(x * k2Log2e, 60.0f));
+    return fmaf(-2.0f, rcp_approx(1.0f + e), 1.0f);
 }
 
 // =====================================================================================================
@@ -38,25 +56,36 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // =====================================================================================================
 constexpr int RT_N = 16;                                 // windows per tile (UMMA N)
 constexpr int RT_W_BYTES = 2 * 3 * H * H * 2;            // W_hh hi+lo, 3 gate blocks: 196 608 B
-constexpr int RT_HPLANE = RT_N * H * 2;                  // one h plane (hi or lo) of a tile: 4096 B
+constexpr int RT_KG = RT_N * 16 + 16;                    // k-group stride of the h tile: 256 B of rows + 16 B pad, so the
+                                                         // 2-byte stores of 8-lane groups land in different banks
+constexpr int RT_HPLANE = (H / 8) * RT_KG;               // one h plane (hi or lo) of a tile: 4352 B
 constexpr int RT_THREADS = 288;
-constexpr uint32_t RT_TMEM_COLS = 128;
+constexpr int RT_WT_COLS = 2 * 3 * (H / 2);              // W_hh hi+lo as TMEM A operand: 384 columns
 
-template <int NT>
+// W_TMEM = true (production): W_hh lives in TENSOR MEMORY for the whole sequence and is the A operand of a
+// tcgen05.mma ".ts" form - with N = 16 an SS-mode MMA re-reads a 4 KiB A tile from shared memory for 8 cycles
+// of tensor work (measured: tensor-core smem reads 41 % busy, 3.25 us per time step; profiles/r01a_*).
+// TMEM budget: 384 columns of weights + NT x 48 accumulator columns <= 512.
+// W_TMEM = false: W_hh in shared memory (SS-mode MMAs); kept as the comparison variant (MDK_REC_SMEM=1).
+template <int NT, bool W_TMEM>
 struct RecSmem {
     static constexpr int w_off = 0;
-    static constexpr int h_off = RT_W_BYTES;                       // [NT][2 planes][4096]
-    static constexpr int bar_off = h_off + NT * 2 * RT_HPLANE;     // acc_ready[NT], h_ready[NT]
+    static constexpr int h_off = W_TMEM ? 0 : RT_W_BYTES;          // [NT][2 planes][RT_HPLANE]
+    static constexpr int bar_off = h_off + ((NT * 2 * RT_HPLANE + 127) / 128) * 128;   // acc_ready[NT], h_ready[NT]
     static constexpr int tmem_off = bar_off + 2 * NT * 8;
-    static constexpr int total = tmem_off + 16;
+    // W_TMEM: the CTA owns all 512 TMEM columns of its SM, so a second co-resident CTA could only spin in
+    // tcgen05.alloc; ask for > half of the shared memory to keep residency at one CTA per SM.
+    static constexpr int total = W_TMEM ? 120 * 1024 : tmem_off + 16;
+    static constexpr uint32_t tmem_cols = W_TMEM ? 512 : 128;
+    static constexpr uint32_t acc_col0 = W_TMEM ? RT_WT_COLS : 0;
 };
 
-template <int NT, bool OUT_TILES>
+template <int NT, bool OUT_TILES, bool W_TMEM>
 __global__ void __launch_bounds__(RT_THREADS, 1)
-rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh_tc, const float *__restrict__ b_hn,
+rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh, const float *__restrict__ b_hn,
               void *__restrict__ h_out, int64_t B, int64_t T) {
     extern __shared__ __align__(128) uint8_t smem[];
-    using L = RecSmem<NT>;
+    using L = RecSmem<NT, W_TMEM>;
     uint64_t *acc_ready = reinterpret_cast<uint64_t *>(smem + L::bar_off);
     uint64_t *h_ready = acc_ready + NT;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::tmem_off);
@@ -67,12 +96,14 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh_tc, 
     const int dir = blockIdx.y;
     const int64_t win0 = (int64_t)blockIdx.x * (RT_N * NT);
 
-    // ---- prologue: weights -> smem (generic proxy), zero h tiles, barriers, TMEM ----
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(reinterpret_cast<const uint8_t *>(w_hh_tc) +
+    // ---- prologue: (weights -> smem), zero h tiles, barriers, TMEM ----
+    if (!W_TMEM) {
+        const int4 *src = reinterpret_cast<const int4 *>(reinterpret_cast<const uint8_t *>(w_hh) +
                                                          (size_t)dir * RT_W_BYTES);
         int4 *dst = reinterpret_cast<int4 *>(smem + L::w_off);
         for (int i = tid; i < RT_W_BYTES / 16; i += RT_THREADS) dst[i] = src[i];
+    }
+    {
         int4 *hz = reinterpret_cast<int4 *>(smem + L::h_off);
         for (int i = tid; i < NT * 2 * RT_HPLANE / 16; i += RT_THREADS) hz[i] = make_int4(0, 0, 0, 0);
     }
@@ -84,7 +115,7 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh_tc, 
         fence_mbar_init();
     }
     if (warp == 8) {
-        tmem_alloc(tmem_slot, RT_TMEM_COLS);
+        tmem_alloc(tmem_slot, L::tmem_cols);
         tmem_relinquish();
     }
     fence_proxy_async_smem();
@@ -93,34 +124,68 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh_tc, 
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (W_TMEM) {
+        // W_hh (row-major fp16 hi/lo, [dir][part][gate][row j][k]) -> TMEM: lane j, 8 columns per K=16 chunk,
+        // each 32-bit cell = (k even | k odd << 16).  Warps 0-3 cover the 128 lanes.
+        if (warp < 4) {
+            const int jrow = warp * 32 + lane;
+            const uint32_t t_w = tmem_base + ((uint32_t)(warp * 32) << 16);
+            for (int pg = 0; pg < 6; ++pg) {   // pg = part*3 + gate
+                const uint4 *src = reinterpret_cast<const uint4 *>(w_hh + (((size_t)dir * 6 + pg) * H + jrow) * H);
+#pragma unroll
+                for (int ks = 0; ks < H / 16; ++ks) {
+                    const uint4 lo4 = src[2 * ks], hi4 = src[2 * ks + 1];
+                    const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                    tmem_st_x8(t_w + (uint32_t)((pg * 8 + ks) * 8), v);
+                }
+            }
+            tmem_st_wait();
+        }
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    }
+
     if (warp == 8) {
         // ================= MMA issuer =================
+        // Every operand of the 72 MMAs per tile-step must sit in UNIFORM registers, otherwise the compiler wraps
+        // each tcgen05.mma in an R2UR + elect waterfall loop (~50 issue cycles per MMA: measured 2.9 us per step,
+        // unchanged between smem- and TMEM-resident weights).  So: TMEM addresses are literals (this CTA owns all
+        // 512 columns, hence its allocation starts at column 0 - checked below), shared-memory descriptors derive
+        // from the constant dynamic-smem base, and the issue is predicated by elect.sync, not by `lane == 0`.
         const uint32_t idesc = make_idesc_f16(128, RT_N);
         const uint32_t w_addr = smem_u32(smem + L::w_off);
-        const uint32_t h_addr = smem_u32(smem + L::h_off);
+        const uint64_t b_desc0 = make_smem_desc(smem_u32(smem + L::h_off), RT_KG, 128);
+        const uint32_t tbase = W_TMEM ? 0u : tmem_base;
+        if (W_TMEM && tmem_base != 0u) {
+            if (lane == 0) printf("mdk: unexpected TMEM base %u for a 512-column allocation\n", tmem_base);
+            __trap();
+        }
         for (int64_t step = 0; step < T; ++step) {
             const uint32_t par = (uint32_t)(step & 1);
 #pragma unroll
             for (int tile = 0; tile < NT; ++tile) {
                 mbar_wait(&h_ready[tile], par);
                 tc_fence_after_sync();
-                if (lane == 0) {
+                if (elect_one()) {
 #pragma unroll
                     for (int g = 0; g < 3; ++g) {
-                        const uint32_t d = tmem_base + (uint32_t)(tile * 48 + g * 16);
-                        uint32_t acc = 0;
+                        const uint32_t d = tbase + L::acc_col0 + (uint32_t)(tile * 48 + g * 16);
 #pragma unroll
                         for (int prod = 0; prod < 3; ++prod) {
                             const int pa = (prod == 2) ? 1 : 0;   // W part: hi, hi, lo
                             const int pb = (prod == 1) ? 1 : 0;   // h part: hi, lo, hi
-                            const uint32_t a0 = w_addr + (uint32_t)((pa * 3 + g) * (H * H * 2));
-                            const uint32_t b0 = h_addr + (uint32_t)((tile * 2 + pb) * RT_HPLANE);
 #pragma unroll
                             for (int ks = 0; ks < H / 16; ++ks) {
-                                const uint64_t ad = make_smem_desc(a0 + ks * 2 * (H * 16), H * 16, 128);
-                                const uint64_t bd = make_smem_desc(b0 + ks * 2 * (RT_N * 16), RT_N * 16, 128);
-                                umma_f16(d, ad, bd, idesc, acc);
-                                acc = 1;
+                                const uint64_t bd = b_desc0 + (uint64_t)(((tile * 2 + pb) * RT_HPLANE + ks * 2 * RT_KG) >> 4);
+                                const uint32_t acc = (prod | ks) ? 1u : 0u;
+                                if (W_TMEM) {
+                                    umma_f16_ts(d, tbase + (uint32_t)(((pa * 3 + g) * 8 + ks) * 8), bd, idesc, acc);
+                                } else {
+                                    const uint64_t ad = make_smem_desc(
+                                        w_addr + (uint32_t)((pa * 3 + g) * (H * H * 2) + ks * 2 * (H * 16)), H * 16, 128);
+                                    umma_f16(d, ad, bd, idesc, acc);
+                                }
                             }
                         }
                     }
@@ -136,26 +201,33 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh_tc, 
         constexpr int NC = (NT == 2) ? 16 : 8;                 // windows (TMEM columns) per thread
         const int col0 = (NT == 2) ? 0 : wg * 8;
         const int j = (warp & 3) * 32 + lane;                  // hidden unit == TMEM lane
-        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tile * 48 + col0);
+        const uint32_t t_lane =
+            tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + L::acc_col0 + (uint32_t)(tile * 48 + col0);
         const float bhn = b_hn[dir * H + j];
         const int64_t wbase = win0 + tile * RT_N + col0;       // first window of this thread's columns
-        uint8_t *hplane = smem + L::h_off + tile * 2 * RT_HPLANE;
-        const uint32_t h_elem_off = (uint32_t)((j >> 3) * (RT_N * 16) + (j & 7) * 2);   // + n*16
+        // bit c set <=> column c is a real window (only the last tile of the batch is ragged)
+        uint32_t okmask = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) okmask |= ((wbase + c) < B ? 1u : 0u) << c;
+        uint8_t *hrow = smem + L::h_off + tile * 2 * RT_HPLANE + (j >> 3) * RT_KG + (j & 7) * 2 + col0 * 16;
         const int kcol = dir * H + j;
-        const int64_t gcol = (int64_t)dir * G3 + j;
+        const int64_t gstride = T * (int64_t)GI_COLS;          // floats between consecutive windows, same t
+        const float *gwin = gi + (wbase * T) * GI_COLS + (int64_t)dir * G3 + j;
+        // output bases (element units)
+        float *o32 = reinterpret_cast<float *>(h_out) + (wbase * T) * H2 + kcol;                       // fp32 [p][256]
+        __half *o16 = reinterpret_cast<__half *>(h_out) + (int64_t)(kcol >> 3) * (XT_ROWS * 8) + (kcol & 7);   // tiles
 
         float hprev[NC];
+        float g[3][NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) hprev[c] = 0.f;
-        float gnext[3][NC];
         {
-            const int64_t t = dir ? (T - 1) : 0;
+            const float *gt = gwin + (dir ? (T - 1) : 0) * (int64_t)GI_COLS;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                const bool ok = (wbase + c) < B;
-                const float *row = gi + ((ok ? (wbase + c) : 0) * T + t) * GI_COLS + gcol;
 #pragma unroll
-                for (int g = 0; g < 3; ++g) gnext[g][c] = ok ? ldg_stream(row + g * H) : 0.f;
+                for (int q = 0; q < 3; ++q)
+                    g[q][c] = ((okmask >> c) & 1u) ? ldg_stream(gt + c * gstride + q * H) : 0.f;
             }
         }
         // h_{-1} = 0 is already in smem: publish it
@@ -164,8 +236,9 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh_tc, 
 
         for (int64_t step = 0; step < T; ++step) {
             const int64_t t = dir ? (T - 1 - step) : step;
-            const int64_t tn = dir ? (t - 1) : (t + 1);
             const bool more = step + 1 < T;
+            const float *gnext = gwin + (dir ? (t - 1) : (t + 1)) * (int64_t)GI_COLS;   // next step's rows
+            const int64_t p0 = wbase * T + t;                                           // position of column 0
             mbar_wait(&acc_ready[tile], (uint32_t)(step & 1));
             tc_fence_after_sync();
 #pragma unroll
@@ -178,36 +251,30 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh_tc, 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int c = c8 + i;
-                    const float r = sigmoid_fast(gnext[0][c] + __uint_as_float(ar[i]));
-                    const float z = sigmoid_fast(gnext[1][c] + __uint_as_float(az[i]));
-                    const float nn = tanh_fast(gnext[2][c] + r * (__uint_as_float(an[i]) + bhn));
+                    float r, z;
+                    sigmoid2_fast(g[0][c] + __uint_as_float(ar[i]), g[1][c] + __uint_as_float(az[i]), r, z);
+                    const float nn = tanh_fast(fmaf(r, __uint_as_float(an[i]) + bhn, g[2][c]));
                     const float h = fmaf(hprev[c] - nn, z, nn);   // (hx - n) * z + n, as ATen's gru_cell
                     hprev[c] = h;
                     __half hi, lo;
                     split_f16(h, hi, lo);
-                    const int n = col0 + c;                       // row of the B operand tile
-                    *reinterpret_cast<__half *>(hplane + h_elem_off + n * 16) = hi;
-                    *reinterpret_cast<__half *>(hplane + RT_HPLANE + h_elem_off + n * 16) = lo;
-                    const int64_t w = wbase + c;
-                    const bool ok = w < B;
-                    if (ok) {
-                        const int64_t p = w * T + t;
+                    *reinterpret_cast<__half *>(hrow + c * 16) = hi;               // B operand of the next step
+                    *reinterpret_cast<__half *>(hrow + RT_HPLANE + c * 16) = lo;
+                    if ((okmask >> c) & 1u) {
                         if (OUT_TILES) {
-                            __half *tb = reinterpret_cast<__half *>(reinterpret_cast<uint8_t *>(h_out) +
-                                                                    (p / XT_ROWS) * (int64_t)XT_TILE_BYTES);
-                            const int64_t off = (int64_t)(kcol >> 3) * (XT_ROWS * 8) + (p % XT_ROWS) * 8 + (kcol & 7);
-                            tb[off] = hi;
-                            tb[XT_PLANE_BYTES / 2 + off] = lo;
+                            const int64_t p = p0 + c * T;
+                            __half *tb = o16 + (p >> 7) * (int64_t)(XT_TILE_BYTES / 2) + (p & (XT_ROWS - 1)) * 8;
+                            tb[0] = hi;
+                            tb[XT_PLANE_BYTES / 2] = lo;
                         } else {
-                            reinterpret_cast<float *>(h_out)[p * H2 + kcol] = h;
+                            o32[(t + c * T) * H2] = h;
                         }
-                    }
-                    // software pipeline: this column's pre-activations of the NEXT step reuse the same
-                    // registers; the loads complete under the next step's MMA
-                    if (more && ok) {
-                        const float *row = gi + (w * T + tn) * GI_COLS + gcol;
+                        // software pipeline: this column's pre-activations of the NEXT step reuse the same
+                        // registers; the loads complete under the next step's MMA
+                        if (more) {
 #pragma unroll
-                        for (int g = 0; g < 3; ++g) gnext[g][c] = ldg_stream(row + g * H);
+                            for (int q = 0; q < 3; ++q) g[q][c] = ldg_stream(gnext + c * gstride + q * H);
+                        }
                     }
                 }
             }
@@ -220,27 +287,34 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh_tc, 
     __syncthreads();
     if (warp == 8) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, RT_TMEM_COLS);
+        tmem_dealloc(tmem_base, L::tmem_cols);
     }
 }
 
-cudaError_t launch_rec_tc(const float *gi, const __half *w_hh_tc, const float *b_hn, void *h_out, int out_tiles,
-                          int64_t B, int64_t T, int sm_count, cudaStream_t s) {
+cudaError_t launch_rec_tc(const float *gi, const __half *w_hh_tc, const __half *w_hh_tm, const float *b_hn,
+                          void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, bool w_in_smem,
+                          cudaStream_t s) {
     if (B == 0 || T == 0) return cudaSuccess;
     const int64_t tiles = (B + RT_N - 1) / RT_N;
     // ping-pong (2 tiles per CTA) only pays once there are more tiles than SMs to run them one per CTA
     const bool two = tiles * NDIR > (int64_t)sm_count;
     cudaError_t e;
-#define MDK_LAUNCH_REC(NTV, OT)                                                                              \
+#define MDK_LAUNCH_REC(NTV, OT, WT)                                                                          \
     do {                                                                                                     \
-        auto kern = rec_tc_kernel<NTV, OT>;                                                                  \
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem<NTV>::total);    \
+        auto kern = rec_tc_kernel<NTV, OT, WT>;                                                              \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem<NTV, WT>::total); \
         if (e != cudaSuccess) return e;                                                                      \
         dim3 grid((unsigned)((tiles + NTV - 1) / NTV), NDIR);                                                \
-        kern<<<grid, RT_THREADS, RecSmem<NTV>::total, s>>>(gi, w_hh_tc, b_hn, h_out, B, T);                  \
+        kern<<<grid, RT_THREADS, RecSmem<NTV, WT>::total, s>>>(gi, WT ? w_hh_tm : w_hh_tc, b_hn, h_out, B, T); \
     } while (0)
-    if (two) { if (out_tiles) MDK_LAUNCH_REC(2, true); else MDK_LAUNCH_REC(2, false); }
-    else     { if (out_tiles) MDK_LAUNCH_REC(1, true); else MDK_LAUNCH_REC(1, false); }
+#define MDK_LAUNCH_REC2(NTV, OT)                                              \
+    do {                                                                      \
+        if (w_in_smem) MDK_LAUNCH_REC(NTV, OT, false);                        \
+        else MDK_LAUNCH_REC(NTV, OT, true);                                   \
+    } while (0)
+    if (two) { if (out_tiles) MDK_LAUNCH_REC2(2, true); else MDK_LAUNCH_REC2(2, false); }
+    else     { if (out_tiles) MDK_LAUNCH_REC2(1, true); else MDK_LAUNCH_REC2(1, false); }
+#undef MDK_LAUNCH_REC2
 #undef MDK_LAUNCH_REC
     return cudaGetLastError();
 }
@@ -262,7 +336,7 @@ constexpr int GT_STAGE_BYTES = 2 * GT_SLICE_BYTES;              // hi + lo
 constexpr int GT_A_BYTES = 2 * H * H2 * 2;                      // 131 072
 constexpr int GT_BAR_OFF = GT_A_BYTES + GT_STAGES * GT_STAGE_BYTES;
 constexpr int GT_SMEM = GT_BAR_OFF + 128;
-constexpr uint32_t GT_TMEM_COLS = 256;
+constexpr uint32_t GT_TMEM_COLS = 512;   // whole TMEM: the allocation then starts at column 0 (literal addresses)
 
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w_in_tc,
@@ -319,30 +393,36 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
             }
         }
     } else if (warp == 1) {
+        // MMA issuer: operands kept in uniform registers (literal TMEM addresses, descriptors derived from the
+        // constant dynamic-smem base, elect.sync predicate) - see the note in rec_tc_kernel.
         const uint32_t idesc = make_idesc_f16(128, XT_ROWS);
-        const uint32_t a_addr = smem_u32(smem);
-        const uint32_t b_addr = smem_u32(smem + GT_A_BYTES);
+        const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), H * 16, 128);
+        const uint64_t b_desc0 = make_smem_desc(smem_u32(smem + GT_A_BYTES), XT_ROWS * 16, 128);
+        if (tmem_base != 0u) {
+            if (lane == 0) printf("mdk: unexpected TMEM base %u for a 512-column allocation\n", tmem_base);
+            __trap();
+        }
         uint32_t it = 0, tcount = 0;
         for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++tcount) {
             const uint32_t as = tcount & 1;
             mbar_wait(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
             tc_fence_after_sync();
-            const uint32_t d = tmem_base + as * XT_ROWS;
             for (int s = 0; s < XT_K / GT_KSLICE; ++s, ++it) {
                 const uint32_t stage = it % GT_STAGES;
                 mbar_wait(&full[stage], (it / GT_STAGES) & 1);
                 tc_fence_after_sync();
-                if (lane == 0) {
+                if (elect_one()) {
+                    const uint32_t d = as * XT_ROWS;
+                    const uint64_t a_s = a_desc0 + (uint64_t)((s * (GT_KSLICE / 8) * (H * 16)) >> 4);
+                    const uint64_t b_s = b_desc0 + (uint64_t)((stage * GT_STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int prod = 0; prod < 3; ++prod) {
                         const int pa = (prod == 2) ? 1 : 0;   // W part
                         const int pb = (prod == 1) ? 1 : 0;   // x part
-                        const uint32_t a0 = a_addr + pa * (H * H2 * 2) + s * (GT_KSLICE / 8) * (H * 16);
-                        const uint32_t b0 = b_addr + stage * GT_STAGE_BYTES + pb * GT_SLICE_BYTES;
 #pragma unroll
                         for (int ks = 0; ks < GT_KSLICE / 16; ++ks) {
-                            const uint64_t ad = make_smem_desc(a0 + ks * 2 * (H * 16), H * 16, 128);
-                            const uint64_t bd = make_smem_desc(b0 + ks * 2 * (XT_ROWS * 16), XT_ROWS * 16, 128);
+                            const uint64_t ad = a_s + (uint64_t)((pa * (H * H2 * 2) + ks * 2 * (H * 16)) >> 4);
+                            const uint64_t bd = b_s + (uint64_t)((pb * GT_SLICE_BYTES + ks * 2 * (XT_ROWS * 16)) >> 4);
                             umma_f16(d, ad, bd, idesc, (s | prod | ks) ? 1u : 0u);
                         }
                     }
@@ -407,7 +487,8 @@ cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tc, const flo
 
 // =====================================================================================================
 // Self test of the UMMA building block: D[128][N] = A[128][K] . B[N][K]^T, fp16 hi/lo split, one CTA.
-// variant 0 = production descriptors; 1 = LBO/SBO swapped; 2 = descriptor version bits cleared.
+// variant 0 = SS-mode descriptors; 1 = LBO/SBO swapped; 2 = descriptor version bits cleared;
+// 3 = A operand from TMEM (production layout of the recurrent kernel); 4 = same with the fp16 pair order swapped.
 // =====================================================================================================
 __global__ void __launch_bounds__(128, 1)
 selftest_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float *__restrict__ D, int N, int K,
@@ -435,18 +516,44 @@ selftest_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float
         *reinterpret_cast<__half *>(sb + b_plane + off) = lo;
     }
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
-    if (warp == 0) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
+    if (warp == 0) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const bool a_tmem = variant >= 3;
+    if (a_tmem) {
+        // A (both planes) -> TMEM columns [128, 128 + K): plane p, chunk ks at column 128 + (p*(K/16) + ks)*8
+        const int r = warp * 32 + lane;
+        for (int p = 0; p < 2; ++p)
+            for (int ks = 0; ks < K / 16; ++ks) {
+                uint32_t v[8];
+                for (int c = 0; c < 8; ++c) {
+                    const int k0 = ks * 16 + 2 * c;
+                    const uint32_t e0 = *reinterpret_cast<const uint16_t *>(sa + p * a_plane + (k0 / 8) * (128 * 16) + r * 16 + (k0 % 8) * 2);
+                    const uint32_t e1 = *reinterpret_cast<const uint16_t *>(sa + p * a_plane + ((k0 + 1) / 8) * (128 * 16) + r * 16 + ((k0 + 1) % 8) * 2);
+                    v[c] = (variant == 4) ? ((e0 << 16) | e1) : ((e1 << 16) | e0);
+                }
+                tmem_st_x8(tmem_base + ((uint32_t)(warp * 32) << 16) + 128 + (uint32_t)((p * (K / 16) + ks) * 8), v);
+            }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+    }
     if (tid == 0) {
         const uint32_t idesc = make_idesc_f16(128, N);
         uint32_t acc = 0;
         for (int prod = 0; prod < 3; ++prod) {
             const int pa = (prod == 2), pb = (prod == 1);
             for (int ks = 0; ks < K / 16; ++ks) {
+                if (a_tmem) {
+                    const uint64_t bd = make_smem_desc(smem_u32(sb + pb * b_plane) + ks * 2 * N * 16, N * 16, 128);
+                    umma_f16_ts(tmem_base, tmem_base + 128 + (uint32_t)((pa * (K / 16) + ks) * 8), bd, idesc, acc);
+                    acc = 1;
+                    continue;
+                }
                 uint32_t a_lbo = 128 * 16, a_sbo = 128, b_lbo = N * 16, b_sbo = 128;
                 if (variant == 1) { uint32_t t = a_lbo; a_lbo = a_sbo; a_sbo = t; t = b_lbo; b_lbo = b_sbo; b_sbo = t; }
                 uint64_t ad = make_smem_desc(smem_u32(sa + pa * a_plane) + ks * 2 * 128 * 16, a_lbo, a_sbo);
@@ -471,7 +578,7 @@ selftest_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 128); }
+    if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
 }
 
 int selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant) {

@@ -175,6 +175,36 @@ __global__ void __launch_bounds__(256) decode_kernel(const float *__restrict__ p
     }
 }
 
+// float64 probabilities (what numpy computes when label_probs is a float64 array, e.g. the reference's own
+// test literals medaka/test/test_labels.py:252-266): every step in double, like numpy would.
+__global__ void __launch_bounds__(256) decode_f64_kernel(const double *__restrict__ probs, int64_t n,
+                                                         uint8_t *__restrict__ labels, uint8_t *__restrict__ quals) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *p = probs + i * NCLS;
+    double best = p[0];
+    int arg = 0;
+#pragma unroll
+    for (int c = 1; c < NCLS; ++c) {
+        const double v = p[c];
+        if (v > best) { best = v; arg = c; }
+    }
+    labels[i] = (uint8_t)arg;
+    if (quals) {
+        double err = 1.0 - best;
+        err = fmin(fmax(err, 1e-7), 1.0);
+        double q = -10.0 * log10(err);
+        q = fmin(q, 70.0);
+        quals[i] = (uint8_t)((int)q + 33);
+    }
+}
+
+cudaError_t launch_decode_f64(const double *probs, int64_t n, uint8_t *labels, uint8_t *quals, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    decode_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(probs, n, labels, quals);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_decode(const float *probs, int64_t n, uint8_t *labels, uint8_t *quals, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     decode_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(probs, n, labels, quals);
@@ -325,7 +355,7 @@ cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b,
 __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const float *w_hh0, const float *w_hh1,
                                   const float *b_ih0, const float *b_ih1, const float *b_hh0, const float *b_hh1,
                                   int in_features, float *w_in_packed, float *bias_gi, float *b_hn, float *w_hh_t,
-                                  __half *w_hh_tc, __half *w_in_tc) {
+                                  __half *w_hh_tc, __half *w_hh_tm, __half *w_in_tc) {
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const float *w_ih[2] = {w_ih0, w_ih1}, *w_hh[2] = {w_hh0, w_hh1};
@@ -358,6 +388,8 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
         const int64_t off = (int64_t)(k / 8) * (H * 8) + j * 8 + (k % 8);
         w_hh_tc[(((int64_t)d * 2 + 0) * 3 + g) * blk_halfs + off] = hi;
         w_hh_tc[(((int64_t)d * 2 + 1) * 3 + g) * blk_halfs + off] = lo;
+        w_hh_tm[(((int64_t)d * 2 + 0) * 3 + g) * blk_halfs + j * H + k] = hi;
+        w_hh_tm[(((int64_t)d * 2 + 1) * 3 + g) * blk_halfs + j * H + k] = lo;
     }
     if (w_in_tc) {   // layer 1: [blk = d*3+g][part][kg 32][row 128][8]
         for (int64_t i = tid; i < (int64_t)GI_COLS * H2; i += stride) {
@@ -378,7 +410,7 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
 cudaError_t launch_prepare_layer(const LayerWeights &lw, int in_features, bool build_in_tc, cudaStream_t s) {
     pack_layer_kernel<<<296, 256, 0, s>>>(lw.w_ih[0], lw.w_ih[1], lw.w_hh[0], lw.w_hh[1], lw.b_ih[0], lw.b_ih[1],
                                           lw.b_hh[0], lw.b_hh[1], in_features, lw.w_in_packed, lw.bias_gi,
-                                          lw.b_hn, lw.w_hh_t, lw.w_hh_tc, build_in_tc ? lw.w_in_tc : nullptr);
+                                          lw.b_hn, lw.w_hh_t, lw.w_hh_tc, lw.w_hh_tm, build_in_tc ? lw.w_in_tc : nullptr);
     return cudaGetLastError();
 }
 

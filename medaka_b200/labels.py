@@ -14,15 +14,19 @@ from medaka_b200 import libmedaka as _lm
 def decode_arrays(label_probs, device=0, with_qualities=True):
     """float32 probabilities [..., 5] -> (labels uint8 [...], quals uint8 [...] or None)."""
     lib = _lm.load()
-    p = np.ascontiguousarray(label_probs, dtype=np.float32)
+    label_probs = label_probs.detach().cpu().numpy() if hasattr(label_probs, "detach") else np.asarray(label_probs)
+    # numpy decodes in the array's own precision: float64 stays float64, everything else runs as float32
+    f64 = label_probs.dtype == np.float64
+    p = np.ascontiguousarray(label_probs, dtype=np.float64 if f64 else np.float32)
     if p.shape[-1] != 5:
         raise ValueError("expected label probabilities with 5 classes, got shape {}".format(p.shape))
     n = int(np.prod(p.shape[:-1]))
     labels = np.empty(p.shape[:-1], dtype=np.uint8)
     quals = np.empty(p.shape[:-1], dtype=np.uint8) if with_qualities else None
     ffi = _lm.ffi
-    _lm.check(lib.mdk_decode_consensus(
-        device, ffi.cast("const float *", ffi.from_buffer(p)), n,
+    fn, ctype = (lib.mdk_decode_consensus_f64, "const double *") if f64 else (lib.mdk_decode_consensus, "const float *")
+    _lm.check(fn(
+        device, ffi.cast(ctype, ffi.from_buffer(p)), n,
         ffi.cast("uint8_t *", ffi.from_buffer(labels)),
         ffi.cast("uint8_t *", ffi.from_buffer(quals)) if with_qualities else ffi.NULL))
     return labels, quals

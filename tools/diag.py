@@ -91,10 +91,9 @@ def check_misc(arg):
 CHECKS = {"selftest": check_selftest, "forward": check_forward, "misc": check_misc}
 
 PLAN = [
-    ("selftest", "0"), ("selftest", "1"), ("selftest", "2"),
-    ("misc", ""),
-    ("forward", "fp32,20,64"), ("forward", "tc,20,64"), ("forward", "tc,37,130"), ("forward", "fp32,37,130"),
-    ("forward", "tc,1200,24"), ("forward", "tc,3,1500"),
+    ("selftest", "0"), ("selftest", "3"), ("selftest", "4"),
+    ("forward", "tc,20,64"), ("forward", "tc,37,130"), ("forward", "tc,1200,24"), ("forward", "tc,3,1500"),
+    ("forward", "tc,200,2000"), ("forward", "fp32,20,64"),
 ]
 
 
