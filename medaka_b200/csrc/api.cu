@@ -67,8 +67,8 @@ static int prepare_weights(mdk_engine *e) {
         if (!lw.bias_gi && (rc = dev_alloc(&lw.bias_gi, (size_t)GI_COLS))) return rc;
         if (!lw.b_hn && (rc = dev_alloc(&lw.b_hn, (size_t)NDIR * H))) return rc;
         if (!lw.w_hh_t && (rc = dev_alloc(&lw.w_hh_t, (size_t)NDIR * H * G3))) return rc;
-        if (!lw.w_hh_tc && (rc = dev_alloc(&lw.w_hh_tc, (size_t)NDIR * 2 * G3 * H))) return rc;
         if (!lw.w_hh_tm && (rc = dev_alloc(&lw.w_hh_tm, (size_t)NDIR * 2 * G3 * H))) return rc;
+        if (l == 0 && in <= 16 && !lw.w_x_tm && (rc = dev_alloc(&lw.w_x_tm, (size_t)NDIR * 2 * G3 * 16))) return rc;
         if (l == 1 && !lw.w_in_tc && (rc = dev_alloc(&lw.w_in_tc, (size_t)2 * GI_COLS * H2))) return rc;
         MDK_CUDA(launch_prepare_layer(lw, in, l == 1, e->stream));
         e->launches++;
@@ -121,22 +121,28 @@ static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t
     cudaStream_t s = e->stream;
     const bool tc = e->precision == MDK_PREC_TC;
     int launches = 0;
+    const bool fuse_x = tc && e->fuse_x && e->layer[0].w_x_tm != nullptr;
     MDK_CUDA(cudaEventRecord(e->ev[1], s));
-    MDK_CUDA(launch_inproj0(feats_dev, e->layer[0].w_in_packed, e->layer[0].bias_gi, e->gi, P,
-                            e->desc.num_features, s));
-    launches++;
+    if (!fuse_x) {
+        MDK_CUDA(launch_inproj0(feats_dev, e->layer[0].w_in_packed, e->layer[0].bias_gi, e->gi, P,
+                                e->desc.num_features, s));
+        launches++;
+    }
     MDK_CUDA(cudaEventRecord(e->ev[2], s));
-    if (tc) MDK_CUDA(launch_rec_tc(e->gi, e->layer[0].w_hh_tc, e->layer[0].w_hh_tm, e->layer[0].b_hn, e->h0, 1, B, T,
-                                   e->sm_count, e->rec_w_in_smem, s));
-    else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[0].w_hh_t, e->layer[0].b_hn, (float *)e->h0, B, T, s));
+    if (tc) {
+        const RecXArgs fx{feats_dev, e->layer[0].w_x_tm, e->layer[0].bias_gi, e->desc.num_features};
+        MDK_CUDA(launch_rec_tc(e->gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn, e->h0, 1, B, T,
+                               e->sm_count, s));
+    } else {
+        MDK_CUDA(launch_rec_fp32(e->gi, e->layer[0].w_hh_t, e->layer[0].b_hn, (float *)e->h0, B, T, s));
+    }
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[3], s));
     if (tc) MDK_CUDA(launch_gemm_tc(e->h0, e->layer[1].w_in_tc, e->layer[1].bias_gi, e->gi, P, e->sm_count, s));
     else MDK_CUDA(launch_gemm_fp32((const float *)e->h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, e->gi, P, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[4], s));
-    if (tc) MDK_CUDA(launch_rec_tc(e->gi, e->layer[1].w_hh_tc, e->layer[1].w_hh_tm, e->layer[1].b_hn, e->h1, 0, B, T,
-                                   e->sm_count, e->rec_w_in_smem, s));
+    if (tc) MDK_CUDA(launch_rec_tc(e->gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn, e->h1, 0, B, T, e->sm_count, s));
     else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[1].w_hh_t, e->layer[1].b_hn, e->h1, B, T, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[5], s));
@@ -253,8 +259,8 @@ int mdk_engine_create(int device, const mdk_model_desc *desc, mdk_engine **out) 
     e->desc = *desc;
     e->sm_count = prop.multiProcessorCount;
     {
-        const char *v = getenv("MDK_REC_SMEM");
-        e->rec_w_in_smem = v && v[0] == '1';
+        const char *v = getenv("MDK_NO_FUSE_X");
+        e->fuse_x = !(v && v[0] == '1');
     }
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
@@ -272,7 +278,7 @@ int mdk_engine_destroy(mdk_engine *e) {
         LayerWeights &lw = e->layer[l];
         for (int d = 0; d < NDIR; ++d) { dev_free(lw.w_ih[d]); dev_free(lw.w_hh[d]); dev_free(lw.b_ih[d]); dev_free(lw.b_hh[d]); }
         dev_free(lw.w_in_packed); dev_free(lw.bias_gi); dev_free(lw.b_hn); dev_free(lw.w_hh_t);
-        dev_free(lw.w_hh_tc); dev_free(lw.w_hh_tm); dev_free(lw.w_in_tc);
+        dev_free(lw.w_hh_tm); dev_free(lw.w_x_tm); dev_free(lw.w_in_tc);
     }
     dev_free(e->lin_w); dev_free(e->lin_b);
     dev_free(e->gi); dev_free(e->h1);

@@ -54,9 +54,10 @@ struct LayerWeights {
     float *bias_gi = nullptr;       // [768]: r,z: b_ih+b_hh ; n: b_ih
     float *b_hn = nullptr;          // [2][128]
     float *w_hh_t = nullptr;        // [2][128(k)][384] fp32 (transposed) for the FFMA path
-    __half *w_hh_tc = nullptr;      // [2][hi/lo][gate][kgroup16][row128][8] fp16: smem operand image (SS-mode rec_tc)
     __half *w_hh_tm = nullptr;      // [2][hi/lo][gate][row128][k128] fp16 row-major: source of the TMEM-resident A operand
-    __half *w_in_tc = nullptr;      // layer 1 only: [6 blocks][hi/lo][kgroup32][row128][8] fp16
+    __half *w_x_tm = nullptr;       // layer 0, F <= 16: [2][hi/lo][gate][row128][16] fp16 (K zero-padded): fused input projection
+    __half *w_in_tc = nullptr;      // layer 1 only: [6 blocks][hi/lo][row128][k256] fp16 row-major: source of the
+                                    // gemm_tc TMEM-resident A operand
 };
 
 }  // namespace mdk
@@ -66,7 +67,7 @@ struct mdk_engine {
     mdk_model_desc desc{};
     int precision = MDK_PREC_TC;
     int sm_count = 148;
-    bool rec_w_in_smem = false;   // MDK_REC_SMEM=1: SS-mode recurrent kernel (debug / comparison)
+    bool fuse_x = true;           // layer-0 input projection fused into rec_tc (F <= 16); MDK_NO_FUSE_X=1 disables
     cudaStream_t stream = nullptr;
     static constexpr int EV_RING = 32;   // per-forward event sets kept for mdk_engine_mean_timings
     cudaEvent_t evr[EV_RING][8] = {};
@@ -114,10 +115,15 @@ cudaError_t launch_rec_fp32(const float *gi, const float *w_hh_t, const float *b
 cudaError_t launch_gemm_fp32(const float *A, const float *W, const float *bias, float *C, int64_t P,
                              cudaStream_t s);
 // gru_tc.cu
-cudaError_t launch_rec_tc(const float *gi, const __half *w_hh_tc, const __half *w_hh_tm, const float *b_hn,
-                          void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, bool w_in_smem,
-                          cudaStream_t s);
-cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tc, const float *bias, float *gi, int64_t P,
+struct RecXArgs {            // fused layer-0 input projection (rec_tc FUSE_X)
+    const float *feats;      // [B][T][F]
+    const __half *w_x;       // LayerWeights::w_x_tm
+    const float *bias;       // LayerWeights::bias_gi
+    int F;
+};
+cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
+                          void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, cudaStream_t s);
+cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const float *bias, float *gi, int64_t P,
                            int sm_count, cudaStream_t s);
 int selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant);
 

@@ -49,43 +49,69 @@ __device__ __forceinline__ float tanh_fast(float x) {
 
 // =====================================================================================================
 // Recurrent kernel.  One CTA = NT tiles of 16 windows of one direction, for the whole sequence.
-//   warps 0-7 : gate warps (TMEM -> registers -> gate math -> next h into smem + global output)
-//   warp  8   : MMA issuer (lane 0) and TMEM owner
-// NT == 2: warpgroup g owns tile g; the MMA of one tile overlaps the gate math of the other (ping-pong).
-// NT == 1: both warpgroups share tile 0 (8 windows each): used when there are too few windows to fill the GPU.
+//   warps 0-15  : gate warps (TMEM -> registers -> gate math -> next h into smem + global output); warp w reads
+//                 TMEM lane quarter w%4 and the column group w/4
+//   warps 16-18 : MMA issuers, one per gate block r/z/n (warp 16 also owns the TMEM allocation)
+// NT == 2: gate-warp groups 0,1 own tile 0 and groups 2,3 tile 1 (8 windows per thread); the MMAs of one tile
+//          overlap the gate math of the other (ping-pong).
+// NT == 1: all four groups share tile 0 (4 windows per thread): used when there are too few windows to give
+//          every SM two tiles.
+//
+// W_hh (fp16 hi+lo, 384 columns) lives in TENSOR MEMORY for the whole sequence and is the A operand of the
+// tcgen05.mma ".ts" form: with N = 16 an SS-mode MMA re-reads a 4 KiB A tile from shared memory for 8 cycles of
+// tensor work (measured in round 1a: tensor-core smem reads 41 % busy; profiles/r01a_*).
+//
+// FUSE_X (layer 0): the input projection W_ih . x_t (K = F <= 16) is done here as 9 extra MMAs per tile-step
+// (x_t staged as a 16x16 fp16 hi/lo B tile by the gate warps one step ahead), so layer 0 needs no gi buffer at
+// all: the separate projection kernel and its 6 KiB/position HBM round trip disappear, and the gate loop has no
+// global loads.  The n gate needs W_in.x and W_hn.h apart, hence a 4th 16-column accumulator per tile.
+// TMEM budget: 384 (W_hh) [+ 48 (W_ih, NT == 1 only; NT == 2 reads it from smem in SS mode)] + NT x 48/64 <= 512.
 // =====================================================================================================
 constexpr int RT_N = 16;                                 // windows per tile (UMMA N)
-constexpr int RT_W_BYTES = 2 * 3 * H * H * 2;            // W_hh hi+lo, 3 gate blocks: 196 608 B
 constexpr int RT_KG = RT_N * 16 + 16;                    // k-group stride of the h tile: 256 B of rows + 16 B pad, so the
                                                          // 2-byte stores of 8-lane groups land in different banks
 constexpr int RT_HPLANE = (H / 8) * RT_KG;               // one h plane (hi or lo) of a tile: 4352 B
-constexpr int RT_THREADS = 288;
+constexpr int RT_XPLANE = 2 * RT_KG;                     // one x plane (K = 16): 544 B
+constexpr int RT_XBUF = 2 * RT_XPLANE;                   // hi + lo
+constexpr int RT_GATE_WARPS = 16;                        // 4 per scheduler: the gate phase is latency-bound
+constexpr int RT_MMA_WARPS = 3;                          // one issuer per gate block (24 MMAs each per tile-step)
+constexpr int RT_THREADS = 32 * (RT_GATE_WARPS + RT_MMA_WARPS);
 constexpr int RT_WT_COLS = 2 * 3 * (H / 2);              // W_hh hi+lo as TMEM A operand: 384 columns
+constexpr int RT_WX_COLS = 2 * 3 * 8;                    // W_ih (K = 16) hi+lo as TMEM A operand: 48 columns
+constexpr int RT_WX_BLOCK = H * 16 * 2;                  // one (part, gate) block of W_ih in smem: [kg 2][row 128][8] = 4 KiB
 
-// W_TMEM = true (production): W_hh lives in TENSOR MEMORY for the whole sequence and is the A operand of a
-// tcgen05.mma ".ts" form - with N = 16 an SS-mode MMA re-reads a 4 KiB A tile from shared memory for 8 cycles
-// of tensor work (measured: tensor-core smem reads 41 % busy, 3.25 us per time step; profiles/r01a_*).
-// TMEM budget: 384 columns of weights + NT x 48 accumulator columns <= 512.
-// W_TMEM = false: W_hh in shared memory (SS-mode MMAs); kept as the comparison variant (MDK_REC_SMEM=1).
-template <int NT, bool W_TMEM>
-struct RecSmem {
-    static constexpr int w_off = 0;
-    static constexpr int h_off = W_TMEM ? 0 : RT_W_BYTES;          // [NT][2 planes][RT_HPLANE]
-    static constexpr int bar_off = h_off + ((NT * 2 * RT_HPLANE + 127) / 128) * 128;   // acc_ready[NT], h_ready[NT]
+template <int NT, bool FUSE_X>
+struct RecCfg {
+    static constexpr bool wx_tmem = FUSE_X && NT == 1;
+    static constexpr int acc_per_tile = FUSE_X ? 64 : 48;
+    static constexpr uint32_t wx_col0 = RT_WT_COLS;
+    static constexpr uint32_t acc_col0 = RT_WT_COLS + (wx_tmem ? RT_WX_COLS : 0);
+    static_assert(acc_col0 + NT * acc_per_tile <= 512, "TMEM budget");
+    static constexpr int h_off = 0;                                        // [NT][2 planes][RT_HPLANE]
+    static constexpr int x_off = ((NT * 2 * RT_HPLANE + 127) / 128) * 128; // [NT][2 bufs][RT_XBUF]
+    static constexpr int wx_off = x_off + ((NT * 2 * RT_XBUF + 127) / 128) * 128;   // [6][RT_WX_BLOCK] (NT == 2)
+    static constexpr int bar_off = wx_off + 6 * RT_WX_BLOCK;               // acc_ready[NT], h_ready[NT]
     static constexpr int tmem_off = bar_off + 2 * NT * 8;
-    // W_TMEM: the CTA owns all 512 TMEM columns of its SM, so a second co-resident CTA could only spin in
-    // tcgen05.alloc; ask for > half of the shared memory to keep residency at one CTA per SM.
-    static constexpr int total = W_TMEM ? 120 * 1024 : tmem_off + 16;
-    static constexpr uint32_t tmem_cols = W_TMEM ? 512 : 128;
-    static constexpr uint32_t acc_col0 = W_TMEM ? RT_WT_COLS : 0;
+    // the CTA owns all 512 TMEM columns of its SM, so a second co-resident CTA could only spin in tcgen05.alloc;
+    // ask for > half of the shared memory to keep residency at one CTA per SM.
+    static constexpr int total = 120 * 1024;
+    static_assert(tmem_off + 16 <= total, "smem budget");
 };
 
-template <int NT, bool OUT_TILES, bool W_TMEM>
+// arguments of the fused input projection (layer 0)
+struct RecX {
+    const float *feats;     // [B][T][F]
+    const __half *w_x;      // [dir][part][gate][row 128][16] fp16, K zero-padded to 16
+    const float *bias;      // [768]: r,z: b_ih + b_hh ; n: b_ih
+    int F;
+};
+
+template <int NT, bool OUT_TILES, bool FUSE_X>
 __global__ void __launch_bounds__(RT_THREADS, 1)
-rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh, const float *__restrict__ b_hn,
-              void *__restrict__ h_out, int64_t B, int64_t T) {
+rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__ w_hh,
+              const float *__restrict__ b_hn, void *__restrict__ h_out, int64_t B, int64_t T) {
     extern __shared__ __align__(128) uint8_t smem[];
-    using L = RecSmem<NT, W_TMEM>;
+    using L = RecCfg<NT, FUSE_X>;
     uint64_t *acc_ready = reinterpret_cast<uint64_t *>(smem + L::bar_off);
     uint64_t *h_ready = acc_ready + NT;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::tmem_off);
@@ -96,26 +122,29 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh, con
     const int dir = blockIdx.y;
     const int64_t win0 = (int64_t)blockIdx.x * (RT_N * NT);
 
-    // ---- prologue: (weights -> smem), zero h tiles, barriers, TMEM ----
-    if (!W_TMEM) {
-        const int4 *src = reinterpret_cast<const int4 *>(reinterpret_cast<const uint8_t *>(w_hh) +
-                                                         (size_t)dir * RT_W_BYTES);
-        int4 *dst = reinterpret_cast<int4 *>(smem + L::w_off);
-        for (int i = tid; i < RT_W_BYTES / 16; i += RT_THREADS) dst[i] = src[i];
-    }
+    // ---- prologue: zero h / x tiles, barriers, TMEM, weights ----
     {
-        int4 *hz = reinterpret_cast<int4 *>(smem + L::h_off);
-        for (int i = tid; i < NT * 2 * RT_HPLANE / 16; i += RT_THREADS) hz[i] = make_int4(0, 0, 0, 0);
+        int4 *z = reinterpret_cast<int4 *>(smem);
+        for (int i = tid; i < L::wx_off / 16; i += RT_THREADS) z[i] = make_int4(0, 0, 0, 0);
+    }
+    if (FUSE_X && !L::wx_tmem) {
+        // W_ih -> smem operand image [part*3+gate][kg 2][row 128][8 halfs]
+        const __half *src = xin.w_x + (size_t)dir * 6 * H * 16;
+        __half *dst = reinterpret_cast<__half *>(smem + L::wx_off);
+        for (int i = tid; i < 6 * H * 16; i += RT_THREADS) {
+            const int pg = i / (H * 16), r = (i / 16) % H, k = i % 16;
+            dst[pg * (RT_WX_BLOCK / 2) + (k >> 3) * (H * 8) + r * 8 + (k & 7)] = src[i];
+        }
     }
     if (tid == 0) {
         for (int i = 0; i < NT; ++i) {
-            mbar_init(&acc_ready[i], 1);
-            mbar_init(&h_ready[i], NT == 2 ? 128 : 256);
+            mbar_init(&acc_ready[i], RT_MMA_WARPS);
+            mbar_init(&h_ready[i], 32 * RT_GATE_WARPS / NT);
         }
         fence_mbar_init();
     }
-    if (warp == 8) {
-        tmem_alloc(tmem_slot, L::tmem_cols);
+    if (warp == RT_GATE_WARPS) {
+        tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
     fence_proxy_async_smem();
@@ -123,44 +152,47 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh, con
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-
-    if (W_TMEM) {
-        // W_hh (row-major fp16 hi/lo, [dir][part][gate][row j][k]) -> TMEM: lane j, 8 columns per K=16 chunk,
-        // each 32-bit cell = (k even | k odd << 16).  Warps 0-3 cover the 128 lanes.
-        if (warp < 4) {
-            const int jrow = warp * 32 + lane;
-            const uint32_t t_w = tmem_base + ((uint32_t)(warp * 32) << 16);
-            for (int pg = 0; pg < 6; ++pg) {   // pg = part*3 + gate
-                const uint4 *src = reinterpret_cast<const uint4 *>(w_hh + (((size_t)dir * 6 + pg) * H + jrow) * H);
-#pragma unroll
-                for (int ks = 0; ks < H / 16; ++ks) {
-                    const uint4 lo4 = src[2 * ks], hi4 = src[2 * ks + 1];
-                    const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-                    tmem_st_x8(t_w + (uint32_t)((pg * 8 + ks) * 8), v);
-                }
-            }
-            tmem_st_wait();
-        }
-        tc_fence_before_sync();
-        __syncthreads();
-        tc_fence_after_sync();
+    if (tmem_base != 0u) {   // a 512-column allocation starts at column 0; the MMA issuers rely on literal addresses
+        if (tid == 0) printf("mdk: unexpected TMEM base %u for a 512-column allocation\n", tmem_base);
+        __trap();
     }
 
-    if (warp == 8) {
-        // ================= MMA issuer =================
-        // Every operand of the 72 MMAs per tile-step must sit in UNIFORM registers, otherwise the compiler wraps
-        // each tcgen05.mma in an R2UR + elect waterfall loop (~50 issue cycles per MMA: measured 2.9 us per step,
-        // unchanged between smem- and TMEM-resident weights).  So: TMEM addresses are literals (this CTA owns all
-        // 512 columns, hence its allocation starts at column 0 - checked below), shared-memory descriptors derive
-        // from the constant dynamic-smem base, and the issue is predicated by elect.sync, not by `lane == 0`.
-        const uint32_t idesc = make_idesc_f16(128, RT_N);
-        const uint32_t w_addr = smem_u32(smem + L::w_off);
-        const uint64_t b_desc0 = make_smem_desc(smem_u32(smem + L::h_off), RT_KG, 128);
-        const uint32_t tbase = W_TMEM ? 0u : tmem_base;
-        if (W_TMEM && tmem_base != 0u) {
-            if (lane == 0) printf("mdk: unexpected TMEM base %u for a 512-column allocation\n", tmem_base);
-            __trap();
+    // weights (row-major fp16 hi/lo) -> TMEM: lane j, 8 columns per K=16 chunk, cell = (k even | k odd << 16)
+    if (warp < 4) {
+        const int jrow = warp * 32 + lane;
+        const uint32_t t_w = (uint32_t)(warp * 32) << 16;
+        for (int pg = 0; pg < 6; ++pg) {   // pg = part*3 + gate
+            const uint4 *src = reinterpret_cast<const uint4 *>(w_hh + (((size_t)dir * 6 + pg) * H + jrow) * H);
+#pragma unroll
+            for (int ks = 0; ks < H / 16; ++ks) {
+                const uint4 lo4 = src[2 * ks], hi4 = src[2 * ks + 1];
+                const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                tmem_st_x8(t_w + (uint32_t)((pg * 8 + ks) * 8), v);
+            }
+            if (L::wx_tmem) {
+                const uint4 *sx = reinterpret_cast<const uint4 *>(xin.w_x + (((size_t)dir * 6 + pg) * H + jrow) * 16);
+                const uint4 lo4 = sx[0], hi4 = sx[1];
+                const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                tmem_st_x8(t_w + L::wx_col0 + (uint32_t)(pg * 8), v);
+            }
         }
+        tmem_st_wait();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+
+    if (warp >= RT_GATE_WARPS) {
+        // ================= MMA issuers (warp 16 + g issues gate block g) =================
+        // Every operand must sit in UNIFORM registers, otherwise the compiler wraps each tcgen05.mma in an
+        // R2UR + elect waterfall loop (~50 issue cycles per MMA, measured).  So: TMEM addresses are literals,
+        // shared-memory descriptors derive from the constant dynamic-smem base, and the issue is predicated by
+        // elect.sync, not by `lane == 0`.
+        const int g = warp - RT_GATE_WARPS;
+        const uint32_t idesc = make_idesc_f16(128, RT_N);
+        const uint64_t b_desc0 = make_smem_desc(smem_u32(smem + L::h_off), RT_KG, 128);
+        const uint64_t x_desc0 = make_smem_desc(smem_u32(smem + L::x_off), RT_KG, 128);
+        const uint64_t wx_desc0 = make_smem_desc(smem_u32(smem + L::wx_off), H * 16, 128);
         for (int64_t step = 0; step < T; ++step) {
             const uint32_t par = (uint32_t)(step & 1);
 #pragma unroll
@@ -168,24 +200,30 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh, con
                 mbar_wait(&h_ready[tile], par);
                 tc_fence_after_sync();
                 if (elect_one()) {
+                    const uint32_t d = L::acc_col0 + (uint32_t)(tile * L::acc_per_tile + g * 16);
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) {
-                        const uint32_t d = tbase + L::acc_col0 + (uint32_t)(tile * 48 + g * 16);
+                    for (int prod = 0; prod < 3; ++prod) {
+                        const int pa = (prod == 2) ? 1 : 0;   // W part: hi, hi, lo
+                        const int pb = (prod == 1) ? 1 : 0;   // activation part: hi, lo, hi
+#pragma unroll
+                        for (int ks = 0; ks < H / 16; ++ks) {
+                            const uint64_t bd = b_desc0 + (uint64_t)(((tile * 2 + pb) * RT_HPLANE + ks * 2 * RT_KG) >> 4);
+                            umma_f16_ts(d, (uint32_t)(((pa * 3 + g) * 8 + ks) * 8), bd, idesc, (prod | ks) ? 1u : 0u);
+                        }
+                    }
+                    if (FUSE_X) {
+                        // + W_ih[g] . x_t ; r and z accumulate onto the recurrent sum, n keeps its own columns
+                        const uint32_t dx = (g == 2) ? d + 16 : d;
 #pragma unroll
                         for (int prod = 0; prod < 3; ++prod) {
-                            const int pa = (prod == 2) ? 1 : 0;   // W part: hi, hi, lo
-                            const int pb = (prod == 1) ? 1 : 0;   // h part: hi, lo, hi
-#pragma unroll
-                            for (int ks = 0; ks < H / 16; ++ks) {
-                                const uint64_t bd = b_desc0 + (uint64_t)(((tile * 2 + pb) * RT_HPLANE + ks * 2 * RT_KG) >> 4);
-                                const uint32_t acc = (prod | ks) ? 1u : 0u;
-                                if (W_TMEM) {
-                                    umma_f16_ts(d, tbase + (uint32_t)(((pa * 3 + g) * 8 + ks) * 8), bd, idesc, acc);
-                                } else {
-                                    const uint64_t ad = make_smem_desc(
-                                        w_addr + (uint32_t)((pa * 3 + g) * (H * H * 2) + ks * 2 * (H * 16)), H * 16, 128);
-                                    umma_f16(d, ad, bd, idesc, acc);
-                                }
+                            const int pa = (prod == 2) ? 1 : 0;
+                            const int pb = (prod == 1) ? 1 : 0;
+                            const uint64_t xd = x_desc0 + (uint64_t)(((tile * 2 + (int)par) * RT_XBUF + pb * RT_XPLANE) >> 4);
+                            const uint32_t acc = (g == 2 && prod == 0) ? 0u : 1u;
+                            if (L::wx_tmem) {
+                                umma_f16_ts(dx, L::wx_col0 + (uint32_t)((pa * 3 + g) * 8), xd, idesc, acc);
+                            } else {
+                                umma_f16(dx, wx_desc0 + (uint64_t)(((pa * 3 + g) * RT_WX_BLOCK) >> 4), xd, idesc, acc);
                             }
                         }
                     }
@@ -196,13 +234,12 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh, con
         }
     } else {
         // ================= gate warps =================
-        const int wg = warp >> 2;
-        const int tile = (NT == 2) ? wg : 0;
-        constexpr int NC = (NT == 2) ? 16 : 8;                 // windows (TMEM columns) per thread
-        const int col0 = (NT == 2) ? 0 : wg * 8;
+        const int grp = warp >> 2;                             // column group 0..3
+        const int tile = (NT == 2) ? (grp >> 1) : 0;
+        constexpr int NC = (NT == 2) ? 8 : 4;                  // windows (TMEM columns) per thread
+        const int col0 = (NT == 2) ? (grp & 1) * 8 : grp * 4;
         const int j = (warp & 3) * 32 + lane;                  // hidden unit == TMEM lane
-        const uint32_t t_lane =
-            tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + L::acc_col0 + (uint32_t)(tile * 48 + col0);
+        const uint32_t t_lane = ((uint32_t)((warp & 3) * 32) << 16) + L::acc_col0 + (uint32_t)(tile * L::acc_per_tile + col0);
         const float bhn = b_hn[dir * H + j];
         const int64_t wbase = win0 + tile * RT_N + col0;       // first window of this thread's columns
         // bit c set <=> column c is a real window (only the last tile of the batch is ragged)
@@ -211,17 +248,38 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh, con
         for (int c = 0; c < NC; ++c) okmask |= ((wbase + c) < B ? 1u : 0u) << c;
         uint8_t *hrow = smem + L::h_off + tile * 2 * RT_HPLANE + (j >> 3) * RT_KG + (j & 7) * 2 + col0 * 16;
         const int kcol = dir * H + j;
-        const int64_t gstride = T * (int64_t)GI_COLS;          // floats between consecutive windows, same t
-        const float *gwin = gi + (wbase * T) * GI_COLS + (int64_t)dir * G3 + j;
         // output bases (element units)
         float *o32 = reinterpret_cast<float *>(h_out) + (wbase * T) * H2 + kcol;                       // fp32 [p][256]
         __half *o16 = reinterpret_cast<__half *>(h_out) + (int64_t)(kcol >> 3) * (XT_ROWS * 8) + (kcol & 7);   // tiles
 
-        float hprev[NC];
+        // unfused path: pre-activations from the gi buffer, prefetched one step ahead into registers
+        const int64_t gstride = T * (int64_t)GI_COLS;          // floats between consecutive windows, same t
+        const float *gwin = FUSE_X ? nullptr : gi + (wbase * T) * GI_COLS + (int64_t)dir * G3 + j;
         float g[3][NC];
+        // fused path: folded biases, and this thread's share of the x_t staging (160 values per tile-step)
+        float b_r = 0.f, b_z = 0.f, b_n = 0.f;
+        const int tix = (NT == 2) ? (tid & 255) : tid;         // thread index within the tile's gate warps
+        const int xF = FUSE_X ? xin.F : 1;                     // 1 <= F <= 16 on the fused path
+        const int xn = tix / xF, xf = tix - xn * xF;           // window row / feature of the staged value
+        const bool xown = FUSE_X && tix < RT_N * xF;
+        const bool xok = xown && (win0 + tile * RT_N + xn) < B;
+        const float *xsrc = nullptr;
+        uint8_t *xdst = nullptr;
+        float xreg = 0.f;
+        if (FUSE_X) {
+            b_r = xin.bias[dir * G3 + j];
+            b_z = xin.bias[dir * G3 + H + j];
+            b_n = xin.bias[dir * G3 + 2 * H + j];
+            if (xown) {
+                xsrc = xin.feats + ((win0 + tile * RT_N + xn) * T) * xin.F + xf;
+                xdst = smem + L::x_off + tile * 2 * RT_XBUF + (xf >> 3) * RT_KG + xn * 16 + (xf & 7) * 2;
+            }
+        }
+
+        float hprev[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) hprev[c] = 0.f;
-        {
+        if (!FUSE_X) {
             const float *gt = gwin + (dir ? (T - 1) : 0) * (int64_t)GI_COLS;
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
@@ -229,31 +287,52 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh, con
                 for (int q = 0; q < 3; ++q)
                     g[q][c] = ((okmask >> c) & 1u) ? ldg_stream(gt + c * gstride + q * H) : 0.f;
             }
+        } else if (xown) {
+            // x of step 0 -> buffer 0; x of step 1 -> register
+            const float x0 = xok ? xsrc[(dir ? (T - 1) : 0) * (int64_t)xin.F] : 0.f;
+            __half hi, lo;
+            split_f16(x0, hi, lo);
+            *reinterpret_cast<__half *>(xdst) = hi;
+            *reinterpret_cast<__half *>(xdst + RT_XPLANE) = lo;
+            if (T > 1 && xok) xreg = xsrc[(dir ? (T - 2) : 1) * (int64_t)xin.F];
         }
-        // h_{-1} = 0 is already in smem: publish it
+        // h_{-1} = 0 (and x_0) are in smem: publish
+        fence_proxy_async_smem();
         tc_fence_before_sync();
         mbar_arrive(&h_ready[tile]);
 
         for (int64_t step = 0; step < T; ++step) {
             const int64_t t = dir ? (T - 1 - step) : step;
             const bool more = step + 1 < T;
-            const float *gnext = gwin + (dir ? (t - 1) : (t + 1)) * (int64_t)GI_COLS;   // next step's rows
+            const float *gnext = FUSE_X ? nullptr : gwin + (dir ? (t - 1) : (t + 1)) * (int64_t)GI_COLS;
             const int64_t p0 = wbase * T + t;                                           // position of column 0
             mbar_wait(&acc_ready[tile], (uint32_t)(step & 1));
             tc_fence_after_sync();
-#pragma unroll
-            for (int c8 = 0; c8 < NC; c8 += 8) {
-                uint32_t ar[8], az[8], an[8];
-                tmem_ld_x8(t_lane + 0 * 16 + c8, ar);
-                tmem_ld_x8(t_lane + 1 * 16 + c8, az);
-                tmem_ld_x8(t_lane + 2 * 16 + c8, an);
+            {
+                uint32_t ar[NC], az[NC], an[NC], ax[NC];
+                if constexpr (NC == 8) {
+                    tmem_ld_x8(t_lane + 0 * 16, ar);
+                    tmem_ld_x8(t_lane + 1 * 16, az);
+                    tmem_ld_x8(t_lane + 2 * 16, an);
+                    if (FUSE_X) tmem_ld_x8(t_lane + 3 * 16, ax);
+                } else {
+                    tmem_ld_x4(t_lane + 0 * 16, ar);
+                    tmem_ld_x4(t_lane + 1 * 16, az);
+                    tmem_ld_x4(t_lane + 2 * 16, an);
+                    if (FUSE_X) tmem_ld_x4(t_lane + 3 * 16, ax);
+                }
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = c8 + i;
-                    float r, z;
-                    sigmoid2_fast(g[0][c] + __uint_as_float(ar[i]), g[1][c] + __uint_as_float(az[i]), r, z);
-                    const float nn = tanh_fast(fmaf(r, __uint_as_float(an[i]) + bhn, g[2][c]));
+                for (int c = 0; c < NC; ++c) {
+                    float r, z, pre_n;
+                    if (FUSE_X) {
+                        sigmoid2_fast(b_r + __uint_as_float(ar[c]), b_z + __uint_as_float(az[c]), r, z);
+                        pre_n = fmaf(r, __uint_as_float(an[c]) + bhn, b_n + __uint_as_float(ax[c]));
+                    } else {
+                        sigmoid2_fast(g[0][c] + __uint_as_float(ar[c]), g[1][c] + __uint_as_float(az[c]), r, z);
+                        pre_n = fmaf(r, __uint_as_float(an[c]) + bhn, g[2][c]);
+                    }
+                    const float nn = tanh_fast(pre_n);
                     const float h = fmaf(hprev[c] - nn, z, nn);   // (hx - n) * z + n, as ATen's gru_cell
                     hprev[c] = h;
                     __half hi, lo;
@@ -271,50 +350,60 @@ rec_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hh, con
                         }
                         // software pipeline: this column's pre-activations of the NEXT step reuse the same
                         // registers; the loads complete under the next step's MMA
-                        if (more) {
+                        if (!FUSE_X && more) {
 #pragma unroll
                             for (int q = 0; q < 3; ++q) g[q][c] = ldg_stream(gnext + c * gstride + q * H);
                         }
                     }
                 }
             }
-            fence_proxy_async_smem();     // h tile writes -> visible to the MMA's async-proxy reads
+            if (FUSE_X && xown && more) {
+                // stage x_{step+1} (loaded a step ago) into the other buffer, then fetch x_{step+2}
+                __half hi, lo;
+                split_f16(xreg, hi, lo);
+                uint8_t *xd = xdst + (((step + 1) & 1) ? RT_XBUF : 0);
+                *reinterpret_cast<__half *>(xd) = hi;
+                *reinterpret_cast<__half *>(xd + RT_XPLANE) = lo;
+                if (step + 2 < T && xok) xreg = xsrc[(dir ? (t - 2) : (t + 2)) * (int64_t)xin.F];
+            }
+            fence_proxy_async_smem();     // h / x tile writes -> visible to the MMA's async-proxy reads
             tc_fence_before_sync();       // order our tcgen05.ld before the next MMA overwrites the accumulators
             mbar_arrive(&h_ready[tile]);
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == RT_GATE_WARPS) {
         tc_fence_after_sync();
-        tmem_dealloc(tmem_base, L::tmem_cols);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
-cudaError_t launch_rec_tc(const float *gi, const __half *w_hh_tc, const __half *w_hh_tm, const float *b_hn,
-                          void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, bool w_in_smem,
-                          cudaStream_t s) {
+cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
+                          void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, cudaStream_t s) {
     if (B == 0 || T == 0) return cudaSuccess;
     const int64_t tiles = (B + RT_N - 1) / RT_N;
     // ping-pong (2 tiles per CTA) only pays once there are more tiles than SMs to run them one per CTA
     const bool two = tiles * NDIR > (int64_t)sm_count;
+    RecX xin{nullptr, nullptr, nullptr, 0};
+    if (fuse) xin = RecX{fuse->feats, fuse->w_x, fuse->bias, fuse->F};
     cudaError_t e;
-#define MDK_LAUNCH_REC(NTV, OT, WT)                                                                          \
+#define MDK_LAUNCH_REC(NTV, OT, FX)                                                                          \
     do {                                                                                                     \
-        auto kern = rec_tc_kernel<NTV, OT, WT>;                                                              \
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecSmem<NTV, WT>::total); \
+        auto kern = rec_tc_kernel<NTV, OT, FX>;                                                              \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecCfg<NTV, FX>::total); \
         if (e != cudaSuccess) return e;                                                                      \
         dim3 grid((unsigned)((tiles + NTV - 1) / NTV), NDIR);                                                \
-        kern<<<grid, RT_THREADS, RecSmem<NTV, WT>::total, s>>>(gi, WT ? w_hh_tm : w_hh_tc, b_hn, h_out, B, T); \
+        kern<<<grid, RT_THREADS, RecCfg<NTV, FX>::total, s>>>(gi, xin, w_hh_tm, b_hn, h_out, B, T);          \
     } while (0)
-#define MDK_LAUNCH_REC2(NTV, OT)                                              \
-    do {                                                                      \
-        if (w_in_smem) MDK_LAUNCH_REC(NTV, OT, false);                        \
-        else MDK_LAUNCH_REC(NTV, OT, true);                                   \
-    } while (0)
-    if (two) { if (out_tiles) MDK_LAUNCH_REC2(2, true); else MDK_LAUNCH_REC2(2, false); }
-    else     { if (out_tiles) MDK_LAUNCH_REC2(1, true); else MDK_LAUNCH_REC2(1, false); }
-#undef MDK_LAUNCH_REC2
+    if (fuse) {
+        if (!out_tiles) return cudaErrorInvalidValue;   // the fused projection is layer 0, which feeds the GEMM
+        if (two) MDK_LAUNCH_REC(2, true, true); else MDK_LAUNCH_REC(1, true, true);
+    } else if (two) {
+        if (out_tiles) MDK_LAUNCH_REC(2, true, false); else MDK_LAUNCH_REC(2, false, false);
+    } else {
+        if (out_tiles) MDK_LAUNCH_REC(1, true, false); else MDK_LAUNCH_REC(1, false, false);
+    }
 #undef MDK_LAUNCH_REC
     return cudaGetLastError();
 }
@@ -329,17 +418,21 @@ cudaError_t launch_rec_tc(const float *gi, const __half *w_hh_tc, const __half *
 //   warps 2-5 : epilogue (TMEM -> registers -> + bias -> coalesced fp32 stores)
 // =====================================================================================================
 constexpr int GT_THREADS = 192;
-constexpr int GT_STAGES = 3;
+constexpr int GT_STAGES = 6;
 constexpr int GT_KSLICE = 64;                                   // K per stage
 constexpr int GT_SLICE_BYTES = XT_ROWS * GT_KSLICE * 2;         // one plane of one slice: 16 KiB
 constexpr int GT_STAGE_BYTES = 2 * GT_SLICE_BYTES;              // hi + lo
-constexpr int GT_A_BYTES = 2 * H * H2 * 2;                      // 131 072
-constexpr int GT_BAR_OFF = GT_A_BYTES + GT_STAGES * GT_STAGE_BYTES;
-constexpr int GT_SMEM = GT_BAR_OFF + 128;
+constexpr int GT_BAR_OFF = GT_STAGES * GT_STAGE_BYTES;          // 192 KiB of activation stages
+constexpr int GT_SMEM = GT_BAR_OFF + 256;
 constexpr uint32_t GT_TMEM_COLS = 512;   // whole TMEM: the allocation then starts at column 0 (literal addresses)
+constexpr uint32_t GT_W_COLS = 2 * (H2 / 2);                    // weight block hi+lo as TMEM A operand: 256 columns
 
+// The 128x256 weight block (hi+lo) is the A operand and lives in TENSOR MEMORY (256 columns) for the CTA's whole
+// life; the two 128-column accumulators take the other half.  Shared memory then only streams activations, which
+// halves the tensor core's shared-memory read traffic (in SS mode an M128 N128 K16 MMA needs 8 KiB of smem reads
+// per 64 cycles = the entire 128 B/clk, leaving nothing for the bulk-copy writes) and doubles the pipeline depth.
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w_in_tc,
+gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w_in_tm,
                const float *__restrict__ bias, float *__restrict__ gi, int64_t P, int64_t ntiles) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + GT_BAR_OFF);
@@ -355,12 +448,6 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
     const int64_t tile0 = blockIdx.x;
     const int64_t tstride = gridDim.x;
 
-    {
-        const int4 *src = reinterpret_cast<const int4 *>(reinterpret_cast<const uint8_t *>(w_in_tc) +
-                                                         (size_t)blk * GT_A_BYTES);
-        int4 *dst = reinterpret_cast<int4 *>(smem);
-        for (int i = tid; i < GT_A_BYTES / 16; i += GT_THREADS) dst[i] = src[i];
-    }
     if (tid == 0) {
         for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
@@ -370,11 +457,30 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
         tmem_alloc(tmem_slot, GT_TMEM_COLS);
         tmem_relinquish();
     }
-    fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 2) {
+        // weights (row-major fp16 [blk][part][row j][k 256]) -> TMEM: lane j, plane p chunk ks at column (p*16+ks)*8
+        const int q = warp & 3;
+        const int jrow = q * 32 + lane;
+        const uint32_t t_w = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int p = 0; p < 2; ++p) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(w_in_tm + (((size_t)blk * 2 + p) * H + jrow) * H2);
+#pragma unroll 4
+            for (int ks = 0; ks < H2 / 16; ++ks) {
+                const uint4 lo4 = src[2 * ks], hi4 = src[2 * ks + 1];
+                const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                tmem_st_x8(t_w + (uint32_t)((p * (H2 / 16) + ks) * 8), v);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -384,7 +490,7 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
                 for (int s = 0; s < XT_K / GT_KSLICE; ++s, ++it) {
                     const uint32_t stage = it % GT_STAGES;
                     mbar_wait(&empty[stage], ((it / GT_STAGES) & 1) ^ 1);
-                    uint8_t *dst = smem + GT_A_BYTES + stage * GT_STAGE_BYTES;
+                    uint8_t *dst = smem + stage * GT_STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[stage], GT_STAGE_BYTES);
                     bulk_g2s(dst, src + (size_t)s * GT_SLICE_BYTES, GT_SLICE_BYTES, &full[stage]);
                     bulk_g2s(dst + GT_SLICE_BYTES, src + XT_PLANE_BYTES + (size_t)s * GT_SLICE_BYTES,
@@ -396,8 +502,7 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
         // MMA issuer: operands kept in uniform registers (literal TMEM addresses, descriptors derived from the
         // constant dynamic-smem base, elect.sync predicate) - see the note in rec_tc_kernel.
         const uint32_t idesc = make_idesc_f16(128, XT_ROWS);
-        const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), H * 16, 128);
-        const uint64_t b_desc0 = make_smem_desc(smem_u32(smem + GT_A_BYTES), XT_ROWS * 16, 128);
+        const uint64_t b_desc0 = make_smem_desc(smem_u32(smem), XT_ROWS * 16, 128);
         if (tmem_base != 0u) {
             if (lane == 0) printf("mdk: unexpected TMEM base %u for a 512-column allocation\n", tmem_base);
             __trap();
@@ -412,8 +517,7 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
                 mbar_wait(&full[stage], (it / GT_STAGES) & 1);
                 tc_fence_after_sync();
                 if (elect_one()) {
-                    const uint32_t d = as * XT_ROWS;
-                    const uint64_t a_s = a_desc0 + (uint64_t)((s * (GT_KSLICE / 8) * (H * 16)) >> 4);
+                    const uint32_t d = GT_W_COLS + as * XT_ROWS;
                     const uint64_t b_s = b_desc0 + (uint64_t)((stage * GT_STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int prod = 0; prod < 3; ++prod) {
@@ -421,9 +525,9 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
                         const int pb = (prod == 1) ? 1 : 0;   // x part
 #pragma unroll
                         for (int ks = 0; ks < GT_KSLICE / 16; ++ks) {
-                            const uint64_t ad = a_s + (uint64_t)((pa * (H * H2 * 2) + ks * 2 * (H * 16)) >> 4);
+                            const uint32_t a_t = (uint32_t)((pa * (H2 / 16) + s * (GT_KSLICE / 16) + ks) * 8);
                             const uint64_t bd = b_s + (uint64_t)((pb * GT_SLICE_BYTES + ks * 2 * (XT_ROWS * 16)) >> 4);
-                            umma_f16(d, ad, bd, idesc, (s | prod | ks) ? 1u : 0u);
+                            umma_f16_ts(d, a_t, bd, idesc, (s | prod | ks) ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty[stage]);
@@ -441,7 +545,7 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
             const uint32_t as = tcount & 1;
             mbar_wait(&acc_full[as], (tcount >> 1) & 1);
             tc_fence_after_sync();
-            const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + as * XT_ROWS;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + GT_W_COLS + as * XT_ROWS;
             float *out = gi + (tile * XT_ROWS) * (int64_t)GI_COLS + blk * H + j;
             const int64_t prem = P - tile * XT_ROWS;
 #pragma unroll 1
@@ -466,7 +570,7 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
     }
 }
 
-cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tc, const float *bias, float *gi, int64_t P,
+cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const float *bias, float *gi, int64_t P,
                            int sm_count, cudaStream_t s) {
     if (P == 0) return cudaSuccess;
     const int64_t ntiles = (P + XT_ROWS - 1) / XT_ROWS;
@@ -480,7 +584,7 @@ cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tc, const flo
     if (ct < 1) ct = 1;
     if (ct > ntiles) ct = ntiles;
     dim3 grid((unsigned)ct, 6);
-    gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, s>>>(reinterpret_cast<const uint8_t *>(x_tiles), w_in_tc, bias, gi,
+    gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, s>>>(reinterpret_cast<const uint8_t *>(x_tiles), w_in_tm, bias, gi,
                                                      P, ntiles);
     return cudaGetLastError();
 }

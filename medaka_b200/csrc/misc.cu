@@ -355,7 +355,7 @@ cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b,
 __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const float *w_hh0, const float *w_hh1,
                                   const float *b_ih0, const float *b_ih1, const float *b_hh0, const float *b_hh1,
                                   int in_features, float *w_in_packed, float *bias_gi, float *b_hn, float *w_hh_t,
-                                  __half *w_hh_tc, __half *w_hh_tm, __half *w_in_tc) {
+                                  __half *w_hh_tm, __half *w_x_tm, __half *w_in_tc) {
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const float *w_ih[2] = {w_ih0, w_ih1}, *w_hh[2] = {w_hh0, w_hh1};
@@ -385,13 +385,23 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
         split_f16(v, hi, lo);
         const int g = c / H, j = c % H;
         const int64_t blk_halfs = (int64_t)H * H;   // 128x128 block
-        const int64_t off = (int64_t)(k / 8) * (H * 8) + j * 8 + (k % 8);
-        w_hh_tc[(((int64_t)d * 2 + 0) * 3 + g) * blk_halfs + off] = hi;
-        w_hh_tc[(((int64_t)d * 2 + 1) * 3 + g) * blk_halfs + off] = lo;
         w_hh_tm[(((int64_t)d * 2 + 0) * 3 + g) * blk_halfs + j * H + k] = hi;
         w_hh_tm[(((int64_t)d * 2 + 1) * 3 + g) * blk_halfs + j * H + k] = lo;
     }
-    if (w_in_tc) {   // layer 1: [blk = d*3+g][part][kg 32][row 128][8]
+    if (w_x_tm) {   // layer 0, in_features <= 16: [d][part][gate][row j][16], K zero-padded
+        for (int64_t i = tid; i < (int64_t)NDIR * G3 * 16; i += stride) {
+            const int d = (int)(i / (G3 * 16));
+            const int rem = (int)(i % (G3 * 16));
+            const int c = rem / 16, k = rem % 16;
+            const float v = (k < in_features) ? w_ih[d][(int64_t)c * in_features + k] : 0.f;
+            __half hi, lo;
+            split_f16(v, hi, lo);
+            const int g = c / H, j = c % H;
+            w_x_tm[((((int64_t)d * 2 + 0) * 3 + g) * H + j) * 16 + k] = hi;
+            w_x_tm[((((int64_t)d * 2 + 1) * 3 + g) * H + j) * 16 + k] = lo;
+        }
+    }
+    if (w_in_tc) {   // layer 1: [blk = dir*3+gate][part][row j][k] row-major
         for (int64_t i = tid; i < (int64_t)GI_COLS * H2; i += stride) {
             const int row = (int)(i / H2), k = (int)(i % H2);
             const int d = row / G3, r = row % G3;
@@ -400,9 +410,8 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
             split_f16(v, hi, lo);
             const int blk = row / H, j = row % H;
             const int64_t plane = (int64_t)H * H2;   // 128 x 256 halfs
-            const int64_t off = (int64_t)(k / 8) * (H * 8) + j * 8 + (k % 8);
-            w_in_tc[((int64_t)blk * 2 + 0) * plane + off] = hi;
-            w_in_tc[((int64_t)blk * 2 + 1) * plane + off] = lo;
+            w_in_tc[((int64_t)blk * 2 + 0) * plane + (int64_t)j * H2 + k] = hi;
+            w_in_tc[((int64_t)blk * 2 + 1) * plane + (int64_t)j * H2 + k] = lo;
         }
     }
 }
@@ -410,7 +419,7 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
 cudaError_t launch_prepare_layer(const LayerWeights &lw, int in_features, bool build_in_tc, cudaStream_t s) {
     pack_layer_kernel<<<296, 256, 0, s>>>(lw.w_ih[0], lw.w_ih[1], lw.w_hh[0], lw.w_hh[1], lw.b_ih[0], lw.b_ih[1],
                                           lw.b_hh[0], lw.b_hh[1], in_features, lw.w_in_packed, lw.bias_gi,
-                                          lw.b_hn, lw.w_hh_t, lw.w_hh_tc, lw.w_hh_tm, build_in_tc ? lw.w_in_tc : nullptr);
+                                          lw.b_hn, lw.w_hh_t, lw.w_hh_tm, lw.w_x_tm, build_in_tc ? lw.w_in_tc : nullptr);
     return cudaGetLastError();
 }
 

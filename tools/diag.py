@@ -88,10 +88,43 @@ def check_misc(arg):
     return res
 
 
-CHECKS = {"selftest": check_selftest, "forward": check_forward, "misc": check_misc}
+def check_determinism(arg):
+    """Same input through fresh engines / repeated calls must be bit-identical; locate oracle deviations."""
+    from medaka_b200 import models
+    from oracle import gru_oracle, synth
+    precision, B, T = arg.split(",")
+    B, T = int(B), int(T)
+    sd = synth.synth_state_dict(0)
+    feats = synth.synth_features(B, T, 10, seed=42)
+    man = gru_oracle.manual_forward(sd, feats)
+    res = {"runs": []}
+    first = None
+    for rep in range(4):
+        m = models.GRUModel(num_features=10)
+        m.load_state_dict(sd)
+        m.set_precision(precision)
+        for call in range(2):
+            out = m.forward_arrays(feats, want_logits=True)
+            h0 = m.read_activation(0)
+            d = np.abs(h0 - man["h0"])
+            idx = np.unravel_index(np.argmax(d), d.shape)
+            entry = {"rep": rep, "call": call, "dh0": float(d.max()), "argmax": [int(i) for i in idx],
+                     "n_bad": int((d > 1e-6).sum()),
+                     "bad_t0_fwd": int((d[:, 0, :128] > 1e-6).sum()), "bad_rows": sorted(set(np.where(d > 1e-6)[0].tolist()))[:10],
+                     "bad_units": sorted(set(np.where(d > 1e-6)[2].tolist()))[:16]}
+            if first is None:
+                first = h0.copy()
+            entry["same_as_first"] = bool(np.array_equal(first, h0))
+            res["runs"].append(entry)
+        m.close()
+    return res
+
+
+CHECKS = {"selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism}
 
 PLAN = [
-    ("selftest", "0"), ("selftest", "3"), ("selftest", "4"),
+    ("determinism", "tc,37,130"), ("determinism", "fp32,37,130"), ("determinism", "tc,200,300"),
+    ("selftest", "0"), ("selftest", "3"),
     ("forward", "tc,20,64"), ("forward", "tc,37,130"), ("forward", "tc,1200,24"), ("forward", "tc,3,1500"),
     ("forward", "tc,200,2000"), ("forward", "fp32,20,64"),
 ]
@@ -121,7 +154,7 @@ def main():
         except subprocess.TimeoutExpired:
             report[key] = {"error": "timeout"}
         report[key + ".s"] = round(time.time() - t0, 1)
-        print(key, json.dumps(report[key])[:600], flush=True)
+        print(key, json.dumps(report[key])[:3000], flush=True)
         with open(os.path.join(OUT, "diag.json"), "w") as fh:
             json.dump(report, fh, indent=1)
 
