@@ -297,45 +297,59 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1,
     float bias[NCLS];
 #pragma unroll
     for (int c = 0; c < NCLS; ++c) bias[c] = lin_b[c];
-    for (int64_t p = warp; p < P; p += nwarps) {
-        const float4 a = *reinterpret_cast<const float4 *>(h1 + p * H2 + lane * 8);
-        const float4 b = *reinterpret_cast<const float4 *>(h1 + p * H2 + lane * 8 + 4);
-        const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        float acc[NCLS];
+    // PU positions per warp iteration: all 2*PU 16-byte loads are issued before any is consumed, so each warp keeps
+    // 4 KiB in flight (the kernel is a pure 1 KiB/position HBM stream; one position at a time left it latency-bound
+    // at 2.6 TB/s)
+    constexpr int PU = 4;
+    for (int64_t pb = warp * PU; pb < P; pb += nwarps * PU) {
+        float4 va[PU], vb[PU];
 #pragma unroll
-        for (int c = 0; c < NCLS; ++c) {
-            float s = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) s = fmaf(x[i], w[c][i], s);
-            acc[c] = s;
+        for (int u = 0; u < PU; ++u) {
+            const int64_t p = min(pb + u, P - 1);
+            va[u] = ld_stream4(h1 + p * H2 + lane * 8);
+            vb[u] = ld_stream4(h1 + p * H2 + lane * 8 + 4);
         }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
+        for (int u = 0; u < PU; ++u) {
+            const int64_t p = pb + u;
+            const float x[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+            float acc[NCLS];
 #pragma unroll
-            for (int c = 0; c < NCLS; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
-        }
-        float l[NCLS];
-        float m = -INFINITY;
+            for (int c = 0; c < NCLS; ++c) {
+                float s = 0.f;
 #pragma unroll
-        for (int c = 0; c < NCLS; ++c) { l[c] = acc[c] + bias[c]; m = fmaxf(m, l[c]); }
-        float e[NCLS], sum = 0.f;
+                for (int i = 0; i < 8; ++i) s = fmaf(x[i], w[c][i], s);
+                acc[c] = s;
+            }
 #pragma unroll
-        for (int c = 0; c < NCLS; ++c) { e[c] = expf(l[c] - m); sum += e[c]; }
-        float pr[NCLS];
+            for (int off = 16; off > 0; off >>= 1) {
 #pragma unroll
-        for (int c = 0; c < NCLS; ++c) pr[c] = e[c] / sum;
-        if (lane < NCLS) {
-            float lv = l[0], pv = pr[0];
+                for (int c = 0; c < NCLS; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+            }
+            if (p >= P) continue;
+            float l[NCLS];
+            float m = -INFINITY;
 #pragma unroll
-            for (int c = 1; c < NCLS; ++c) if (lane == c) { lv = l[c]; pv = pr[c]; }
-            probs[p * NCLS + lane] = pv;
-            if (logits) logits[p * NCLS + lane] = lv;
-        }
-        if (labels && lane == 0) {
-            float best = pr[0]; int arg = 0;
+            for (int c = 0; c < NCLS; ++c) { l[c] = acc[c] + bias[c]; m = fmaxf(m, l[c]); }
+            float e[NCLS], sum = 0.f;
 #pragma unroll
-            for (int c = 1; c < NCLS; ++c) if (pr[c] > best) { best = pr[c]; arg = c; }
-            labels[p] = (uint8_t)arg;
+            for (int c = 0; c < NCLS; ++c) { e[c] = expf(l[c] - m); sum += e[c]; }
+            float pr[NCLS];
+#pragma unroll
+            for (int c = 0; c < NCLS; ++c) pr[c] = e[c] / sum;
+            if (lane < NCLS) {
+                float lv = l[0], pv = pr[0];
+#pragma unroll
+                for (int c = 1; c < NCLS; ++c) if (lane == c) { lv = l[c]; pv = pr[c]; }
+                probs[p * NCLS + lane] = pv;
+                if (logits) logits[p * NCLS + lane] = lv;
+            }
+            if (labels && lane == 0) {
+                float best = pr[0]; int arg = 0;
+#pragma unroll
+                for (int c = 1; c < NCLS; ++c) if (pr[c] > best) { best = pr[c]; arg = c; }
+                labels[p] = (uint8_t)arg;
+            }
         }
     }
 }
@@ -343,7 +357,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1,
 cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b, int64_t P, float *probs,
                         float *logits, uint8_t *labels, cudaStream_t s) {
     if (P == 0) return cudaSuccess;
-    int64_t blocks = (P + 7) / 8;              // 8 warps per block, 1 position per warp per iteration
+    int64_t blocks = (P + 31) / 32;            // 8 warps per block, 4 positions per warp per iteration
     if (blocks > 148 * 8) blocks = 148 * 8;    // persistent-ish grid: multiple of the SM count
     head_kernel<<<(unsigned)blocks, 256, 0, s>>>(h1, lin_w, lin_b, P, probs, logits, labels);
     return cudaGetLastError();

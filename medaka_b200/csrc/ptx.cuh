@@ -209,4 +209,12 @@ __device__ __forceinline__ float ldg_stream(const float *p) {
     return v;
 }
 
+__device__ __forceinline__ float4 ld_stream4(const float *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
 }  // namespace mdk
