@@ -309,26 +309,31 @@ def main():
     lm.check(lib.mdk_memcpy_d2h(dev, ffi.from_buffer(chk), d_probs, chk.nbytes))
     assert np.isfinite(chk).all() and abs(float(chk.sum(-1).mean()) - 1.0) < 1e-4
 
-    # ---- host-buffer leg ("e2e"): pinned H2D + forward + D2H of probs and labels per step ----
+    # ---- host-buffer leg ("e2e"): pinned H2D + forward + D2H of probs and labels EVERY step, through the
+    # reference-facing C-ABI call with host buffers (mdk_engine_submit / mdk_engine_wait, the asynchronous form of
+    # mdk_engine_forward that medaka_b200.prediction.run_prediction uses: two calls in flight, so the copies of
+    # neighbouring steps hide under the compute of the current one) ----
     h_feats = feats
-    h_probs = model.pinned("bench_probs", (B, T, 5), np.float32)
-    h_labels = model.pinned("bench_labels", (B, T), np.uint8)
+    h_probs = [model.pinned("bench_probs%d" % i, (B, T, 5), np.float32) for i in range(2)]
+    h_labels = [model.pinned("bench_labels%d" % i, (B, T), np.uint8) for i in range(2)]
 
-    def step_host():
-        lm.check(lib.mdk_engine_forward(eng, ffi.cast("const float *", ffi.from_buffer(h_feats)), B, T,
-                                        ffi.cast("float *", ffi.from_buffer(h_probs)), ffi.NULL,
-                                        ffi.cast("uint8_t *", ffi.from_buffer(h_labels))))
+    def run_host(n):
+        tickets = []
+        for k in range(n):
+            tickets.append(model.submit_arrays(h_feats, h_probs[k % 2], h_labels[k % 2]))
+            if k >= 1:
+                model.wait(tickets[k - 1])
+        model.wait(tickets[-1])
 
     log("host-buffer leg")
-    for _ in range(max(1, min(args.warmup, 2))):
-        step_host()
+    run_host(max(1, min(args.warmup, 2)))
     barrier()
     lm.check(lib.mdk_engine_timer_start(eng))
-    for _ in range(args.steps):
-        step_host()
+    run_host(args.steps)
     lm.check(lib.mdk_engine_timer_stop(eng, ms))
     barrier()
     e2e_ms = float(ms[0])
+    assert np.isfinite(h_probs[(args.steps - 1) % 2][:2]).all()
 
     if dist is not None:
         t = torch.tensor([dev_ms, e2e_ms], device="cuda")

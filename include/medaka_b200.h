@@ -115,6 +115,13 @@ int mdk_engine_reserve(mdk_engine *e, int64_t B, int64_t T);
  * non-NULL); returns when outputs are in host memory. */
 int mdk_engine_forward(mdk_engine *e, const float *feats_host, int64_t B, int64_t T,
                        float *probs_host, float *logits_host, uint8_t *labels_host);
+/* asynchronous form of the same call: returns once the work is queued (copy-in, compute and copy-out run on
+ * three streams chained by events, two I/O slots), so the H2D of batch k+1 and the D2H of batch k-1 overlap
+ * the compute of batch k.  Host buffers must stay valid (and should be page-locked) until mdk_engine_wait
+ * (ticket) returns.  At most 2 tickets are in flight; a third submit waits for the oldest. */
+int mdk_engine_submit(mdk_engine *e, const float *feats_host, int64_t B, int64_t T,
+                      float *probs_host, float *logits_host, uint8_t *labels_host, int64_t *ticket);
+int mdk_engine_wait(mdk_engine *e, int64_t ticket);
 /* same forward with DEVICE buffers (inputs resident in HBM); asynchronous on the engine stream,
  * complete after mdk_engine_sync(). */
 int mdk_engine_forward_dev(mdk_engine *e, const float *feats_dev, int64_t B, int64_t T,

@@ -100,13 +100,18 @@ static int ensure_io(mdk_engine *e, int64_t B, int64_t T) {
     const int64_t feats = P * e->desc.num_features;
     if (P <= e->cap_io && feats <= e->cap_feats_floats) return MDK_OK;
     MDK_CUDA(cudaStreamSynchronize(e->stream));
-    dev_free(e->d_feats); dev_free(e->d_probs); dev_free(e->d_logits); dev_free(e->d_labels);
+    MDK_CUDA(cudaStreamSynchronize(e->copy_in));
+    MDK_CUDA(cudaStreamSynchronize(e->copy_out));
     e->cap_io = 0; e->cap_feats_floats = 0;
-    int rc;
-    if ((rc = dev_alloc(&e->d_feats, (size_t)feats))) return rc;
-    if ((rc = dev_alloc(&e->d_probs, (size_t)P * NCLS))) return rc;
-    if ((rc = dev_alloc(&e->d_logits, (size_t)P * NCLS))) return rc;
-    if ((rc = dev_alloc(&e->d_labels, (size_t)P))) return rc;
+    for (auto &sl : e->io) {
+        dev_free(sl.d_feats); dev_free(sl.d_probs); dev_free(sl.d_logits); dev_free(sl.d_labels);
+        sl.busy = false;
+        int rc;
+        if ((rc = dev_alloc(&sl.d_feats, (size_t)feats))) return rc;
+        if ((rc = dev_alloc(&sl.d_probs, (size_t)P * NCLS))) return rc;
+        if ((rc = dev_alloc(&sl.d_logits, (size_t)P * NCLS))) return rc;
+        if ((rc = dev_alloc(&sl.d_labels, (size_t)P))) return rc;
+    }
     e->cap_io = P; e->cap_feats_floats = feats;
     return MDK_OK;
 }
@@ -265,6 +270,13 @@ int mdk_engine_create(int device, const mdk_model_desc *desc, mdk_engine **out) 
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
     for (auto &set : e->evr) for (auto &ev : set) cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
+    for (auto &sl : e->io) {
+        cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming);
+    }
     for (auto &ev : e->ev_timer) cudaEventCreate(&ev);
     *out = e;
     return MDK_OK;
@@ -283,7 +295,14 @@ int mdk_engine_destroy(mdk_engine *e) {
     dev_free(e->lin_w); dev_free(e->lin_b);
     dev_free(e->gi); dev_free(e->h1);
     if (e->h0) cudaFree(e->h0);
-    dev_free(e->d_feats); dev_free(e->d_probs); dev_free(e->d_logits); dev_free(e->d_labels);
+    for (auto &sl : e->io) {
+        dev_free(sl.d_feats); dev_free(sl.d_probs); dev_free(sl.d_logits); dev_free(sl.d_labels);
+        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
+        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+        if (sl.ev_out) cudaEventDestroy(sl.ev_out);
+    }
+    if (e->copy_in) cudaStreamDestroy(e->copy_in);
+    if (e->copy_out) cudaStreamDestroy(e->copy_out);
     for (auto &set : e->evr) for (auto &ev : set) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ev_timer) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(e->stream);
@@ -355,35 +374,72 @@ int mdk_engine_forward_dev(mdk_engine *e, const float *feats_dev, int64_t B, int
     return MDK_OK;
 }
 
-int mdk_engine_forward(mdk_engine *e, const float *feats_host, int64_t B, int64_t T, float *probs_host,
-                       float *logits_host, uint8_t *labels_host) {
+int mdk_engine_submit(mdk_engine *e, const float *feats_host, int64_t B, int64_t T, float *probs_host,
+                      float *logits_host, uint8_t *labels_host, int64_t *ticket) {
     int rc;
     if ((rc = check_shapes(e, feats_host, B, T, probs_host))) return rc;
+    MDK_REQUIRE(ticket, MDK_ERR_ARG, "submit: ticket is NULL");
     MDK_CUDA(cudaSetDevice(e->device));
     if ((rc = ensure_io(e, B, T))) return rc;
     const int64_t P = B * T;
+    mdk_engine::IoSlot &sl = e->io[e->submit_count % mdk_engine::IO_SLOTS];
+    if (sl.busy) {   // the slot's previous result must have left the device before its buffers are reused
+        MDK_CUDA(cudaEventSynchronize(sl.ev_out));
+        sl.busy = false;
+    }
     cudaStream_t s = e->stream;
     e->ev = e->evr[e->fwd_count % mdk_engine::EV_RING];
     e->fwd_count++;
     MDK_CUDA(cudaEventRecord(e->ev[0], s));
-    MDK_CUDA(cudaMemcpyAsync(e->d_feats, feats_host, (size_t)P * e->desc.num_features * sizeof(float),
-                             cudaMemcpyHostToDevice, s));
-    if ((rc = run_forward(e, e->d_feats, B, T, e->d_probs, logits_host ? e->d_logits : nullptr,
-                          labels_host ? e->d_labels : nullptr)))
+    // copy-in stream: features H2D (asynchronous when feats_host is page-locked)
+    MDK_CUDA(cudaMemcpyAsync(sl.d_feats, feats_host, (size_t)P * e->desc.num_features * sizeof(float),
+                             cudaMemcpyHostToDevice, e->copy_in));
+    MDK_CUDA(cudaEventRecord(sl.ev_in, e->copy_in));
+    MDK_CUDA(cudaStreamWaitEvent(s, sl.ev_in, 0));
+    if ((rc = run_forward(e, sl.d_feats, B, T, sl.d_probs, logits_host ? sl.d_logits : nullptr,
+                          labels_host ? sl.d_labels : nullptr)))
         return rc;
-    MDK_CUDA(cudaMemcpyAsync(probs_host, e->d_probs, (size_t)P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (logits_host)
-        MDK_CUDA(cudaMemcpyAsync(logits_host, e->d_logits, (size_t)P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (labels_host) MDK_CUDA(cudaMemcpyAsync(labels_host, e->d_labels, (size_t)P, cudaMemcpyDeviceToHost, s));
+    MDK_CUDA(cudaEventRecord(sl.ev_done, s));
     MDK_CUDA(cudaEventRecord(e->ev[7], s));
-    MDK_CUDA(cudaStreamSynchronize(s));
+    // copy-out stream: results D2H
+    MDK_CUDA(cudaStreamWaitEvent(e->copy_out, sl.ev_done, 0));
+    MDK_CUDA(cudaMemcpyAsync(probs_host, sl.d_probs, (size_t)P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, e->copy_out));
+    if (logits_host)
+        MDK_CUDA(cudaMemcpyAsync(logits_host, sl.d_logits, (size_t)P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, e->copy_out));
+    if (labels_host) MDK_CUDA(cudaMemcpyAsync(labels_host, sl.d_labels, (size_t)P, cudaMemcpyDeviceToHost, e->copy_out));
+    MDK_CUDA(cudaEventRecord(sl.ev_out, e->copy_out));
+    sl.busy = true;
+    *ticket = e->submit_count++;
     return MDK_OK;
+}
+
+int mdk_engine_wait(mdk_engine *e, int64_t ticket) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
+    MDK_REQUIRE(ticket >= 0 && ticket < e->submit_count, MDK_ERR_ARG, "wait: unknown ticket");
+    if (ticket < e->submit_count - mdk_engine::IO_SLOTS)
+        return MDK_OK;   // older than the slots in flight: already waited on when its slot was reused
+    MDK_CUDA(cudaSetDevice(e->device));
+    mdk_engine::IoSlot &sl = e->io[ticket % mdk_engine::IO_SLOTS];
+    MDK_CUDA(cudaEventSynchronize(sl.ev_out));
+    sl.busy = false;
+    return MDK_OK;
+}
+
+int mdk_engine_forward(mdk_engine *e, const float *feats_host, int64_t B, int64_t T, float *probs_host,
+                       float *logits_host, uint8_t *labels_host) {
+    int64_t ticket = -1;
+    int rc = mdk_engine_submit(e, feats_host, B, T, probs_host, logits_host, labels_host, &ticket);
+    if (rc) return rc;
+    return mdk_engine_wait(e, ticket);
 }
 
 int mdk_engine_sync(mdk_engine *e) {
     MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
     MDK_CUDA(cudaSetDevice(e->device));
+    MDK_CUDA(cudaStreamSynchronize(e->copy_in));
     MDK_CUDA(cudaStreamSynchronize(e->stream));
+    MDK_CUDA(cudaStreamSynchronize(e->copy_out));
+    for (auto &sl : e->io) sl.busy = false;
     return MDK_OK;
 }
 
@@ -431,6 +487,9 @@ int mdk_engine_timer_start(mdk_engine *e) {
 int mdk_engine_timer_stop(mdk_engine *e, float *elapsed_ms) {
     MDK_REQUIRE(e && elapsed_ms, MDK_ERR_ARG, "NULL argument");
     MDK_CUDA(cudaSetDevice(e->device));
+    // the end event must follow every copy-out still in flight, not just the compute stream
+    for (auto &sl : e->io)
+        if (sl.busy) MDK_CUDA(cudaStreamWaitEvent(e->stream, sl.ev_out, 0));
     MDK_CUDA(cudaEventRecord(e->ev_timer[1], e->stream));
     MDK_CUDA(cudaEventSynchronize(e->ev_timer[1]));
     MDK_CUDA(cudaEventElapsedTime(elapsed_ms, e->ev_timer[0], e->ev_timer[1]));

@@ -83,10 +83,18 @@ struct mdk_engine {
     float *gi = nullptr;       // [cap_pos][768]
     void *h0 = nullptr;        // fp32 [cap_pos][256]  or  fp16 hi/lo tiles (same byte size)
     float *h1 = nullptr;       // [cap_pos][256]
-    // staging for the host-buffer API
+    // staging for the host-buffer API: two I/O slots so the H2D of call k+1 and the D2H of call k-1 overlap
+    // the compute of call k (copy-in / compute / copy-out streams chained by events)
+    static constexpr int IO_SLOTS = 2;
+    struct IoSlot {
+        float *d_feats = nullptr, *d_probs = nullptr, *d_logits = nullptr;
+        uint8_t *d_labels = nullptr;
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+        bool busy = false;
+    } io[IO_SLOTS];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    int64_t submit_count = 0;
     int64_t cap_io = 0;
-    float *d_feats = nullptr, *d_probs = nullptr, *d_logits = nullptr;
-    uint8_t *d_labels = nullptr;
     int64_t cap_feats_floats = 0;
     mdk_timings last{};
     int64_t launches = 0;

@@ -219,6 +219,52 @@ class GRUModel(object):
         return ForwardOutput(probs.copy(), logits.copy() if want_logits else None,
                              labels.copy() if want_labels else None)
 
+    def submit_arrays(self, feats_pinned, probs_out, labels_out=None, logits_out=None):
+        """Queue one forward on host arrays WITHOUT waiting (mdk_engine_submit); returns a ticket for ``wait``.
+
+        All arrays must stay alive and untouched until ``wait(ticket)``; page-locked arrays (``pinned``)
+        make the copies asynchronous so consecutive calls overlap H2D, compute and D2H.
+        """
+        B, T, F = feats_pinned.shape
+        lib, ffi = _lm.lib, _lm.ffi
+        ticket = ffi.new("int64_t *")
+        _lm.check(lib.mdk_engine_submit(
+            self._engine, ffi.cast("const float *", ffi.from_buffer(feats_pinned)), B, T,
+            ffi.cast("float *", ffi.from_buffer(probs_out)),
+            ffi.cast("float *", ffi.from_buffer(logits_out)) if logits_out is not None else ffi.NULL,
+            ffi.cast("uint8_t *", ffi.from_buffer(labels_out)) if labels_out is not None else ffi.NULL, ticket))
+        self._last_shape = (B, T)
+        return int(ticket[0])
+
+    def wait(self, ticket):
+        _lm.check(_lm.lib.mdk_engine_wait(self._engine, ticket))
+
+    def predict_async(self, batch):
+        """Asynchronous predict_on_batch: returns a handle whose ``result()`` is the CPU tensor [B,T,5].
+
+        Two calls may be in flight; ``run_prediction`` uses this with a one-batch look-ahead so the PCIe copies of
+        neighbouring batches hide under the compute of the current one.
+        """
+        import torch
+        x = _as_f32(self.get_model_input_features(batch))
+        B, T, F = x.shape
+        slot = getattr(self, "_async_n", 0) % 2
+        self._async_n = getattr(self, "_async_n", 0) + 1
+        xin = self.pinned("afeats%d" % slot, (B, T, F), np.float32)
+        np.copyto(xin, x)
+        probs = self.pinned("aprobs%d" % slot, (B, T, 5), np.float32)
+        labels = self.pinned("alabels%d" % slot, (B, T), np.uint8)
+        ticket = self.submit_arrays(xin, probs, labels)
+        model = self
+
+        class _Handle(object):
+            def result(self_inner):
+                model.wait(ticket)
+                model.last_labels = labels.copy()
+                return torch.from_numpy(probs.copy())
+
+        return _Handle()
+
     def forward(self, x):
         """gru.py:58-72 on host tensors: returns probabilities (or logits if normalise is off)."""
         import torch

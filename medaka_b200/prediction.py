@@ -136,14 +136,28 @@ def run_prediction(output, bam, regions, model, feature_encoder, chunk_len, chun
     logger.info("Running inference for {:.1f}M draft bases.".format(total_region_mbases))
     n_batches, n_positions = 0, 0
     t0 = now()
+    def _store(ds, data, batch, class_probs):
+        for sample, prob, feat in zip(data, class_probs, batch.features):
+            feats = feat if save_features else None
+            ds.write_sample(sample.amend(label_probs=prob, features=feats))
+
     with datastore.DataStore(output, 'a') as ds:
+        # one-batch look-ahead: batch k+1 is queued on the engine (copy-in + compute) before the results of
+        # batch k are collected, so PCIe traffic and the HDF writer overlap the GPU work
+        pending = None
+        use_async = hasattr(model, "predict_async")
         for data, batch in loader:
             n_batches += 1
-            class_probs = model.predict_on_batch(batch)
-            for sample, prob, feat in zip(data, class_probs, batch.features):
-                feats = feat if save_features else None
-                ds.write_sample(sample.amend(label_probs=prob, features=feats))
             n_positions += int(batch.features.shape[0]) * int(batch.features.shape[1])
+            if not use_async:
+                _store(ds, data, batch, model.predict_on_batch(batch))
+                continue
+            handle = model.predict_async(batch)
+            if pending is not None:
+                _store(ds, pending[0], pending[1], pending[2].result())
+            pending = (data, batch, handle)
+        if pending is not None:
+            _store(ds, pending[0], pending[1], pending[2].result())
     dt = max(now() - t0, 1e-9)
     logger.info("Processed {} batches, {} positions in {:.2f}s ({:.3e} positions/s)".format(
         n_batches, n_positions, dt, n_positions / dt))

@@ -117,16 +117,21 @@ def check_determinism(arg):
             entry["same_as_first"] = bool(np.array_equal(first, h0))
             res["runs"].append(entry)
         m.close()
+    man2 = gru_oracle.manual_forward(sd, feats)
+    res["oracle_stable"] = bool(np.array_equal(man["h0"], man2["h0"]))
+    res["oracle_drift"] = float(np.abs(man["h0"] - man2["h0"]).max())
+    import torch
+    res["torch_threads"] = torch.get_num_threads()
     return res
 
 
 CHECKS = {"selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism}
 
 PLAN = [
-    ("determinism", "tc,37,130"), ("determinism", "fp32,37,130"), ("determinism", "tc,200,300"),
+    ("determinism", "fp32,20,64"), ("determinism", "fp32,37,130"), ("determinism", "tc,200,300"),
     ("selftest", "0"), ("selftest", "3"),
     ("forward", "tc,20,64"), ("forward", "tc,37,130"), ("forward", "tc,1200,24"), ("forward", "tc,3,1500"),
-    ("forward", "tc,200,2000"), ("forward", "fp32,20,64"),
+    ("forward", "tc,200,2000"), ("forward", "fp32,20,64"), ("determinism", "fp32,20,64"), ("forward", "fp32,20,64"),
 ]
 
 
