@@ -79,8 +79,9 @@ static int prepare_weights(mdk_engine *e) {
 }
 
 static int ensure_workspace(mdk_engine *e, int64_t B, int64_t T) {
-    const int64_t P = B * T;
-    const int64_t need = ((P + XT_ROWS - 1) / XT_ROWS) * XT_ROWS;
+    // rows of the tile-interleaved intermediates (>= B*T: the last window tile is padded to 16 windows)
+    const int64_t rows = tiled_rows(B, T);
+    const int64_t need = ((rows + XT_ROWS - 1) / XT_ROWS) * XT_ROWS;
     if (need <= e->cap_pos) return MDK_OK;
     MDK_CUDA(cudaStreamSynchronize(e->stream));
     dev_free(e->gi);
@@ -130,7 +131,7 @@ static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t
     MDK_CUDA(cudaEventRecord(e->ev[1], s));
     if (!fuse_x) {
         MDK_CUDA(launch_inproj0(feats_dev, e->layer[0].w_in_packed, e->layer[0].bias_gi, e->gi, P,
-                                e->desc.num_features, s));
+                                e->desc.num_features, T, tc ? 1 : 0, s));
         launches++;
     }
     MDK_CUDA(cudaEventRecord(e->ev[2], s));
@@ -143,7 +144,7 @@ static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t
     }
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[3], s));
-    if (tc) MDK_CUDA(launch_gemm_tc(e->h0, e->layer[1].w_in_tc, e->layer[1].bias_gi, e->gi, P, e->sm_count, s));
+    if (tc) MDK_CUDA(launch_gemm_tc(e->h0, e->layer[1].w_in_tc, e->layer[1].bias_gi, e->gi, tiled_rows(B, T), e->sm_count, s));
     else MDK_CUDA(launch_gemm_fp32((const float *)e->h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, e->gi, P, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[4], s));
@@ -151,7 +152,7 @@ static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t
     else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[1].w_hh_t, e->layer[1].b_hn, e->h1, B, T, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[5], s));
-    MDK_CUDA(launch_head(e->h1, e->lin_w, e->lin_b, P, probs_dev, logits_dev, labels_dev, s));
+    MDK_CUDA(launch_head(e->h1, e->lin_w, e->lin_b, B, T, tc ? 1 : 0, probs_dev, logits_dev, labels_dev, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[6], s));
     e->launches += launches;
@@ -503,19 +504,20 @@ int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_
     MDK_REQUIRE(P > 0 && n_floats == P * H2, MDK_ERR_ARG, "read_activation: size must be B*T*256 of the last forward");
     MDK_CUDA(cudaSetDevice(e->device));
     MDK_CUDA(cudaStreamSynchronize(e->stream));
-    if (which == 1) {
-        MDK_CUDA(cudaMemcpy(out_host, e->h1, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
-    } else if (e->last_precision == MDK_PREC_FP32) {
-        MDK_CUDA(cudaMemcpy(out_host, e->h0, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    if (e->last_precision == MDK_PREC_FP32) {
+        MDK_CUDA(cudaMemcpy(out_host, which == 1 ? (const void *)e->h1 : (const void *)e->h0,
+                            (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
     } else {
+        // tensor-core path: rows are tile-interleaved (and layer 0 is stored as fp16 hi/lo operand tiles)
         float *tmp = nullptr;
         MDK_CUDA(cudaMalloc(&tmp, (size_t)n_floats * sizeof(float)));
-        cudaError_t err = launch_unpack_h0(e->h0, tmp, P, e->stream);
+        cudaError_t err = which == 0 ? launch_unpack_h0(e->h0, tmp, e->last_B, e->last_T, e->stream)
+                                     : launch_untile_rows(e->h1, tmp, e->last_B, e->last_T, e->stream);
         if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
         if (err == cudaSuccess) err = cudaMemcpy(out_host, tmp, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost);
         cudaFree(tmp);
         e->launches++;
-        if (err != cudaSuccess) return cuda_fail(err, "unpack_h0", __FILE__, __LINE__);
+        if (err != cudaSuccess) return cuda_fail(err, "read_activation", __FILE__, __LINE__);
     }
     return MDK_OK;
 }

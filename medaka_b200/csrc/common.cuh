@@ -42,6 +42,15 @@ constexpr int XT_K = H2;                           // 256
 constexpr int XT_PLANE_BYTES = XT_ROWS * XT_K * 2; // one plane (hi or lo) of a tile: 64 KiB
 constexpr int XT_TILE_BYTES = 2 * XT_PLANE_BYTES;  // hi plane then lo plane
 
+// Tile-interleaved row order of the tensor-core path's intermediates (gi, h0 tiles, h1): windows are grouped in
+// tiles of WT = 16 (the recurrent kernel's N) and rows run  p' = ((w / 16) * T + t) * 16 + w % 16 , i.e. the 16
+// windows of a tile are adjacent for a given time step.  A thread's windows are then `base + c * const` apart
+// (immediate offsets, no per-element address arithmetic, no ragged-edge predicates: padding windows are real rows
+// that are simply never copied out), and one tile-step of gi is a single contiguous 48 KiB block.
+constexpr int WT = 16;
+__host__ __device__ inline int64_t tiled_rows(int64_t B, int64_t T) { return ((B + WT - 1) / WT) * WT * T; }
+__host__ __device__ inline int64_t tiled_row(int64_t w, int64_t t, int64_t T) { return ((w / WT) * T + t) * WT + (w % WT); }
+
 struct LayerWeights {
     // fp32 originals (device), torch layout
     float *w_ih[NDIR] = {nullptr, nullptr};  // [3H][in]
@@ -106,17 +115,19 @@ namespace mdk {
 
 // ---- launchers (each returns cudaGetLastError() of its launch) -------------------------------
 // misc.cu
+// tiled != 0: gi rows are written / h1 rows are read in tile-interleaved order (T = window length)
 cudaError_t launch_inproj0(const float *feats, const float *w_packed, const float *bias, float *gi,
-                           int64_t P, int F, cudaStream_t s);
-cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b, int64_t P, float *probs,
-                        float *logits, uint8_t *labels, cudaStream_t s);
+                           int64_t P, int F, int64_t T, int tiled, cudaStream_t s);
+cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b, int64_t B, int64_t T, int tiled,
+                        float *probs, float *logits, uint8_t *labels, cudaStream_t s);
+cudaError_t launch_untile_rows(const float *src_tiled, float *dst, int64_t B, int64_t T, cudaStream_t s);
 cudaError_t launch_normalise(const uint64_t *counts, const int64_t *major, const int64_t *minor, int64_t n,
                              int num_dtypes, int mode, int sym_indels, float *feats, int64_t *depth,
                              cudaStream_t s);
 cudaError_t launch_decode(const float *probs, int64_t n, uint8_t *labels, uint8_t *quals, cudaStream_t s);
 cudaError_t launch_decode_f64(const double *probs, int64_t n, uint8_t *labels, uint8_t *quals, cudaStream_t s);
 cudaError_t launch_prepare_layer(const LayerWeights &lw, int in_features, bool build_in_tc, cudaStream_t s);
-cudaError_t launch_unpack_h0(const void *h0_tiles, float *out, int64_t P, cudaStream_t s);
+cudaError_t launch_unpack_h0(const void *h0_tiles, float *out, int64_t B, int64_t T, cudaStream_t s);
 // gru_fp32.cu
 cudaError_t launch_rec_fp32(const float *gi, const float *w_hh_t, const float *b_hn, float *h_out, int64_t B,
                             int64_t T, cudaStream_t s);

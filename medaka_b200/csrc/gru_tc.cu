@@ -234,62 +234,71 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         }
     } else {
         // ================= gate warps =================
+        // All intermediates use the tile-interleaved row order (common.cuh): row(w, t) = ((w/16)*T + t)*16 + w%16,
+        // so this thread's NC windows are NC consecutive rows: every address below is `step base + constant`.
+        // Padding windows of a ragged last tile are ordinary rows (never copied out), hence no predicates.
         const int grp = warp >> 2;                             // column group 0..3
         const int tile = (NT == 2) ? (grp >> 1) : 0;
         constexpr int NC = (NT == 2) ? 8 : 4;                  // windows (TMEM columns) per thread
+        constexpr int NP = NC / 2;                             // ... processed as packed fp32 pairs
         const int col0 = (NT == 2) ? (grp & 1) * 8 : grp * 4;
         const int j = (warp & 3) * 32 + lane;                  // hidden unit == TMEM lane
         const uint32_t t_lane = ((uint32_t)((warp & 3) * 32) << 16) + L::acc_col0 + (uint32_t)(tile * L::acc_per_tile + col0);
-        const float bhn = b_hn[dir * H + j];
-        const int64_t wbase = win0 + tile * RT_N + col0;       // first window of this thread's columns
-        // bit c set <=> column c is a real window (only the last tile of the batch is ragged)
-        uint32_t okmask = 0;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) okmask |= ((wbase + c) < B ? 1u : 0u) << c;
+        const int64_t wtile = blockIdx.x * NT + tile;          // window tile (16 windows) of this warp group
+        // NT == 2 with an odd number of window tiles: the last CTA's second tile does not exist - it still runs the
+        // barrier protocol (on zeros) but must not touch global memory
+        const bool tile_ok = wtile * WT < B;
         uint8_t *hrow = smem + L::h_off + tile * 2 * RT_HPLANE + (j >> 3) * RT_KG + (j & 7) * 2 + col0 * 16;
         const int kcol = dir * H + j;
-        // output bases (element units)
-        float *o32 = reinterpret_cast<float *>(h_out) + (wbase * T) * H2 + kcol;                       // fp32 [p][256]
-        __half *o16 = reinterpret_cast<__half *>(h_out) + (int64_t)(kcol >> 3) * (XT_ROWS * 8) + (kcol & 7);   // tiles
+        const int64_t row0 = (wtile * T) * WT + col0;          // row of (column 0, t = 0); row(t) = row0 + t*16
+        const int64_t tstep = dir ? -(int64_t)WT : (int64_t)WT;   // rows per time step, signed by direction
+        const int64_t t_first = dir ? (T - 1) : 0;
 
         // unfused path: pre-activations from the gi buffer, prefetched one step ahead into registers
-        const int64_t gstride = T * (int64_t)GI_COLS;          // floats between consecutive windows, same t
-        const float *gwin = FUSE_X ? nullptr : gi + (wbase * T) * GI_COLS + (int64_t)dir * G3 + j;
-        float g[3][NC];
-        // fused path: folded biases, and this thread's share of the x_t staging (160 values per tile-step)
-        float b_r = 0.f, b_z = 0.f, b_n = 0.f;
+        const float *gptr = FUSE_X ? nullptr : gi + (row0 + t_first * WT) * GI_COLS + (int64_t)dir * G3 + j;
+        F2 g2[3][NP];
+        // fused path: folded biases, and this thread's share of the x_t staging (16 x F values per tile-step)
+        const F2 bhn2 = f2_make(b_hn[dir * H + j], b_hn[dir * H + j]);
+        F2 br2 = f2_make(0.f, 0.f), bz2 = br2, bn2 = br2;
         const int tix = (NT == 2) ? (tid & 255) : tid;         // thread index within the tile's gate warps
         const int xF = FUSE_X ? xin.F : 1;                     // 1 <= F <= 16 on the fused path
         const int xn = tix / xF, xf = tix - xn * xF;           // window row / feature of the staged value
         const bool xown = FUSE_X && tix < RT_N * xF;
-        const bool xok = xown && (win0 + tile * RT_N + xn) < B;
+        const bool xok = xown && (wtile * WT + xn) < B;
         const float *xsrc = nullptr;
         uint8_t *xdst = nullptr;
         float xreg = 0.f;
         if (FUSE_X) {
-            b_r = xin.bias[dir * G3 + j];
-            b_z = xin.bias[dir * G3 + H + j];
-            b_n = xin.bias[dir * G3 + 2 * H + j];
+            br2 = f2_make(xin.bias[dir * G3 + j], xin.bias[dir * G3 + j]);
+            bz2 = f2_make(xin.bias[dir * G3 + H + j], xin.bias[dir * G3 + H + j]);
+            bn2 = f2_make(xin.bias[dir * G3 + 2 * H + j], xin.bias[dir * G3 + 2 * H + j]);
             if (xown) {
-                xsrc = xin.feats + ((win0 + tile * RT_N + xn) * T) * xin.F + xf;
+                xsrc = xin.feats + ((wtile * WT + xn) * T) * xin.F + xf;
                 xdst = smem + L::x_off + tile * 2 * RT_XBUF + (xf >> 3) * RT_KG + xn * 16 + (xf & 7) * 2;
             }
         }
+        // output pointers at (column 0, first time step); advanced by a constant every step
+        float *o32 = reinterpret_cast<float *>(h_out) + (row0 + t_first * WT) * H2 + kcol;
+        int64_t orow = row0 + t_first * WT;                    // OUT_TILES: row -> (tile, row in tile)
+        __half *o16 = reinterpret_cast<__half *>(h_out) + (int64_t)(kcol >> 3) * (XT_ROWS * 8) + (kcol & 7);
 
-        float hprev[NC];
+        const F2 one2 = f2_make(1.0f, 1.0f), neg2 = f2_make(-2.0f, -2.0f), negone2 = f2_make(-1.0f, -1.0f);
+        const F2 knl2 = f2_make(-1.4426950408889634f, -1.4426950408889634f);     // -log2(e)
+        const F2 k2l2 = f2_make(2.8853900817779268f, 2.8853900817779268f);       // 2 log2(e)
+        F2 hprev2[NP];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) hprev[c] = 0.f;
+        for (int q = 0; q < NP; ++q) hprev2[q] = f2_make(0.f, 0.f);
         if (!FUSE_X) {
-            const float *gt = gwin + (dir ? (T - 1) : 0) * (int64_t)GI_COLS;
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
+            for (int q = 0; q < NP; ++q)
 #pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    g[q][c] = ((okmask >> c) & 1u) ? ldg_stream(gt + c * gstride + q * H) : 0.f;
-            }
+                for (int gt = 0; gt < 3; ++gt)
+                    g2[gt][q] = tile_ok ? f2_make(ldg_stream(gptr + (2 * q) * GI_COLS + gt * H),
+                                                  ldg_stream(gptr + (2 * q + 1) * GI_COLS + gt * H))
+                                        : f2_make(0.f, 0.f);
         } else if (xown) {
             // x of step 0 -> buffer 0; x of step 1 -> register
-            const float x0 = xok ? xsrc[(dir ? (T - 1) : 0) * (int64_t)xin.F] : 0.f;
+            const float x0 = xok ? xsrc[t_first * (int64_t)xin.F] : 0.f;
             __half hi, lo;
             split_f16(x0, hi, lo);
             *reinterpret_cast<__half *>(xdst) = hi;
@@ -302,63 +311,92 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         mbar_arrive(&h_ready[tile]);
 
         for (int64_t step = 0; step < T; ++step) {
-            const int64_t t = dir ? (T - 1 - step) : step;
             const bool more = step + 1 < T;
-            const float *gnext = FUSE_X ? nullptr : gwin + (dir ? (t - 1) : (t + 1)) * (int64_t)GI_COLS;
-            const int64_t p0 = wbase * T + t;                                           // position of column 0
             mbar_wait(&acc_ready[tile], (uint32_t)(step & 1));
             tc_fence_after_sync();
-            {
-                uint32_t ar[NC], az[NC], an[NC], ax[NC];
-                if constexpr (NC == 8) {
-                    tmem_ld_x8(t_lane + 0 * 16, ar);
-                    tmem_ld_x8(t_lane + 1 * 16, az);
-                    tmem_ld_x8(t_lane + 2 * 16, an);
-                    if (FUSE_X) tmem_ld_x8(t_lane + 3 * 16, ax);
+            uint32_t ar[NC], az[NC], an[NC], ax[NC];
+            if constexpr (NC == 8) {
+                tmem_ld_x8(t_lane + 0 * 16, ar);
+                tmem_ld_x8(t_lane + 1 * 16, az);
+                tmem_ld_x8(t_lane + 2 * 16, an);
+                if (FUSE_X) tmem_ld_x8(t_lane + 3 * 16, ax);
+            } else {
+                tmem_ld_x4(t_lane + 0 * 16, ar);
+                tmem_ld_x4(t_lane + 1 * 16, az);
+                tmem_ld_x4(t_lane + 2 * 16, an);
+                if (FUSE_X) tmem_ld_x4(t_lane + 3 * 16, ax);
+            }
+            tmem_ld_wait();
+            if (!FUSE_X) gptr += tstep * GI_COLS;          // rows of the next time step
+            __half *tb = nullptr;
+            if (OUT_TILES) tb = o16 + (orow >> 7) * (int64_t)(XT_TILE_BYTES / 2) + (orow & (XT_ROWS - 1)) * 8;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const F2 accr = f2_make(__uint_as_float(ar[2 * q]), __uint_as_float(ar[2 * q + 1]));
+                const F2 accz = f2_make(__uint_as_float(az[2 * q]), __uint_as_float(az[2 * q + 1]));
+                const F2 accn = f2_make(__uint_as_float(an[2 * q]), __uint_as_float(an[2 * q + 1]));
+                F2 pre_r, pre_z, gin;
+                if (FUSE_X) {
+                    pre_r = f2_add(br2, accr);
+                    pre_z = f2_add(bz2, accz);
+                    gin = f2_add(bn2, f2_make(__uint_as_float(ax[2 * q]), __uint_as_float(ax[2 * q + 1])));
                 } else {
-                    tmem_ld_x4(t_lane + 0 * 16, ar);
-                    tmem_ld_x4(t_lane + 1 * 16, az);
-                    tmem_ld_x4(t_lane + 2 * 16, an);
-                    if (FUSE_X) tmem_ld_x4(t_lane + 3 * 16, ax);
+                    pre_r = f2_add(g2[0][q], accr);
+                    pre_z = f2_add(g2[1][q], accz);
+                    gin = g2[2][q];
                 }
-                tmem_ld_wait();
+                // r = sigmoid(pre_r), z = sigmoid(pre_z) with one reciprocal per element: 1/((1+e^-a)(1+e^-b))
+                float a0, a1, b0, b1;
+                f2_get(f2_mul(pre_r, knl2), a0, a1);
+                f2_get(f2_mul(pre_z, knl2), b0, b1);
+                const F2 ea = f2_add(f2_make(ex2_approx(fminf(a0, 60.0f)), ex2_approx(fminf(a1, 60.0f))), one2);
+                const F2 eb = f2_add(f2_make(ex2_approx(fminf(b0, 60.0f)), ex2_approx(fminf(b1, 60.0f))), one2);
+                float p0, p1;
+                f2_get(f2_mul(ea, eb), p0, p1);
+                const F2 inv = f2_make(rcp_approx(p0), rcp_approx(p1));
+                const F2 r = f2_mul(eb, inv), z = f2_mul(ea, inv);
+                // n = tanh(gi_n + r * (gh_n + b_hn)) = 1 - 2 / (1 + e^{2x})
+                float t0, t1;
+                f2_get(f2_mul(f2_fma(r, f2_add(accn, bhn2), gin), k2l2), t0, t1);
+                float e0, e1;
+                f2_get(f2_add(f2_make(ex2_approx(fminf(t0, 60.0f)), ex2_approx(fminf(t1, 60.0f))), one2), e0, e1);
+                const F2 nn = f2_fma(neg2, f2_make(rcp_approx(e0), rcp_approx(e1)), one2);
+                // h = (h_prev - n) * z + n   (ATen's gru_cell form)
+                const F2 h2 = f2_fma(f2_fma(nn, negone2, hprev2[q]), z, nn);
+                hprev2[q] = h2;
+                float h0v, h1v;
+                f2_get(h2, h0v, h1v);
+                __half hi0, lo0, hi1, lo1;
+                split_f16(h0v, hi0, lo0);
+                split_f16(h1v, hi1, lo1);
+                *reinterpret_cast<__half *>(hrow + (2 * q) * 16) = hi0;                // B operand of the next step
+                *reinterpret_cast<__half *>(hrow + RT_HPLANE + (2 * q) * 16) = lo0;
+                *reinterpret_cast<__half *>(hrow + (2 * q + 1) * 16) = hi1;
+                *reinterpret_cast<__half *>(hrow + RT_HPLANE + (2 * q + 1) * 16) = lo1;
+                if (!tile_ok) continue;
+                if (OUT_TILES) {
+                    tb[(2 * q) * 8] = hi0;
+                    tb[XT_PLANE_BYTES / 2 + (2 * q) * 8] = lo0;
+                    tb[(2 * q + 1) * 8] = hi1;
+                    tb[XT_PLANE_BYTES / 2 + (2 * q + 1) * 8] = lo1;
+                } else {
+                    o32[(2 * q) * H2] = h0v;
+                    o32[(2 * q + 1) * H2] = h1v;
+                }
+                // software pipeline: this pair's pre-activations of the NEXT step reuse the same registers; the
+                // loads complete under the next step's MMAs
+                if (!FUSE_X && more) {
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    float r, z, pre_n;
-                    if (FUSE_X) {
-                        sigmoid2_fast(b_r + __uint_as_float(ar[c]), b_z + __uint_as_float(az[c]), r, z);
-                        pre_n = fmaf(r, __uint_as_float(an[c]) + bhn, b_n + __uint_as_float(ax[c]));
-                    } else {
-                        sigmoid2_fast(g[0][c] + __uint_as_float(ar[c]), g[1][c] + __uint_as_float(az[c]), r, z);
-                        pre_n = fmaf(r, __uint_as_float(an[c]) + bhn, g[2][c]);
-                    }
-                    const float nn = tanh_fast(pre_n);
-                    const float h = fmaf(hprev[c] - nn, z, nn);   // (hx - n) * z + n, as ATen's gru_cell
-                    hprev[c] = h;
-                    __half hi, lo;
-                    split_f16(h, hi, lo);
-                    *reinterpret_cast<__half *>(hrow + c * 16) = hi;               // B operand of the next step
-                    *reinterpret_cast<__half *>(hrow + RT_HPLANE + c * 16) = lo;
-                    if ((okmask >> c) & 1u) {
-                        if (OUT_TILES) {
-                            const int64_t p = p0 + c * T;
-                            __half *tb = o16 + (p >> 7) * (int64_t)(XT_TILE_BYTES / 2) + (p & (XT_ROWS - 1)) * 8;
-                            tb[0] = hi;
-                            tb[XT_PLANE_BYTES / 2] = lo;
-                        } else {
-                            o32[(t + c * T) * H2] = h;
-                        }
-                        // software pipeline: this column's pre-activations of the NEXT step reuse the same
-                        // registers; the loads complete under the next step's MMA
-                        if (!FUSE_X && more) {
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) g[q][c] = ldg_stream(gnext + c * gstride + q * H);
-                        }
-                    }
+                    for (int gt = 0; gt < 3; ++gt)
+                        g2[gt][q] = f2_make(ldg_stream(gptr + (2 * q) * GI_COLS + gt * H),
+                                            ldg_stream(gptr + (2 * q + 1) * GI_COLS + gt * H));
                 }
             }
+            o32 += tstep * H2;
+            orow += tstep;
             if (FUSE_X && xown && more) {
                 // stage x_{step+1} (loaded a step ago) into the other buffer, then fetch x_{step+2}
+                const int64_t t = dir ? (T - 1 - step) : step;
                 __half hi, lo;
                 split_f16(xreg, hi, lo);
                 uint8_t *xd = xdst + (((step + 1) & 1) ? RT_XBUF : 0);

@@ -219,7 +219,7 @@ cudaError_t launch_decode(const float *probs, int64_t n, uint8_t *labels, uint8_
 template <int F>
 __global__ void __launch_bounds__(256) inproj0_kernel(const float *__restrict__ feats, const float *__restrict__ w,
                                                       const float *__restrict__ bias, float *__restrict__ gi,
-                                                      int64_t P) {
+                                                      int64_t P, int64_t T, int tiled) {
     constexpr int PT = 64;   // positions per block
     __shared__ float xs[PT * F];
     const int tid = threadIdx.x;
@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(256) inproj0_kernel(const float *__restrict__ 
             a1 = fmaf(x, wr[1][f], a1);
             a2 = fmaf(x, wr[2][f], a2);
         }
-        float *row = gi + (p0 + p) * GI_COLS;
+        const int64_t pp = p0 + p;
+        const int64_t orow = tiled ? tiled_row(pp / T, pp % T, T) : pp;
+        float *row = gi + orow * GI_COLS;
         row[tid] = a0;
         row[tid + 256] = a1;
         row[tid + 512] = a2;
@@ -255,23 +257,24 @@ __global__ void __launch_bounds__(256) inproj0_kernel(const float *__restrict__ 
 __global__ void __launch_bounds__(256) inproj0_generic_kernel(const float *__restrict__ feats,
                                                               const float *__restrict__ w,
                                                               const float *__restrict__ bias, float *__restrict__ gi,
-                                                              int64_t P, int F) {
+                                                              int64_t P, int F, int64_t T, int tiled) {
     const int64_t p = blockIdx.x;
     if (p >= P) return;
+    const int64_t orow = tiled ? tiled_row(p / T, p % T, T) : p;
     for (int c = threadIdx.x; c < GI_COLS; c += 256) {
         float a = bias[c];
         for (int f = 0; f < F; ++f) a = fmaf(feats[p * F + f], w[c * F + f], a);
-        gi[p * GI_COLS + c] = a;
+        gi[orow * GI_COLS + c] = a;
     }
 }
 
 cudaError_t launch_inproj0(const float *feats, const float *w_packed, const float *bias, float *gi, int64_t P,
-                           int F, cudaStream_t s) {
+                           int F, int64_t T, int tiled, cudaStream_t s) {
     if (P == 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((P + 63) / 64);
-    if (F == 10) inproj0_kernel<10><<<blocks, 256, 0, s>>>(feats, w_packed, bias, gi, P);
-    else if (F == 20) inproj0_kernel<20><<<blocks, 256, 0, s>>>(feats, w_packed, bias, gi, P);
-    else inproj0_generic_kernel<<<(unsigned)P, 256, 0, s>>>(feats, w_packed, bias, gi, P, F);
+    if (F == 10) inproj0_kernel<10><<<blocks, 256, 0, s>>>(feats, w_packed, bias, gi, P, T, tiled);
+    else if (F == 20) inproj0_kernel<20><<<blocks, 256, 0, s>>>(feats, w_packed, bias, gi, P, T, tiled);
+    else inproj0_generic_kernel<<<(unsigned)P, 256, 0, s>>>(feats, w_packed, bias, gi, P, F, T, tiled);
     return cudaGetLastError();
 }
 
@@ -279,9 +282,11 @@ cudaError_t launch_inproj0(const float *feats, const float *w_packed, const floa
 // Head: logits = h1 . W^T + b (gru.py:67), probs = softmax (gru.py:71), label = argmax (labels.py:1063)
 // One warp per position, 8 of the 256 inputs per lane; 1 KiB read + 41 B written per position.
 // =====================================================================================
+// R = number of h1 rows (P, or the tile-interleaved row count which includes padding windows); outputs always go to
+// position p = w*T + t.
 __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1, const float *__restrict__ lin_w,
-                                                   const float *__restrict__ lin_b, int64_t P,
-                                                   float *__restrict__ probs, float *__restrict__ logits,
+                                                   const float *__restrict__ lin_b, int64_t P, int64_t B, int64_t T,
+                                                   int tiled, float *__restrict__ probs, float *__restrict__ logits,
                                                    uint8_t *__restrict__ labels) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -301,17 +306,24 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1,
     // 4 KiB in flight (the kernel is a pure 1 KiB/position HBM stream; one position at a time left it latency-bound
     // at 2.6 TB/s)
     constexpr int PU = 4;
-    for (int64_t pb = warp * PU; pb < P; pb += nwarps * PU) {
+    const int64_t R = tiled ? tiled_rows(B, T) : P;
+    for (int64_t pb = warp * PU; pb < R; pb += nwarps * PU) {
         float4 va[PU], vb[PU];
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
-            const int64_t p = min(pb + u, P - 1);
-            va[u] = ld_stream4(h1 + p * H2 + lane * 8);
-            vb[u] = ld_stream4(h1 + p * H2 + lane * 8 + 4);
+            const int64_t r = min(pb + u, R - 1);
+            va[u] = ld_stream4(h1 + r * H2 + lane * 8);
+            vb[u] = ld_stream4(h1 + r * H2 + lane * 8 + 4);
         }
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
-            const int64_t p = pb + u;
+            int64_t p = pb + u;           // row index; mapped to the output position below
+            if (tiled) {
+                const int64_t rr = p;
+                const int64_t tile = rr / (WT * T), rem = rr % (WT * T);
+                const int64_t w = tile * WT + rem % WT;
+                p = (rr < R && w < B) ? w * T + rem / WT : P;    // padding windows have no output
+            }
             const float x[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
             float acc[NCLS];
 #pragma unroll
@@ -354,12 +366,13 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1,
     }
 }
 
-cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b, int64_t P, float *probs,
-                        float *logits, uint8_t *labels, cudaStream_t s) {
+cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b, int64_t B, int64_t T, int tiled,
+                        float *probs, float *logits, uint8_t *labels, cudaStream_t s) {
+    const int64_t P = B * T;
     if (P == 0) return cudaSuccess;
     int64_t blocks = (P + 31) / 32;            // 8 warps per block, 4 positions per warp per iteration
     if (blocks > 148 * 8) blocks = 148 * 8;    // persistent-ish grid: multiple of the SM count
-    head_kernel<<<(unsigned)blocks, 256, 0, s>>>(h1, lin_w, lin_b, P, probs, logits, labels);
+    head_kernel<<<(unsigned)blocks, 256, 0, s>>>(h1, lin_w, lin_b, P, B, T, tiled, probs, logits, labels);
     return cudaGetLastError();
 }
 
@@ -437,23 +450,39 @@ cudaError_t launch_prepare_layer(const LayerWeights &lw, int in_features, bool b
     return cudaGetLastError();
 }
 
-// fp16 hi/lo activation tiles -> fp32 [P][256]  (debug / layer-wise parity only)
-__global__ void unpack_h0_kernel(const __half *__restrict__ tiles, float *__restrict__ out, int64_t P) {
+// fp16 hi/lo activation tiles (tile-interleaved rows) -> fp32 [B*T][256] in position order (debug / layer-wise parity)
+__global__ void unpack_h0_kernel(const __half *__restrict__ tiles, float *__restrict__ out, int64_t B, int64_t T) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= P * H2) return;
+    if (i >= B * T * H2) return;
     const int64_t p = i / H2;
     const int k = (int)(i % H2);
-    const int64_t tile = p / XT_ROWS;
-    const int r = (int)(p % XT_ROWS);
+    const int64_t row = tiled_row(p / T, p % T, T);
+    const int64_t tile = row / XT_ROWS;
+    const int r = (int)(row % XT_ROWS);
     const __half *base = tiles + tile * (XT_TILE_BYTES / 2);
     const int64_t off = (int64_t)(k / 8) * (XT_ROWS * 8) + r * 8 + (k % 8);
     out[i] = __half2float(base[off]) + __half2float(base[XT_PLANE_BYTES / 2 + off]);
 }
 
-cudaError_t launch_unpack_h0(const void *h0_tiles, float *out, int64_t P, cudaStream_t s) {
-    if (P == 0) return cudaSuccess;
-    const int64_t n = P * H2;
-    unpack_h0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __half *>(h0_tiles), out, P);
+cudaError_t launch_unpack_h0(const void *h0_tiles, float *out, int64_t B, int64_t T, cudaStream_t s) {
+    const int64_t n = B * T * H2;
+    if (n == 0) return cudaSuccess;
+    unpack_h0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const __half *>(h0_tiles), out, B, T);
+    return cudaGetLastError();
+}
+
+// fp32 [rows'][256] in tile-interleaved order -> [B*T][256] in position order (debug / layer-wise parity)
+__global__ void untile_rows_kernel(const float *__restrict__ src, float *__restrict__ dst, int64_t B, int64_t T) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= B * T * H2) return;
+    const int64_t p = i / H2;
+    dst[i] = src[tiled_row(p / T, p % T, T) * H2 + (i % H2)];
+}
+
+cudaError_t launch_untile_rows(const float *src_tiled, float *dst, int64_t B, int64_t T, cudaStream_t s) {
+    const int64_t n = B * T * H2;
+    if (n == 0) return cudaSuccess;
+    untile_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src_tiled, dst, B, T);
     return cudaGetLastError();
 }
 

@@ -202,6 +202,34 @@ __device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo) {
     lo = __float2half_rn(v - __half2float(hi));
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (FADD2 / FMUL2 / FFMA2)
+// Blackwell issues two fp32 operations per instruction on a 64-bit register pair; the gate phase of the recurrent
+// kernel is instruction-issue bound, so its arithmetic runs on pairs of (independent) windows.
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 f2_make(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_get(F2 a, float &lo, float &hi) {
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+    F2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+    F2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    F2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+
 // ---------------------------------------------------------------- streaming global access
 __device__ __forceinline__ float ldg_stream(const float *p) {
     float v;
