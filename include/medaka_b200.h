@@ -154,6 +154,25 @@ int mdk_normalise_counts_dev(int device, const uint64_t *counts_dev, const int64
                              int32_t mode, int32_t sym_indels, float *feats_out_dev,
                              int64_t *depth_out_dev);
 
+/* ---- featuriser seam, raw counts: replaces calculate_pileup (src/medaka_counts.c:199-372, declared
+ * src/medaka_counts.h:105-108) for num_homop == 1.  htslib's BGZF/BAM decoding stays on the host
+ * (medaka_b200/bam.py); the records arrive in BAM's own packed encodings:
+ *   pos[n] 0-based reference start, flag[n], mapq[n], dtype[n] (datatype index, 0 when num_dtypes == 1),
+ *   cigar[] uint32 (len << 4 | op) with cigar_off[n+1] (op index of each read's first op),
+ *   seq[] 4-bit codes, two per byte, high nibble first, with seq_off[n+1] (byte offset of each read).
+ * Region is [start, end) 0-based on one contig; reads failing the flag / min_mapQ filter of
+ * src/medaka_bamiter.c:19-21 are skipped on the device (tag / RG filters are the reader's job).
+ * Outputs like the plp_data struct (src/medaka_counts.h:5-14): counts uint64 [n_cols][10*num_dtypes] in
+ * 'acgtACGTdD' order, major / minor [n_cols].  *n_cols_out is always set; if it exceeds max_cols the call
+ * returns MDK_ERR_NOMEM without writing counts and the caller retries with larger buffers
+ * (enlarge_plp_data, medaka_counts.c:266-271).  All pointers are HOST pointers. */
+int mdk_pileup_counts(int device, int64_t n_rec, const int32_t *pos, const uint16_t *flag,
+                      const uint8_t *mapq, const uint8_t *dtype, const uint32_t *cigar,
+                      const int64_t *cigar_off, const uint8_t *seq, const int64_t *seq_off,
+                      int32_t start, int32_t end, int32_t num_dtypes, int32_t min_mapq,
+                      int64_t max_cols, uint64_t *counts_out, int64_t *major_out, int64_t *minor_out,
+                      int64_t *n_cols_out);
+
 /* ---- decode seam: replaces the array part of HaploidLabelScheme.decode_consensus ------------
  * (medaka/labels.py:1053-1085 with _phred :387-401): labels = argmax (first max wins),
  * quals = uint8(min(70, -10*log10(clip(1-p_max, 1e-7, 1)))) + 33.  probs float32 [n][5].

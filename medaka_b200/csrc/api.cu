@@ -567,6 +567,63 @@ int mdk_normalise_counts(int device, const uint64_t *counts, const int64_t *majo
     return MDK_OK;
 }
 
+int mdk_pileup_counts(int device, int64_t n_rec, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
+                      const uint8_t *dtype, const uint32_t *cigar, const int64_t *cigar_off, const uint8_t *seq,
+                      const int64_t *seq_off, int32_t start, int32_t end, int32_t num_dtypes, int32_t min_mapq,
+                      int64_t max_cols, uint64_t *counts_out, int64_t *major_out, int64_t *minor_out,
+                      int64_t *n_cols_out) {
+    MDK_REQUIRE(n_cols_out, MDK_ERR_ARG, "pileup_counts: n_cols_out is NULL");
+    *n_cols_out = 0;
+    MDK_REQUIRE(n_rec >= 0 && end >= start && max_cols >= 0, MDK_ERR_ARG, "pileup_counts: bad sizes");
+    MDK_REQUIRE(num_dtypes >= 1 && num_dtypes <= 4, MDK_ERR_UNSUPPORTED, "pileup_counts: 1..4 dtypes supported");
+    if (n_rec == 0 || end == start) return MDK_OK;
+    MDK_REQUIRE(pos && flag && mapq && dtype && cigar && cigar_off && seq && seq_off, MDK_ERR_ARG,
+                "pileup_counts: NULL record array");
+    MDK_REQUIRE(max_cols == 0 || (counts_out && major_out && minor_out), MDK_ERR_ARG, "pileup_counts: NULL output");
+    MDK_CUDA(cudaSetDevice(device));
+    const int64_t n_ops = cigar_off[n_rec], n_seq = seq_off[n_rec];
+    const int F = 10 * num_dtypes;
+    // one device blob: records in, columns out
+    size_t off = 0;
+    auto take = [&off](size_t bytes) { size_t o = off; off += (bytes + 15) / 16 * 16; return o; };
+    const size_t o_pos = take((size_t)n_rec * 4), o_flag = take((size_t)n_rec * 2), o_mapq = take((size_t)n_rec),
+                 o_dt = take((size_t)n_rec), o_cig = take((size_t)n_ops * 4), o_coff = take((size_t)(n_rec + 1) * 8),
+                 o_seq = take((size_t)n_seq), o_soff = take((size_t)(n_rec + 1) * 8),
+                 o_cnt = take((size_t)max_cols * F * 8), o_maj = take((size_t)max_cols * 8),
+                 o_min = take((size_t)max_cols * 8);
+    uint8_t *buf = nullptr;
+    MDK_CUDA(cudaMalloc(&buf, off + 16));
+    cudaStream_t s = 0;
+    cudaError_t err = cudaMemcpy(buf + o_pos, pos, (size_t)n_rec * 4, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(buf + o_flag, flag, (size_t)n_rec * 2, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(buf + o_mapq, mapq, (size_t)n_rec, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(buf + o_dt, dtype, (size_t)n_rec, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess && n_ops) err = cudaMemcpy(buf + o_cig, cigar, (size_t)n_ops * 4, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(buf + o_coff, cigar_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess && n_seq) err = cudaMemcpy(buf + o_seq, seq, (size_t)n_seq, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(buf + o_soff, seq_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice);
+    int rc = MDK_OK;
+    if (err == cudaSuccess) {
+        rc = pileup_counts_dev(n_rec, (const int32_t *)(buf + o_pos), (const uint16_t *)(buf + o_flag), buf + o_mapq,
+                               buf + o_dt, (const uint32_t *)(buf + o_cig), (const int64_t *)(buf + o_coff), n_ops,
+                               buf + o_seq, (const int64_t *)(buf + o_soff), start, end, num_dtypes, min_mapq, max_cols,
+                               (uint64_t *)(buf + o_cnt), (int64_t *)(buf + o_maj), (int64_t *)(buf + o_min),
+                               n_cols_out, s);
+    }
+    if (rc == MDK_OK && err == cudaSuccess && *n_cols_out > max_cols) {
+        set_error("pileup_counts: output buffers too small (see *n_cols_out)");
+        rc = MDK_ERR_NOMEM;
+    } else if (rc == MDK_OK && err == cudaSuccess && *n_cols_out > 0) {
+        const int64_t n = *n_cols_out;
+        err = cudaMemcpy(counts_out, buf + o_cnt, (size_t)n * F * 8, cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess) err = cudaMemcpy(major_out, buf + o_maj, (size_t)n * 8, cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess) err = cudaMemcpy(minor_out, buf + o_min, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(buf);
+    if (err != cudaSuccess) return cuda_fail(err, "pileup_counts", __FILE__, __LINE__);
+    return rc;
+}
+
 // ---------------------------------------------------------------------------- decode seam
 int mdk_decode_consensus_dev(int device, const float *probs_dev, int64_t n, uint8_t *labels_out_dev,
                              uint8_t *quals_out_dev) {

@@ -145,5 +145,11 @@ cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w
 cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const float *bias, float *gi, int64_t P,
                            int sm_count, cudaStream_t s);
 int selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant);
+// pileup.cu
+int pileup_counts_dev(int64_t n_rec, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
+                      const uint8_t *dtype, const uint32_t *cigar, const int64_t *cigar_off, int64_t n_ops,
+                      const uint8_t *seq, const int64_t *seq_off, int32_t start, int32_t end, int num_dtypes,
+                      int min_mapq, int64_t max_cols, uint64_t *counts, int64_t *major, int64_t *minor,
+                      int64_t *n_cols_host, cudaStream_t s);
 
 }  // namespace mdk

@@ -5,8 +5,9 @@ Mirrors the inference half of medaka/features.py: ``pileup_counts_norm_indices``
 device through mdk_normalise_counts) and ``SampleGenerator`` (:1208-1313).  Raw pileup
 counts come from ``_pileup_function`` - in the reference that is htslib's multi-pileup walked
 by src/medaka_counts.c; here it is pluggable (``pileup_source``) because no BAM decoder is
-part of this engine; the synthetic source used by the benchmark and tests
-produces counts in exactly the layout calculate_pileup returns.
+part of the reference tree; ``pileup_counts`` below is the GPU replacement (BAM inflate/parse on the
+host in medaka_b200/bam.py, per-base counting in csrc/pileup.cu), and a custom ``pileup_source`` can
+still be plugged in (the benchmark's synthetic source does).
 """
 import inspect
 from collections import defaultdict
@@ -32,6 +33,82 @@ def pileup_counts_norm_indices(dtypes, num_qstrat=1):
             for base_i, code in enumerate(codes):
                 indices[dt, code.islower()].append(base_i + featlen * (dti * num_qstrat + qindex))
     return dict(indices)
+
+
+def _split_on_gaps(counts, positions):
+    """First pass of __enforce_pileup_chunk_contiguity (medaka/features.py:111-164): a jump of the major
+    coordinate by more than one starts a new chunk.  (The second pass - re-joining abutting sub-region results -
+    is moot here because the GPU featuriser processes a region in one piece instead of 100 kb slices.)"""
+    if len(positions) == 0:
+        return []
+    cuts = np.where(np.ediff1d(positions['major']) > 1)[0] + 1
+    bounds = [0] + cuts.tolist() + [len(positions)]
+    return [(counts[a:b], positions[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
+
+
+def pileup_counts(region, bam, dtype_prefixes=None, region_split=100000, workers=8, tag_name=None,
+                  tag_value=None, keep_missing=False, num_qstrat=1, weibull_summation=False, read_group=None,
+                  min_mapq=1, device=0):
+    """Create pileup counts feature array for region - the reference's ``pileup_counts``
+    (medaka/features.py:199-255) with the per-base work on the GPU (mdk_pileup_counts).
+
+    :param bam: a ``medaka_b200.bam.BamFile`` (or a path to a BAM file).
+    :returns: list of (counts uint64 [n, 10*len(dtypes)], positions) chunks, split at coverage gaps.
+    ``region_split`` / ``workers`` are accepted for signature compatibility; the device processes the whole
+    region at once.  Quality stratification / Weibull summation (legacy RLE models) are not supported.
+    """
+    from medaka_b200 import bam as mbam
+    if num_qstrat != 1 or weibull_summation:
+        raise NotImplementedError("q-score stratification / Weibull summation belong to the legacy RLE models")
+    if tag_name is not None and len(tag_name) != 2:
+        raise ValueError("'tag_name' must be a length-2 string.")
+    if not isinstance(bam, mbam.BamFile):
+        bam = mbam.BamFile(bam)
+    multi = not (dtype_prefixes is None or isinstance(dtype_prefixes, str) or len(dtype_prefixes) == 1)
+    num_dtypes = len(dtype_prefixes) if multi else 1
+    batch = bam.fetch(region.ref_name, region.start, region.end, dtypes=dtype_prefixes if multi else None,
+                      tag_name=tag_name, tag_value=tag_value, keep_missing=keep_missing, read_group=read_group)
+    counts, positions = pileup_counts_from_batch(batch, region.start, region.end, num_dtypes, min_mapq, device)
+    return _split_on_gaps(counts, positions)
+
+
+def pileup_counts_from_batch(batch, start, end, num_dtypes=1, min_mapq=1, device=0):
+    """Run the GPU pileup over a ``RecordBatch``; returns (counts, positions) for [start, end)."""
+    lib, ffi = _lm.load(), _lm.ffi
+    n_rec = len(batch.pos)
+    F = 10 * num_dtypes
+    max_cols = max(2 * (end - start), 16)          # the reference's initial guess (medaka_counts.c:245)
+    arrs = dict(pos=np.ascontiguousarray(batch.pos, np.int32), flag=np.ascontiguousarray(batch.flag, np.uint16),
+                mapq=np.ascontiguousarray(batch.mapq, np.uint8), dtype=np.ascontiguousarray(batch.dtype, np.uint8),
+                cigar=np.ascontiguousarray(batch.cigar, np.uint32), coff=np.ascontiguousarray(batch.cigar_off, np.int64),
+                seq=np.ascontiguousarray(batch.seq, np.uint8), soff=np.ascontiguousarray(batch.seq_off, np.int64))
+    n_cols = ffi.new("int64_t *")
+    for _ in range(2):
+        counts = np.zeros((max_cols, F), dtype=np.uint64)
+        major = np.zeros(max_cols, dtype=np.int64)
+        minor = np.zeros(max_cols, dtype=np.int64)
+        rc = lib.mdk_pileup_counts(
+            device, n_rec, ffi.cast("const int32_t *", ffi.from_buffer(arrs["pos"])),
+            ffi.cast("const uint16_t *", ffi.from_buffer(arrs["flag"])),
+            ffi.cast("const uint8_t *", ffi.from_buffer(arrs["mapq"])),
+            ffi.cast("const uint8_t *", ffi.from_buffer(arrs["dtype"])),
+            ffi.cast("const uint32_t *", ffi.from_buffer(arrs["cigar"])),
+            ffi.cast("const int64_t *", ffi.from_buffer(arrs["coff"])),
+            ffi.cast("const uint8_t *", ffi.from_buffer(arrs["seq"])),
+            ffi.cast("const int64_t *", ffi.from_buffer(arrs["soff"])),
+            int(start), int(end), num_dtypes, int(min_mapq), max_cols,
+            ffi.cast("uint64_t *", ffi.from_buffer(counts)), ffi.cast("int64_t *", ffi.from_buffer(major)),
+            ffi.cast("int64_t *", ffi.from_buffer(minor)), n_cols)
+        if rc == lib.MDK_ERR_NOMEM and n_cols[0] > max_cols:
+            max_cols = int(n_cols[0])       # like enlarge_plp_data: retry with room for every column
+            continue
+        _lm.check(rc)
+        break
+    n = int(n_cols[0])
+    positions = np.empty(n, dtype=[('major', '<i8'), ('minor', '<i8')])
+    positions['major'] = major[:n]
+    positions['minor'] = minor[:n]
+    return counts[:n].copy(), positions
 
 
 class CountsFeatureEncoder(object):
@@ -71,11 +148,12 @@ class CountsFeatureEncoder(object):
 
     def _pileup_function(self, region, bam):
         """Raw counts for a region: list of (counts uint64 [n,F], positions) chunks (features.py:863-869)."""
-        if self.pileup_source is None:
-            raise NotImplementedError(
-                "no pileup source configured: BAM decoding (htslib in the reference) is outside this "
-                "engine; pass pileup_source=callable(region, bam, encoder) -> [(counts, positions), ...]")
-        return self.pileup_source(region, bam, self)
+        if self.pileup_source is not None:
+            return self.pileup_source(region, bam, self)
+        return pileup_counts(
+            region, bam, dtype_prefixes=self.dtypes, tag_name=self.tag_name, tag_value=self.tag_value,
+            keep_missing=self.tag_keep_missing, read_group=self.read_group, min_mapq=self.min_mapq,
+            device=self.device)
 
     def _post_process_pileup(self, counts, positions, region):
         """Normalise counts on the GPU (features.py:871-935) and wrap them in a Sample."""

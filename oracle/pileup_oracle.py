@@ -139,3 +139,33 @@ def pileup_counts(records, start, end, dtypes=None, min_mapq=1, tag_name=None,
     positions["minor"] = minor
     counts = np.stack(rows) if rows else np.zeros((0, F), dtype=np.uint64)
     return counts, positions
+
+
+def records_from_batch(batch):
+    """RecordBatch (medaka_b200.bam: BAM-packed CIGAR ops and 4-bit sequence) -> the dict records used above."""
+    ops = "MIDNSHP=X"
+    nt = "=ACMGRSVTWYHKDBN"
+    recs = []
+    for i in range(len(batch.pos)):
+        c = batch.cigar[batch.cigar_off[i]:batch.cigar_off[i + 1]]
+        cig = "".join("%d%s" % (int(x) >> 4, ops[int(x) & 15]) for x in c)
+        sb = np.asarray(batch.seq[batch.seq_off[i]:batch.seq_off[i + 1]])
+        nib = np.empty(2 * len(sb), dtype=np.uint8)
+        nib[0::2] = sb >> 4
+        nib[1::2] = sb & 15
+        seq = "".join(nt[x] for x in nib[:int(batch.l_seq[i])])
+        tags = {"DT": None}
+        recs.append(dict(pos=int(batch.pos[i]), cigar=cig, seq=seq, flag=int(batch.flag[i]),
+                         mapq=int(batch.mapq[i]), tags=tags, _dtype=int(batch.dtype[i])))
+    return recs
+
+
+def pileup_counts_from_batch(batch, start, end, num_dtypes=1, min_mapq=1):
+    """calculate_pileup over a RecordBatch; dtype indices come pre-resolved in ``batch.dtype``."""
+    recs = records_from_batch(batch)
+    dtypes = None
+    if num_dtypes > 1:
+        dtypes = ["dt%d" % k for k in range(num_dtypes)]
+        for r in recs:
+            r["tags"]["DT"] = dtypes[r["_dtype"]]
+    return pileup_counts(recs, start, end, dtypes=dtypes, min_mapq=min_mapq)

@@ -137,3 +137,44 @@ def synth_features_fast(B, T, F=10, seed=1234):
     x *= x * x
     x /= x.sum(axis=-1, keepdims=True)
     return x
+
+
+def synth_reads(n_reads, ref_len, seed=0, mean_len=3000, p_ins=0.04, p_del=0.04, p_skip=0.0, num_dtypes=1):
+    """Random alignment records (dicts as oracle/pileup_oracle.py takes them): CIGARs with M/=/X runs, insertions
+    (incl. consecutive I ops and I right after D), deletions, optional N skips, soft clips, both strands, a few
+    filtered flags / low mapQ reads and IUPAC ambiguity codes."""
+    rs = np.random.RandomState(seed)
+    recs = []
+    for i in range(n_reads):
+        pos = int(rs.randint(0, max(1, ref_len - 50)))
+        target = int(min(ref_len - pos, max(20, rs.exponential(mean_len))))
+        ops, ref_used, qlen = [], 0, 0
+        if rs.uniform() < 0.3:
+            s = int(rs.randint(1, 30)); ops.append((s, "S")); qlen += s
+        last = None
+        while ref_used < target:
+            u = rs.uniform()
+            if u < p_ins and last in ("M", "D", "I"):
+                l = int(rs.randint(1, 6)); ops.append((l, "I")); qlen += l; last = "I"
+            elif u < p_ins + p_del and last == "M":
+                l = int(min(rs.randint(1, 8), target - ref_used)); ops.append((l, "D")); ref_used += l; last = "D"
+            elif u < p_ins + p_del + p_skip and last == "M":
+                l = int(min(rs.randint(5, 40), target - ref_used)); ops.append((l, "N")); ref_used += l; last = "N"
+            else:
+                l = int(min(rs.randint(1, 40), target - ref_used))
+                ops.append((l, "M=X"[int(rs.randint(0, 3))])); ref_used += l; qlen += l; last = "M"
+        if ops[-1][1] not in "M=X":
+            ops.append((1, "M")); qlen += 1
+        if rs.uniform() < 0.3:
+            s = int(rs.randint(1, 30)); ops.append((s, "S")); qlen += s
+        alphabet = "ACGT" * 12 + "NRY"
+        seq = "".join(alphabet[int(k)] for k in rs.randint(0, len(alphabet), qlen))
+        flag = 16 if rs.uniform() < 0.5 else 0
+        if rs.uniform() < 0.05:
+            flag |= int(rs.choice([0x100, 0x800, 0x400, 0x200]))
+        mapq = 0 if rs.uniform() < 0.05 else int(rs.randint(1, 61))
+        tags = {"DT": "dt%d" % int(rs.randint(0, num_dtypes))} if num_dtypes > 1 else {}
+        recs.append(dict(query_name="r%d" % i, pos=pos, cigar="".join("%d%s" % o for o in ops), seq=seq,
+                         flag=flag, mapq=mapq, tags=tags))
+    recs.sort(key=lambda r: r["pos"])
+    return recs
