@@ -90,8 +90,11 @@ struct RecCfg {
     static constexpr int h_off = 0;                                        // [NT][2 planes][RT_HPLANE]
     static constexpr int x_off = ((NT * 2 * RT_HPLANE + 127) / 128) * 128; // [NT][2 bufs][RT_XBUF]
     static constexpr int wx_off = x_off + ((NT * 2 * RT_XBUF + 127) / 128) * 128;   // [6][RT_WX_BLOCK] (NT == 2)
-    static constexpr int bar_off = wx_off + 6 * RT_WX_BLOCK;               // acc_ready[NT], h_ready[NT]
-    static constexpr int tmem_off = bar_off + 2 * NT * 8;
+    // NT == 1 splits the accumulator hand-off: the r/z blocks are committed (and their sigmoids start) while the
+    // n-gate MMAs still run; with NT == 2 the other tile already fills that time
+    static constexpr bool split = (NT == 1);
+    static constexpr int bar_off = wx_off + 6 * RT_WX_BLOCK;               // acc_ready[NT], h_ready[NT], acc_n[NT], rz_issued[NT]
+    static constexpr int tmem_off = bar_off + 4 * NT * 8;
     // the CTA owns all 512 TMEM columns of its SM, so a second co-resident CTA could only spin in tcgen05.alloc;
     // ask for > half of the shared memory to keep residency at one CTA per SM.
     static constexpr int total = 120 * 1024;
@@ -112,8 +115,10 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
               const float *__restrict__ b_hn, void *__restrict__ h_out, int64_t B, int64_t T) {
     extern __shared__ __align__(128) uint8_t smem[];
     using L = RecCfg<NT, FUSE_X>;
-    uint64_t *acc_ready = reinterpret_cast<uint64_t *>(smem + L::bar_off);
+    uint64_t *acc_ready = reinterpret_cast<uint64_t *>(smem + L::bar_off);   // split: r and z blocks only
     uint64_t *h_ready = acc_ready + NT;
+    uint64_t *acc_n = h_ready + NT;          // split: n block(s)
+    uint64_t *rz_issued = acc_n + NT;        // split: r and z issuers have queued their MMAs
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::tmem_off);
 
     const int tid = threadIdx.x;
@@ -138,8 +143,10 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
     }
     if (tid == 0) {
         for (int i = 0; i < NT; ++i) {
-            mbar_init(&acc_ready[i], RT_MMA_WARPS);
+            mbar_init(&acc_ready[i], L::split ? 2 : RT_MMA_WARPS);
             mbar_init(&h_ready[i], 32 * RT_GATE_WARPS / NT);
+            mbar_init(&acc_n[i], 1);
+            mbar_init(&rz_issued[i], 2);
         }
         fence_mbar_init();
     }
@@ -198,6 +205,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
 #pragma unroll
             for (int tile = 0; tile < NT; ++tile) {
                 mbar_wait(&h_ready[tile], par);
+                if (L::split && g == 2) mbar_wait(&rz_issued[tile], par);   // let the r/z MMAs into the pipe first
                 tc_fence_after_sync();
                 if (elect_one()) {
                     const uint32_t d = L::acc_col0 + (uint32_t)(tile * L::acc_per_tile + g * 16);
@@ -227,7 +235,12 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                             }
                         }
                     }
-                    umma_commit(&acc_ready[tile]);
+                    if (L::split && g == 2) {
+                        umma_commit(&acc_n[tile]);
+                    } else {
+                        umma_commit(&acc_ready[tile]);
+                        if (L::split) mbar_arrive(&rz_issued[tile]);
+                    }
                 }
                 __syncwarp();
             }
@@ -318,33 +331,30 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             if constexpr (NC == 8) {
                 tmem_ld_x8(t_lane + 0 * 16, ar);
                 tmem_ld_x8(t_lane + 1 * 16, az);
-                tmem_ld_x8(t_lane + 2 * 16, an);
-                if (FUSE_X) tmem_ld_x8(t_lane + 3 * 16, ax);
+                if (!L::split) {
+                    tmem_ld_x8(t_lane + 2 * 16, an);
+                    if (FUSE_X) tmem_ld_x8(t_lane + 3 * 16, ax);
+                }
             } else {
                 tmem_ld_x4(t_lane + 0 * 16, ar);
                 tmem_ld_x4(t_lane + 1 * 16, az);
-                tmem_ld_x4(t_lane + 2 * 16, an);
-                if (FUSE_X) tmem_ld_x4(t_lane + 3 * 16, ax);
+                if (!L::split) {
+                    tmem_ld_x4(t_lane + 2 * 16, an);
+                    if (FUSE_X) tmem_ld_x4(t_lane + 3 * 16, ax);
+                }
             }
             tmem_ld_wait();
             if (!FUSE_X) gptr += tstep * GI_COLS;          // rows of the next time step
+            __half hh[NC], hl[NC];
             __half *tb = nullptr;
             if (OUT_TILES) tb = o16 + (orow >> 7) * (int64_t)(XT_TILE_BYTES / 2) + (orow & (XT_ROWS - 1)) * 8;
+            F2 r2[NP], z2[NP];
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 const F2 accr = f2_make(__uint_as_float(ar[2 * q]), __uint_as_float(ar[2 * q + 1]));
                 const F2 accz = f2_make(__uint_as_float(az[2 * q]), __uint_as_float(az[2 * q + 1]));
-                const F2 accn = f2_make(__uint_as_float(an[2 * q]), __uint_as_float(an[2 * q + 1]));
-                F2 pre_r, pre_z, gin;
-                if (FUSE_X) {
-                    pre_r = f2_add(br2, accr);
-                    pre_z = f2_add(bz2, accz);
-                    gin = f2_add(bn2, f2_make(__uint_as_float(ax[2 * q]), __uint_as_float(ax[2 * q + 1])));
-                } else {
-                    pre_r = f2_add(g2[0][q], accr);
-                    pre_z = f2_add(g2[1][q], accz);
-                    gin = g2[2][q];
-                }
+                const F2 pre_r = f2_add(FUSE_X ? br2 : g2[0][q], accr);
+                const F2 pre_z = f2_add(FUSE_X ? bz2 : g2[1][q], accz);
                 // r = sigmoid(pre_r), z = sigmoid(pre_z) with one reciprocal per element: 1/((1+e^-a)(1+e^-b))
                 float a0, a1, b0, b1;
                 f2_get(f2_mul(pre_r, knl2), a0, a1);
@@ -354,7 +364,28 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 float p0, p1;
                 f2_get(f2_mul(ea, eb), p0, p1);
                 const F2 inv = f2_make(rcp_approx(p0), rcp_approx(p1));
-                const F2 r = f2_mul(eb, inv), z = f2_mul(ea, inv);
+                r2[q] = f2_mul(eb, inv);
+                z2[q] = f2_mul(ea, inv);
+            }
+            if (L::split) {
+                // the n-gate accumulators arrive while the sigmoids above were running
+                mbar_wait(&acc_n[tile], (uint32_t)(step & 1));
+                tc_fence_after_sync();
+                if constexpr (NC == 8) {
+                    tmem_ld_x8(t_lane + 2 * 16, an);
+                    if (FUSE_X) tmem_ld_x8(t_lane + 3 * 16, ax);
+                } else {
+                    tmem_ld_x4(t_lane + 2 * 16, an);
+                    if (FUSE_X) tmem_ld_x4(t_lane + 3 * 16, ax);
+                }
+                tmem_ld_wait();
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const F2 accn = f2_make(__uint_as_float(an[2 * q]), __uint_as_float(an[2 * q + 1]));
+                const F2 gin = FUSE_X ? f2_add(bn2, f2_make(__uint_as_float(ax[2 * q]), __uint_as_float(ax[2 * q + 1])))
+                                      : g2[2][q];
+                const F2 r = r2[q], z = z2[q];
                 // n = tanh(gi_n + r * (gh_n + b_hn)) = 1 - 2 / (1 + e^{2x})
                 float t0, t1;
                 f2_get(f2_mul(f2_fma(r, f2_add(accn, bhn2), gin), k2l2), t0, t1);
@@ -366,47 +397,59 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 hprev2[q] = h2;
                 float h0v, h1v;
                 f2_get(h2, h0v, h1v);
-                __half hi0, lo0, hi1, lo1;
-                split_f16(h0v, hi0, lo0);
-                split_f16(h1v, hi1, lo1);
-                *reinterpret_cast<__half *>(hrow + (2 * q) * 16) = hi0;                // B operand of the next step
+                __half lo0, lo1;
+                split_f16(h0v, hh[2 * q], lo0);
+                split_f16(h1v, hh[2 * q + 1], lo1);
+                hl[2 * q] = lo0;
+                hl[2 * q + 1] = lo1;
+                *reinterpret_cast<__half *>(hrow + (2 * q) * 16) = hh[2 * q];           // B operand of the next step
                 *reinterpret_cast<__half *>(hrow + RT_HPLANE + (2 * q) * 16) = lo0;
-                *reinterpret_cast<__half *>(hrow + (2 * q + 1) * 16) = hi1;
+                *reinterpret_cast<__half *>(hrow + (2 * q + 1) * 16) = hh[2 * q + 1];
                 *reinterpret_cast<__half *>(hrow + RT_HPLANE + (2 * q + 1) * 16) = lo1;
-                if (!tile_ok) continue;
-                if (OUT_TILES) {
-                    tb[(2 * q) * 8] = hi0;
-                    tb[XT_PLANE_BYTES / 2 + (2 * q) * 8] = lo0;
-                    tb[(2 * q + 1) * 8] = hi1;
-                    tb[XT_PLANE_BYTES / 2 + (2 * q + 1) * 8] = lo1;
-                } else {
-                    o32[(2 * q) * H2] = h0v;
-                    o32[(2 * q + 1) * H2] = h1v;
-                }
-                // software pipeline: this pair's pre-activations of the NEXT step reuse the same registers; the
-                // loads complete under the next step's MMAs
-                if (!FUSE_X && more) {
-#pragma unroll
-                    for (int gt = 0; gt < 3; ++gt)
-                        g2[gt][q] = f2_make(ldg_stream(gptr + (2 * q) * GI_COLS + gt * H),
-                                            ldg_stream(gptr + (2 * q + 1) * GI_COLS + gt * H));
-                }
             }
-            o32 += tstep * H2;
-            orow += tstep;
             if (FUSE_X && xown && more) {
-                // stage x_{step+1} (loaded a step ago) into the other buffer, then fetch x_{step+2}
-                const int64_t t = dir ? (T - 1 - step) : step;
+                // stage x_{step+1} (loaded a step ago) into the other x buffer
                 __half hi, lo;
                 split_f16(xreg, hi, lo);
                 uint8_t *xd = xdst + (((step + 1) & 1) ? RT_XBUF : 0);
                 *reinterpret_cast<__half *>(xd) = hi;
                 *reinterpret_cast<__half *>(xd + RT_XPLANE) = lo;
-                if (step + 2 < T && xok) xreg = xsrc[(dir ? (t - 2) : (t + 2)) * (int64_t)xin.F];
             }
+            // publish the next B operand first: everything below (global stores of this step's output, loads of the
+            // next step's pre-activations / features) is off the MMA -> gate -> MMA critical path
             fence_proxy_async_smem();     // h / x tile writes -> visible to the MMA's async-proxy reads
             tc_fence_before_sync();       // order our tcgen05.ld before the next MMA overwrites the accumulators
             mbar_arrive(&h_ready[tile]);
+            if (tile_ok) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (OUT_TILES) {
+                        tb[(2 * q) * 8] = hh[2 * q];
+                        tb[XT_PLANE_BYTES / 2 + (2 * q) * 8] = hl[2 * q];
+                        tb[(2 * q + 1) * 8] = hh[2 * q + 1];
+                        tb[XT_PLANE_BYTES / 2 + (2 * q + 1) * 8] = hl[2 * q + 1];
+                    } else {
+                        float h0v, h1v;
+                        f2_get(hprev2[q], h0v, h1v);
+                        o32[(2 * q) * H2] = h0v;
+                        o32[(2 * q + 1) * H2] = h1v;
+                    }
+                    // software pipeline: this pair's pre-activations of the NEXT step; the loads complete under
+                    // the next step's MMAs
+                    if (!FUSE_X && more) {
+#pragma unroll
+                        for (int gt = 0; gt < 3; ++gt)
+                            g2[gt][q] = f2_make(ldg_stream(gptr + (2 * q) * GI_COLS + gt * H),
+                                                ldg_stream(gptr + (2 * q + 1) * GI_COLS + gt * H));
+                    }
+                }
+            }
+            o32 += tstep * H2;
+            orow += tstep;
+            if (FUSE_X && xok && step + 2 < T) {
+                const int64_t t = dir ? (T - 1 - step) : step;
+                xreg = xsrc[(dir ? (t - 2) : (t + 2)) * (int64_t)xin.F];
+            }
         }
     }
     tc_fence_before_sync();

@@ -306,24 +306,20 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1,
     // 4 KiB in flight (the kernel is a pure 1 KiB/position HBM stream; one position at a time left it latency-bound
     // at 2.6 TB/s)
     constexpr int PU = 4;
-    const int64_t R = tiled ? tiled_rows(B, T) : P;
-    for (int64_t pb = warp * PU; pb < R; pb += nwarps * PU) {
+    // iterate in OUTPUT order (consecutive positions of one window) so the stores stay coalesced; on the tensor-core
+    // path the h1 row of position p = w*T + t is the tile-interleaved row(w, t), a 1 KiB contiguous read either way
+    for (int64_t pb = warp * PU; pb < P; pb += nwarps * PU) {
         float4 va[PU], vb[PU];
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
-            const int64_t r = min(pb + u, R - 1);
+            const int64_t pp = min(pb + u, P - 1);
+            const int64_t r = tiled ? tiled_row(pp / T, pp % T, T) : pp;
             va[u] = ld_stream4(h1 + r * H2 + lane * 8);
             vb[u] = ld_stream4(h1 + r * H2 + lane * 8 + 4);
         }
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
-            int64_t p = pb + u;           // row index; mapped to the output position below
-            if (tiled) {
-                const int64_t rr = p;
-                const int64_t tile = rr / (WT * T), rem = rr % (WT * T);
-                const int64_t w = tile * WT + rem % WT;
-                p = (rr < R && w < B) ? w * T + rem / WT : P;    // padding windows have no output
-            }
+            const int64_t p = pb + u;
             const float x[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
             float acc[NCLS];
 #pragma unroll
