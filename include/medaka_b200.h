@@ -185,6 +185,13 @@ int mdk_decode_consensus_dev(int device, const float *probs_dev, int64_t n,
 int mdk_decode_consensus_f64(int device, const double *probs, int64_t n, uint8_t *labels_out,
                              uint8_t *quals_out);
 
+/* variant_columns (src/medaka_rnn_variants.h:26, called at medaka/labels.py:869-887): which pileup columns belong
+ * to a variant run.  minor [len] pileup minor indices; reference / prediction [len] one byte per column (the
+ * symbol or label code incl. the gap - the reference passes wchar_t strings, any 1-byte coding with the same
+ * equalities works); out [len] 0/1.  Host pointers. */
+int mdk_variant_columns(int device, const int64_t *minor, const uint8_t *reference,
+                        const uint8_t *prediction, uint8_t *out, int64_t len);
+
 /* ---- self test of the tcgen05 building block (one 128xN tile GEMM), used by tests ----------
  * Computes D[128][N] = A[128][K] * B[N][K]^T with the same smem layouts, descriptors and
  * fp16 hi/lo split the GRU kernels use.  A, B, D are host fp32.  variant selects descriptor

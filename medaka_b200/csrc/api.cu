@@ -673,6 +673,27 @@ int mdk_decode_consensus_f64(int device, const double *probs, int64_t n, uint8_t
     return MDK_OK;
 }
 
+int mdk_variant_columns(int device, const int64_t *minor, const uint8_t *reference, const uint8_t *prediction,
+                        uint8_t *out, int64_t len) {
+    MDK_REQUIRE(len >= 0, MDK_ERR_ARG, "variant_columns: len < 0");
+    if (len == 0) return MDK_OK;
+    MDK_REQUIRE(minor && reference && prediction && out, MDK_ERR_ARG, "variant_columns: NULL pointer");
+    MDK_CUDA(cudaSetDevice(device));
+    uint8_t *buf = nullptr;
+    const size_t n = (size_t)len;
+    MDK_CUDA(cudaMalloc(&buf, n * 8 + 3 * n + 64));
+    int64_t *d_minor = reinterpret_cast<int64_t *>(buf);
+    uint8_t *d_ref = buf + n * 8, *d_pred = d_ref + n, *d_out = d_pred + n;
+    cudaError_t err = cudaMemcpy(d_minor, minor, n * 8, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(d_ref, reference, n, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(d_pred, prediction, n, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = launch_variant_columns(d_minor, d_ref, d_pred, len, d_out, 0);
+    if (err == cudaSuccess) err = cudaMemcpy(out, d_out, n, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    if (err != cudaSuccess) return cuda_fail(err, "variant_columns", __FILE__, __LINE__);
+    return MDK_OK;
+}
+
 int mdk_selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant) {
     MDK_REQUIRE(A && B && D, MDK_ERR_ARG, "selftest_umma: NULL pointer");
     return selftest_umma(device, A, B, D, N, K, variant);

@@ -144,7 +144,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
     if (tid == 0) {
         for (int i = 0; i < NT; ++i) {
             mbar_init(&acc_ready[i], L::split ? 2 : RT_MMA_WARPS);
-            mbar_init(&h_ready[i], 32 * RT_GATE_WARPS / NT);
+            mbar_init(&h_ready[i], RT_GATE_WARPS / NT);    // one arrival per gate warp (lane 0 after __syncwarp)
             mbar_init(&acc_n[i], 1);
             mbar_init(&rz_issued[i], 2);
         }
@@ -204,8 +204,11 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             const uint32_t par = (uint32_t)(step & 1);
 #pragma unroll
             for (int tile = 0; tile < NT; ++tile) {
-                mbar_wait(&h_ready[tile], par);
-                if (L::split && g == 2) mbar_wait(&rz_issued[tile], par);   // let the r/z MMAs into the pipe first
+                if (lane == 0) {
+                    mbar_wait(&h_ready[tile], par);
+                    if (L::split && g == 2) mbar_wait(&rz_issued[tile], par);   // let the r/z MMAs into the pipe first
+                }
+                __syncwarp();
                 tc_fence_after_sync();
                 if (elect_one()) {
                     const uint32_t d = L::acc_col0 + (uint32_t)(tile * L::acc_per_tile + g * 16);
@@ -318,14 +321,17 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             *reinterpret_cast<__half *>(xdst + RT_XPLANE) = lo;
             if (T > 1 && xok) xreg = xsrc[(dir ? (T - 2) : 1) * (int64_t)xin.F];
         }
-        // h_{-1} = 0 (and x_0) are in smem: publish
+        // h_{-1} = 0 (and x_0) are in smem: publish (one mbarrier arrival per warp: 512 per-thread arrivals on one
+        // barrier serialise in the shared-memory atomics unit)
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(&h_ready[tile]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&h_ready[tile]);
 
         for (int64_t step = 0; step < T; ++step) {
             const bool more = step + 1 < T;
-            mbar_wait(&acc_ready[tile], (uint32_t)(step & 1));
+            if (lane == 0) mbar_wait(&acc_ready[tile], (uint32_t)(step & 1));   // one poller per warp
+            __syncwarp();
             tc_fence_after_sync();
             uint32_t ar[NC], az[NC], an[NC], ax[NC];
             if constexpr (NC == 8) {
@@ -369,7 +375,8 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             }
             if (L::split) {
                 // the n-gate accumulators arrive while the sigmoids above were running
-                mbar_wait(&acc_n[tile], (uint32_t)(step & 1));
+                if (lane == 0) mbar_wait(&acc_n[tile], (uint32_t)(step & 1));
+                __syncwarp();
                 tc_fence_after_sync();
                 if constexpr (NC == 8) {
                     tmem_ld_x8(t_lane + 2 * 16, an);
@@ -419,7 +426,8 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             // next step's pre-activations / features) is off the MMA -> gate -> MMA critical path
             fence_proxy_async_smem();     // h / x tile writes -> visible to the MMA's async-proxy reads
             tc_fence_before_sync();       // order our tcgen05.ld before the next MMA overwrites the accumulators
-            mbar_arrive(&h_ready[tile]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&h_ready[tile]);
             if (tile_ok) {
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {

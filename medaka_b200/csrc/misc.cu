@@ -212,6 +212,39 @@ cudaError_t launch_decode(const float *probs, int64_t n, uint8_t *labels, uint8_
 }
 
 // =====================================================================================
+// Variant columns (src/medaka_rnn_variants.c:28-55, called from labels.py:869-887): a major column is variant when
+// reference and prediction differ there; the minor (insertion) columns that follow it are variant when ANY column of
+// the group - the major or one of its minors - differs.  The reference walks the columns sequentially; here every
+// column finds its group (insertion runs are short) and reduces over it.  ~10 B per column.
+// =====================================================================================
+__global__ void __launch_bounds__(256) variant_columns_kernel(const int64_t *__restrict__ minor,
+                                                              const uint8_t *__restrict__ ref,
+                                                              const uint8_t *__restrict__ pred, int64_t n,
+                                                              uint8_t *__restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool mism = ref[i] != pred[i];
+    if (i == 0 || minor[i] == 0) {          // the first column is taken as a major ("assume start on major")
+        out[i] = mism;
+        return;
+    }
+    bool any = mism;
+    for (int64_t j = i - 1; j >= 0 && !any; --j) {      // back to (and including) the group's major column
+        any = ref[j] != pred[j];
+        if (j == 0 || minor[j] == 0) break;
+    }
+    for (int64_t j = i + 1; j < n && !any && minor[j] != 0; ++j) any = ref[j] != pred[j];
+    out[i] = any;
+}
+
+cudaError_t launch_variant_columns(const int64_t *minor, const uint8_t *ref, const uint8_t *pred, int64_t n,
+                                   uint8_t *out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    variant_columns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(minor, ref, pred, n, out);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
 // Layer-0 input projection: gi[p][c] = sum_f x[p][f] * W[c][f] + bias[c],  c in [0,768)
 // K = F (10 or 20) is far too thin for the tensor cores; the kernel is bound by the 3 KiB/position
 // write of gi.  256 threads, each owns 3 of the 768 columns with its weights in registers.

@@ -32,6 +32,37 @@ def decode_arrays(label_probs, device=0, with_qualities=True):
     return labels, quals
 
 
+def variant_columns(minor, reference, prediction, device=0):
+    """Which pileup columns belong to a variant run - ``HaploidLabelScheme._find_variants``
+    (medaka/labels.py:869-887 -> libmedaka.lib.variant_columns, src/medaka_rnn_variants.c:28-55) on the GPU.
+
+    :param minor: pileup minor indices; :param reference, prediction: per-column symbols (str, '|U1' / '|S1'
+        arrays or uint8 label codes) including gaps.  :returns: bool array.
+    """
+    lib, ffi = _lm.load(), _lm.ffi
+
+    def codes(x):
+        a = np.asarray(list(x) if isinstance(x, str) else x)
+        if a.dtype.kind == 'U':
+            a = np.array([ord(c) for c in a.tolist()], dtype=np.uint32)
+        elif a.dtype.kind == 'S':
+            a = np.frombuffer(a.tobytes(), dtype=np.uint8)
+        if a.size and int(a.max()) > 255:
+            raise ValueError("symbols must fit one byte")
+        return np.ascontiguousarray(a, dtype=np.uint8)
+
+    mn = np.ascontiguousarray(minor, dtype=np.int64)
+    r, p = codes(reference), codes(prediction)
+    if not (len(mn) == len(r) == len(p)):
+        raise ValueError("minor, reference and prediction must have the same length")
+    out = np.zeros(len(mn), dtype=np.uint8)
+    _lm.check(lib.mdk_variant_columns(device, ffi.cast("const int64_t *", ffi.from_buffer(mn)),
+                                      ffi.cast("const uint8_t *", ffi.from_buffer(r)),
+                                      ffi.cast("const uint8_t *", ffi.from_buffer(p)),
+                                      ffi.cast("uint8_t *", ffi.from_buffer(out)), len(mn)))
+    return out.astype(bool)
+
+
 class HaploidLabelScheme(object):
     """The decode half of the reference's HaploidLabelScheme (labels.py:703-1085)."""
 
@@ -50,6 +81,11 @@ class HaploidLabelScheme(object):
         """Host restatement kept for API compatibility (labels.py:387-401); not used on the hot path."""
         err = np.clip(err, 10 ** (-cap / 10.0), 1)
         return np.minimum(-10 * np.log10(err), cap)
+
+    @staticmethod
+    def _find_variants(minor, reference, prediction):
+        """labels.py:869-887."""
+        return variant_columns(minor, reference, prediction)
 
     def decode_consensus(self, sample, with_gaps=False, dtype=None, with_qualities=False):
         """Convert network output to consensus sequence by argmax decoding.

@@ -41,3 +41,27 @@ def decode_consensus(label_probs, with_gaps=False, with_qualities=False):
         qual = (phred(1 - probs).astype("u1") + 33).tobytes().decode()
         return seq, qual
     return seq
+
+
+def variant_columns(minor, reference, prediction):
+    """src/medaka_rnn_variants.c:28-55 restated: sequential walk over the pileup columns."""
+    n = len(minor)
+    out = np.zeros(n, dtype=bool)
+    if n == 0:
+        return out
+    is_var = reference[0] != prediction[0]      # assume start on major
+    insert_length = 0
+    out[0] = is_var
+    for i in range(1, n):
+        if minor[i] == 0:
+            if is_var:
+                out[i - insert_length:i] = True
+            is_var = reference[i] != prediction[i]
+            out[i] = is_var
+            insert_length = 0
+        else:
+            insert_length += 1
+            is_var = is_var or reference[i] != prediction[i]
+    if is_var:
+        out[n - insert_length:n] = True
+    return out

@@ -264,3 +264,24 @@ def test_decode_large_matches_oracle():
     exp_lab, exp_q = labels_oracle.decode_arrays(p)
     assert np.array_equal(lab, exp_lab)
     assert np.array_equal(q, exp_q)
+
+
+# ------------------------------------------------------------------ variant columns (decode seam, config 4)
+def test_variant_columns_gpu():
+    from medaka_b200 import labels as mlabels
+    from tests.test_oracle import VARIANT_CASES
+    for minor, ref, pred, exp in VARIANT_CASES:                       # medaka/test/test_labels.py:101-135
+        got = mlabels.HaploidLabelScheme._find_variants(minor, np.array(list(ref)), np.array(list(pred)))
+        assert "".join("+" if x else "-" for x in got) == exp, (minor, ref, pred)
+    rs = np.random.RandomState(4)
+    n = 500000
+    is_minor = rs.uniform(size=n) < 0.25
+    is_minor[0] = False
+    idx = np.arange(n)
+    last_major = np.maximum.accumulate(np.where(~is_minor, idx, -1))
+    minor = (idx - last_major).astype(np.int64)
+    ref = rs.randint(0, 5, n).astype(np.uint8)
+    pred = np.where(rs.uniform(size=n) < 0.9, ref, rs.randint(0, 5, n)).astype(np.uint8)
+    got = mlabels.variant_columns(minor, ref, pred)
+    assert np.array_equal(got, labels_oracle.variant_columns(minor, ref, pred))
+    assert mlabels.variant_columns([], [], []).size == 0

@@ -194,3 +194,21 @@ def test_contiguity_splits_on_gaps():
     c, p = pileup_oracle.pileup_counts(reads, 0, 100)
     chunks = features_oracle.enforce_pileup_chunk_contiguity([(c, p)])
     assert [len(x[1]) for x in chunks] == [8, 8]
+
+
+# medaka/test/test_labels.py:101-135 (VariantBoundaries.test_001_boundaries)
+VARIANT_CASES = [
+    ([0, 0, 0, 0], 'ATCG', 'ATCG', '----'), ([0, 1, 0, 0], 'A*CG', 'ATCG', '-+--'),
+    ([0, 1, 2, 0], 'A**G', 'ATCG', '-++-'), ([0, 1, 2, 3], 'A***', 'ATC*', '-+++'),
+    ([0, 1, 2, 3], 'A***', 'A*CG', '-+++'), ([0, 0, 0, 0], 'ATCG', 'AACG', '-+--'),
+    ([0, 0, 0, 0], 'ATCG', 'ATCC', '---+'), ([0, 1, 2, 3], 'A***', 'CTC*', '++++'),
+    ([0, 1, 2, 3], 'A***', 'C*CG', '++++'), ([0, 1, 2, 3, 0], 'A***A', 'CTC*A', '++++-'),
+    ([0, 1, 2, 3, 0], 'A***A', 'C*CGG', '+++++'), ([0, 1, 2, 3, 0, 1, 2], 'A***A**', 'CTC*A*A', '++++-++'),
+    ([0, 1, 2, 3, 0, 1, 2], 'A***A**', 'C*CGGA*', '+++++++'),
+]
+
+
+def test_variant_columns_reference_cases():
+    for minor, ref, pred, exp in VARIANT_CASES:
+        got = labels_oracle.variant_columns(np.array(minor), np.array(list(ref)), np.array(list(pred)))
+        assert "".join("+" if x else "-" for x in got) == exp, (minor, ref, pred)
