@@ -185,6 +185,21 @@ int mdk_decode_consensus_dev(int device, const float *probs_dev, int64_t n,
 int mdk_decode_consensus_f64(int device, const double *probs, int64_t n, uint8_t *labels_out,
                              uint8_t *quals_out);
 
+/* Consensus stitching (medaka/stitch.py:33-85 `_stitch_samples`: per trimmed sample decode_consensus(with_qualities)
+ * -> gap removal -> append).  The caller plans the kept row ranges (overlap trimming medaka/common.py:327-427,495-557,
+ * region trimming :560-609, depth filter :612-644) and passes one pointer per range; the library copies only those
+ * rows in, decodes them, removes gap calls and returns the concatenated ASCII bases / phred+33 quality characters.
+ *   seg_probs[k]   host float32 [seg_rows[k]][5], first kept row of range k;  seg_rows[k] > 0
+ *   seq_out/qual_out  host, capacity sum(seg_rows) bytes (qual_out may be NULL)
+ *   seg_out_off    host [n_seg + 1]: range k produced seq_out[seg_out_off[k] : seg_out_off[k+1]]
+ * The _dev form takes the ranges already back to back on the device (probs_dev [n_rows][5], 16-byte aligned) with
+ * seg_base[k] = first row of range k (host array, strictly increasing from 0); seq/qual outputs are device pointers
+ * of capacity n_rows, seg_out_off stays a host array. */
+int mdk_stitch_consensus(int device, const float *const *seg_probs, const int64_t *seg_rows, int64_t n_seg,
+                         uint8_t *seq_out, uint8_t *qual_out, int64_t *seg_out_off);
+int mdk_stitch_consensus_dev(int device, const float *probs_dev, int64_t n_rows, const int64_t *seg_base,
+                             int64_t n_seg, uint8_t *seq_out_dev, uint8_t *qual_out_dev, int64_t *seg_out_off);
+
 /* variant_columns (src/medaka_rnn_variants.h:26, called at medaka/labels.py:869-887): which pileup columns belong
  * to a variant run.  minor [len] pileup minor indices; reference / prediction [len] one byte per column (the
  * symbol or label code incl. the gap - the reference passes wchar_t strings, any 1-byte coding with the same
@@ -198,6 +213,13 @@ int mdk_variant_columns(int device, const int64_t *minor, const uint8_t *referen
  * hypotheses (0 = production encoding). */
 int mdk_selftest_umma(int device, const float *A, const float *B, float *D, int N, int K,
                       int variant);
+
+/* ---- diagnostics: cycle stamps of the recurrent kernel's hand-off points ------------------
+ * enable != 0 switches the (slower, instrumented) recurrent kernels on for subsequent forwards on `device` at batch
+ * sizes that run one tile per CTA; enable == 0 switches back.  If out is not NULL it first receives the stamps of
+ * the last traced forward: uint64 [2 layers][16 time steps (512..527)][16 slots] of %clock64 on CTA (0,0); the slot
+ * meanings are listed in tools/diag.py.  Not part of the hot path. */
+int mdk_debug_rec_trace(int device, int enable, uint64_t *out);
 
 #ifdef __cplusplus
 }

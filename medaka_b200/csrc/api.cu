@@ -699,4 +699,11 @@ int mdk_selftest_umma(int device, const float *A, const float *B, float *D, int 
     return selftest_umma(device, A, B, D, N, K, variant);
 }
 
+int mdk_debug_rec_trace(int device, int enable, uint64_t *out) {
+    MDK_CUDA(cudaSetDevice(device));
+    MDK_CUDA(cudaDeviceSynchronize());
+    MDK_CUDA(rec_trace_control(enable, reinterpret_cast<unsigned long long *>(out)));
+    return MDK_OK;
+}
+
 }  // extern "C"

@@ -142,6 +142,7 @@ struct RecXArgs {            // fused layer-0 input projection (rec_tc FUSE_X)
     const float *bias;       // LayerWeights::bias_gi
     int F;
 };
+cudaError_t rec_trace_control(int enable, unsigned long long *host_out);
 cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
                           void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, cudaStream_t s);
 cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const float *bias, float *gi, int64_t P,

@@ -109,10 +109,19 @@ struct RecX {
     int F;
 };
 
-template <int NT, bool OUT_TILES, bool FUSE_X>
+// Diagnostics (TRACE instantiations only, selected by mdk_debug_rec_trace): CTA (0,0) stamps %clock64 at the hand-off
+// points of time steps [RT_TRACE_STEP0, +RT_TRACE_STEPS) into trace[step][slot]; slots are listed in tools/diag.py.
+constexpr int RT_TRACE_STEP0 = 512, RT_TRACE_STEPS = 16, RT_TRACE_SLOTS = 16;
+#define REC_STAMP(slot)                                       \
+    do {                                                      \
+        if (TRACE && tr) tr[slot] = (unsigned long long)clock64(); \
+    } while (0)
+
+template <int NT, bool OUT_TILES, bool FUSE_X, bool TRACE = false>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__ w_hh,
-              const float *__restrict__ b_hn, void *__restrict__ h_out, int64_t B, int64_t T) {
+              const float *__restrict__ b_hn, void *__restrict__ h_out, int64_t B, int64_t T,
+              unsigned long long *__restrict__ trace) {
     extern __shared__ __align__(128) uint8_t smem[];
     using L = RecCfg<NT, FUSE_X>;
     uint64_t *acc_ready = reinterpret_cast<uint64_t *>(smem + L::bar_off);   // split: r and z blocks only
@@ -144,7 +153,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
     if (tid == 0) {
         for (int i = 0; i < NT; ++i) {
             mbar_init(&acc_ready[i], L::split ? 2 : RT_MMA_WARPS);
-            mbar_init(&h_ready[i], RT_GATE_WARPS / NT);    // one arrival per gate warp (lane 0 after __syncwarp)
+            mbar_init(&h_ready[i], 32 * RT_GATE_WARPS / NT);
             mbar_init(&acc_n[i], 1);
             mbar_init(&rz_issued[i], 2);
         }
@@ -202,15 +211,18 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         const uint64_t wx_desc0 = make_smem_desc(smem_u32(smem + L::wx_off), H * 16, 128);
         for (int64_t step = 0; step < T; ++step) {
             const uint32_t par = (uint32_t)(step & 1);
+            unsigned long long *tr = nullptr;
+            if (TRACE && trace && blockIdx.x == 0 && blockIdx.y == 0 && step >= RT_TRACE_STEP0 &&
+                step < RT_TRACE_STEP0 + RT_TRACE_STEPS)
+                tr = trace + (step - RT_TRACE_STEP0) * RT_TRACE_SLOTS;
 #pragma unroll
             for (int tile = 0; tile < NT; ++tile) {
-                if (lane == 0) {
-                    mbar_wait(&h_ready[tile], par);
-                    if (L::split && g == 2) mbar_wait(&rz_issued[tile], par);   // let the r/z MMAs into the pipe first
-                }
-                __syncwarp();
+                mbar_wait(&h_ready[tile], par);
+                if (L::split && g == 2) mbar_wait(&rz_issued[tile], par);   // let the r/z MMAs into the pipe first
                 tc_fence_after_sync();
                 if (elect_one()) {
+                    if (g == 0) REC_STAMP(0);
+                    if (g == 2) REC_STAMP(2);
                     const uint32_t d = L::acc_col0 + (uint32_t)(tile * L::acc_per_tile + g * 16);
 #pragma unroll
                     for (int prod = 0; prod < 3; ++prod) {
@@ -244,6 +256,8 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                         umma_commit(&acc_ready[tile]);
                         if (L::split) mbar_arrive(&rz_issued[tile]);
                     }
+                    if (g == 0) REC_STAMP(1);
+                    if (g == 2) REC_STAMP(3);
                 }
                 __syncwarp();
             }
@@ -321,17 +335,21 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             *reinterpret_cast<__half *>(xdst + RT_XPLANE) = lo;
             if (T > 1 && xok) xreg = xsrc[(dir ? (T - 2) : 1) * (int64_t)xin.F];
         }
-        // h_{-1} = 0 (and x_0) are in smem: publish (one mbarrier arrival per warp: 512 per-thread arrivals on one
-        // barrier serialise in the shared-memory atomics unit)
+        // h_{-1} = 0 (and x_0) are in smem: publish.  (Per-thread arrivals and all-lane polling are deliberate: electing
+        // one lane per warp for the barrier traffic measured 35 % SLOWER - the extra __syncwarp sits on the critical
+        // path while the mbarrier unit absorbs 512 arrivals without trouble.)
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&h_ready[tile]);
+        mbar_arrive(&h_ready[tile]);
 
         for (int64_t step = 0; step < T; ++step) {
             const bool more = step + 1 < T;
-            if (lane == 0) mbar_wait(&acc_ready[tile], (uint32_t)(step & 1));   // one poller per warp
-            __syncwarp();
+            unsigned long long *tr = nullptr;
+            if (TRACE && trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && step >= RT_TRACE_STEP0 &&
+                step < RT_TRACE_STEP0 + RT_TRACE_STEPS)
+                tr = trace + (step - RT_TRACE_STEP0) * RT_TRACE_SLOTS;
+            mbar_wait(&acc_ready[tile], (uint32_t)(step & 1));
+            REC_STAMP(4);
             tc_fence_after_sync();
             uint32_t ar[NC], az[NC], an[NC], ax[NC];
             if constexpr (NC == 8) {
@@ -350,6 +368,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 }
             }
             tmem_ld_wait();
+            REC_STAMP(5);
             if (!FUSE_X) gptr += tstep * GI_COLS;          // rows of the next time step
             __half hh[NC], hl[NC];
             __half *tb = nullptr;
@@ -373,10 +392,11 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 r2[q] = f2_mul(eb, inv);
                 z2[q] = f2_mul(ea, inv);
             }
+            REC_STAMP(6);
             if (L::split) {
                 // the n-gate accumulators arrive while the sigmoids above were running
-                if (lane == 0) mbar_wait(&acc_n[tile], (uint32_t)(step & 1));
-                __syncwarp();
+                mbar_wait(&acc_n[tile], (uint32_t)(step & 1));
+                REC_STAMP(7);
                 tc_fence_after_sync();
                 if constexpr (NC == 8) {
                     tmem_ld_x8(t_lane + 2 * 16, an);
@@ -387,6 +407,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 }
                 tmem_ld_wait();
             }
+            REC_STAMP(8);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
                 const F2 accn = f2_make(__uint_as_float(an[2 * q]), __uint_as_float(an[2 * q + 1]));
@@ -424,10 +445,12 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             }
             // publish the next B operand first: everything below (global stores of this step's output, loads of the
             // next step's pre-activations / features) is off the MMA -> gate -> MMA critical path
+            REC_STAMP(9);
             fence_proxy_async_smem();     // h / x tile writes -> visible to the MMA's async-proxy reads
             tc_fence_before_sync();       // order our tcgen05.ld before the next MMA overwrites the accumulators
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&h_ready[tile]);
+            REC_STAMP(10);
+            mbar_arrive(&h_ready[tile]);
+            REC_STAMP(11);
             if (tile_ok) {
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
@@ -458,6 +481,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 const int64_t t = dir ? (T - 1 - step) : step;
                 xreg = xsrc[(dir ? (t - 2) : (t + 2)) * (int64_t)xin.F];
             }
+            REC_STAMP(12);
         }
     }
     tc_fence_before_sync();
@@ -466,6 +490,26 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 512);
     }
+}
+
+static unsigned long long *g_rec_trace = nullptr;   // device buffer [2 layers][steps][slots]; null = tracing off
+
+cudaError_t rec_trace_control(int enable, unsigned long long *host_out) {
+    const size_t bytes = 2 * RT_TRACE_STEPS * RT_TRACE_SLOTS * sizeof(unsigned long long);
+    if (host_out && g_rec_trace) {
+        cudaError_t e = cudaMemcpy(host_out, g_rec_trace, bytes, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return e;
+    }
+    if (enable && !g_rec_trace) {
+        cudaError_t e = cudaMalloc(&g_rec_trace, bytes);
+        if (e != cudaSuccess) return e;
+        return cudaMemset(g_rec_trace, 0, bytes);
+    }
+    if (!enable && g_rec_trace) {
+        cudaFree(g_rec_trace);
+        g_rec_trace = nullptr;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
@@ -477,14 +521,29 @@ cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w
     RecX xin{nullptr, nullptr, nullptr, 0};
     if (fuse) xin = RecX{fuse->feats, fuse->w_x, fuse->bias, fuse->F};
     cudaError_t e;
-#define MDK_LAUNCH_REC(NTV, OT, FX)                                                                          \
+    unsigned long long *trace = nullptr;
+#define MDK_LAUNCH_REC_T(NTV, OT, FX, TR)                                                                    \
     do {                                                                                                     \
-        auto kern = rec_tc_kernel<NTV, OT, FX>;                                                              \
+        auto kern = rec_tc_kernel<NTV, OT, FX, TR>;                                                          \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecCfg<NTV, FX>::total); \
         if (e != cudaSuccess) return e;                                                                      \
         dim3 grid((unsigned)((tiles + NTV - 1) / NTV), NDIR);                                                \
-        kern<<<grid, RT_THREADS, RecCfg<NTV, FX>::total, s>>>(gi, xin, w_hh_tm, b_hn, h_out, B, T);          \
+        kern<<<grid, RT_THREADS, RecCfg<NTV, FX>::total, s>>>(gi, xin, w_hh_tm, b_hn, h_out, B, T, trace);   \
     } while (0)
+#define MDK_LAUNCH_REC(NTV, OT, FX) MDK_LAUNCH_REC_T(NTV, OT, FX, false)
+    if (g_rec_trace && !two && T >= RT_TRACE_STEP0 + RT_TRACE_STEPS) {
+        // diagnostics: the two shapes the engine uses at NT = 1 (fused layer 0 -> tiles, layer 1 -> fp32 rows)
+        if (fuse && out_tiles) {
+            trace = g_rec_trace;
+            MDK_LAUNCH_REC_T(1, true, true, true);
+            return cudaGetLastError();
+        }
+        if (!fuse && !out_tiles) {
+            trace = g_rec_trace + RT_TRACE_STEPS * RT_TRACE_SLOTS;
+            MDK_LAUNCH_REC_T(1, false, false, true);
+            return cudaGetLastError();
+        }
+    }
     if (fuse) {
         if (!out_tiles) return cudaErrorInvalidValue;   // the fused projection is layer 0, which feeds the GEMM
         if (two) MDK_LAUNCH_REC(2, true, true); else MDK_LAUNCH_REC(1, true, true);
@@ -494,6 +553,7 @@ cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w
         if (out_tiles) MDK_LAUNCH_REC(1, true, false); else MDK_LAUNCH_REC(1, false, false);
     }
 #undef MDK_LAUNCH_REC
+#undef MDK_LAUNCH_REC_T
     return cudaGetLastError();
 }
 

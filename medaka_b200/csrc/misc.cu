@@ -315,8 +315,11 @@ cudaError_t launch_inproj0(const float *feats, const float *w_packed, const floa
 // Head: logits = h1 . W^T + b (gru.py:67), probs = softmax (gru.py:71), label = argmax (labels.py:1063)
 // One warp per position, 8 of the 256 inputs per lane; 1 KiB read + 41 B written per position.
 // =====================================================================================
-// R = number of h1 rows (P, or the tile-interleaved row count which includes padding windows); outputs always go to
-// position p = w*T + t.
+// Outputs always go to position p = w*T + t; on the tensor-core path the h1 row of that position is the
+// tile-interleaved row(w, t).  Each warp handles 4 positions per iteration: 8 of the 256 inputs per lane, the
+// 4 x 5 (padded to 4 x 8) partial dot products are reduced with a transposing butterfly (31 shuffles for all 32
+// values instead of 5 per value), after which lane L owns logit (position L/8, class L%8) and the softmax / argmax
+// run across the 8-lane groups - one expf per lane instead of five per lane.
 __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1, const float *__restrict__ lin_w,
                                                    const float *__restrict__ lin_b, int64_t P, int64_t B, int64_t T,
                                                    int tiled, float *__restrict__ probs, float *__restrict__ logits,
@@ -332,15 +335,9 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1,
         w[c][0] = a.x; w[c][1] = a.y; w[c][2] = a.z; w[c][3] = a.w;
         w[c][4] = b.x; w[c][5] = b.y; w[c][6] = b.z; w[c][7] = b.w;
     }
-    float bias[NCLS];
-#pragma unroll
-    for (int c = 0; c < NCLS; ++c) bias[c] = lin_b[c];
-    // PU positions per warp iteration: all 2*PU 16-byte loads are issued before any is consumed, so each warp keeps
-    // 4 KiB in flight (the kernel is a pure 1 KiB/position HBM stream; one position at a time left it latency-bound
-    // at 2.6 TB/s)
+    const int cls = lane & 7;                      // class owned by this lane after the reduction
+    const float my_bias = cls < NCLS ? lin_b[cls] : 0.f;
     constexpr int PU = 4;
-    // iterate in OUTPUT order (consecutive positions of one window) so the stores stay coalesced; on the tensor-core
-    // path the h1 row of position p = w*T + t is the tile-interleaved row(w, t), a 1 KiB contiguous read either way
     for (int64_t pb = warp * PU; pb < P; pb += nwarps * PU) {
         float4 va[PU], vb[PU];
 #pragma unroll
@@ -350,47 +347,58 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1,
             va[u] = ld_stream4(h1 + r * H2 + lane * 8);
             vb[u] = ld_stream4(h1 + r * H2 + lane * 8 + 4);
         }
+        float v[32];
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
-            const int64_t p = pb + u;
             const float x[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-            float acc[NCLS];
 #pragma unroll
-            for (int c = 0; c < NCLS; ++c) {
+            for (int c = 0; c < 8; ++c) {
                 float s = 0.f;
+                if (c < NCLS) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) s = fmaf(x[i], w[c][i], s);
-                acc[c] = s;
+                    for (int i = 0; i < 8; ++i) s = fmaf(x[i], w[c][i], s);
+                }
+                v[u * 8 + c] = s;
             }
+        }
+        // transposing butterfly: after the step with mask m a lane keeps the half of its values selected by (lane & m)
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
+        for (int m = 16, cnt = 16; m >= 1; m >>= 1, cnt >>= 1) {
+            const bool hi = (lane & m) != 0;
 #pragma unroll
-                for (int c = 0; c < NCLS; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+            for (int i = 0; i < cnt; ++i) {
+                const float send = hi ? v[i] : v[i + cnt];
+                const float keep = hi ? v[i + cnt] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
             }
-            if (p >= P) continue;
-            float l[NCLS];
-            float m = -INFINITY;
+        }
+        // lane L: logit of position pb + L/8, class L%8 (classes 5..7 are padding)
+        const float logit = cls < NCLS ? v[0] + my_bias : -INFINITY;
+        float mx = logit;
 #pragma unroll
-            for (int c = 0; c < NCLS; ++c) { l[c] = acc[c] + bias[c]; m = fmaxf(m, l[c]); }
-            float e[NCLS], sum = 0.f;
+        for (int m = 4; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+        const float e = cls < NCLS ? expf(logit - mx) : 0.f;
+        float e0 = __shfl_sync(0xffffffffu, e, (lane & 24) + 0), e1 = __shfl_sync(0xffffffffu, e, (lane & 24) + 1),
+              e2 = __shfl_sync(0xffffffffu, e, (lane & 24) + 2), e3 = __shfl_sync(0xffffffffu, e, (lane & 24) + 3),
+              e4 = __shfl_sync(0xffffffffu, e, (lane & 24) + 4);
+        const float sum = (((e0 + e1) + e2) + e3) + e4;          // class order, like a sequential softmax
+        const float pr = e / sum;
+        // argmax over the 5 probabilities, first maximum wins (np.argmax, labels.py:1063)
+        float best = cls < NCLS ? pr : -1.f;
+        int arg = cls;
 #pragma unroll
-            for (int c = 0; c < NCLS; ++c) { e[c] = expf(l[c] - m); sum += e[c]; }
-            float pr[NCLS];
-#pragma unroll
-            for (int c = 0; c < NCLS; ++c) pr[c] = e[c] / sum;
-            if (lane < NCLS) {
-                float lv = l[0], pv = pr[0];
-#pragma unroll
-                for (int c = 1; c < NCLS; ++c) if (lane == c) { lv = l[c]; pv = pr[c]; }
-                probs[p * NCLS + lane] = pv;
-                if (logits) logits[p * NCLS + lane] = lv;
+        for (int m = 4; m >= 1; m >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, m);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, m);
+            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        const int64_t p = pb + (lane >> 3);
+        if (p < P) {
+            if (cls < NCLS) {
+                probs[p * NCLS + cls] = pr;
+                if (logits) logits[p * NCLS + cls] = logit;
             }
-            if (labels && lane == 0) {
-                float best = pr[0]; int arg = 0;
-#pragma unroll
-                for (int c = 1; c < NCLS; ++c) if (pr[c] > best) { best = pr[c]; arg = c; }
-                labels[p] = (uint8_t)arg;
-            }
+            if (labels && cls == 0) labels[p] = (uint8_t)arg;
         }
     }
 }

@@ -178,3 +178,73 @@ def synth_reads(n_reads, ref_len, seed=0, mean_len=3000, p_ins=0.04, p_del=0.04,
                          flag=flag, mapq=mapq, tags=tags))
     recs.sort(key=lambda r: r["pos"])
     return recs
+
+
+def synth_stitch_stream(seed=0, n_major=3000, first_major=1000, chunk_len=400, overlap=100, p_ins=0.08,
+                        ragged=(), drop=(), nest=(), low_depth=(), ref_name='contig1'):
+    """A stream of network-output samples as `medaka consensus` stores them, for the stitching tests.
+
+    One pileup (majors first_major .. first_major+n_major-1, random insertion columns) is cut into overlapping
+    chunks like Sample.chunks.  Perturbations, all by chunk index:
+      ragged    - delete one insertion column inside the chunk's leading overlap (the two neighbours then disagree
+                  on the columns of their overlap -> junction heuristic)
+      drop      - remove the chunk from the stream (-> gap between its neighbours when overlap < chunk_len / 2)
+      nest      - insert after the chunk a short extra sample lying completely inside it
+      low_depth - (chunk, a, b): set depth to 1 on columns [a, b) of the chunk
+
+    :returns: list of dicts {ref_name, positions, label_probs float32 [n,5], depth int64 [n]}.
+    """
+    rs = np.random.RandomState(seed)
+    n_ins = rs.geometric(1.0 - p_ins, size=n_major) - 1
+    n_ins = np.minimum(n_ins, 4)
+    counts = 1 + n_ins
+    major = np.repeat(np.arange(first_major, first_major + n_major), counts)
+    starts = np.cumsum(counts) - counts
+    minor = np.arange(len(major)) - np.repeat(starts, counts)
+    positions = np.empty(len(major), dtype=[('major', int), ('minor', int)])
+    positions['major'], positions['minor'] = major, minor
+    n = len(positions)
+
+    def make(lo, hi, sub_seed):
+        r = np.random.RandomState(sub_seed)
+        pos = positions[lo:hi].copy()
+        logits = r.randn(hi - lo, 5).astype(np.float32) * 3.0
+        logits[pos['minor'] > 0, 0] += 4.0            # insertion columns are mostly gap calls
+        logits[pos['minor'] == 0, 0] -= 2.0
+        e = np.exp(logits - logits.max(-1, keepdims=True))
+        probs = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+        sure = r.rand(hi - lo) < 0.3                   # confident calls: exercise the quality cap
+        probs[sure] = np.eye(5, dtype=np.float32)[np.argmax(probs[sure], -1)] * np.float32(0.99999994) \
+            if sure.any() else probs[sure]
+        depth = r.randint(20, 60, size=hi - lo).astype(np.int64)
+        return dict(ref_name=ref_name, positions=pos, label_probs=probs, depth=depth)
+
+    ranges = []
+    step = chunk_len - overlap
+    last_end = 0
+    for lo in range(0, n - chunk_len + 1, step):
+        ranges.append((lo, lo + chunk_len))
+        last_end = lo + chunk_len
+    if n > last_end:
+        ranges.append((max(0, n - chunk_len), n))
+    stream = []
+    low = {c: (a, b) for c, a, b in low_depth}
+    for c, (lo, hi) in enumerate(ranges):
+        if c in drop:
+            continue
+        s = make(lo, hi, seed * 1000 + c)
+        if c in ragged:
+            cand = np.flatnonzero(s['positions']['minor'][:overlap] > 0)
+            # only a trailing insertion column can go without leaving a hole in the minor numbering
+            nxt = np.append(s['positions']['minor'][1:], 0)
+            cand = [k for k in cand if nxt[k] == 0 and 5 < k < overlap - 5]
+            if cand:
+                k = cand[len(cand) // 2]
+                s = {key: (np.delete(v, k, axis=0) if key != 'ref_name' else v) for key, v in s.items()}
+        if c in low:
+            a, b = low[c]
+            s['depth'][a:b] = 1
+        stream.append(s)
+        if c in nest:
+            stream.append(make(lo + chunk_len // 4, lo + chunk_len // 2, seed * 1000 + 500 + c))
+    return stream

@@ -125,7 +125,44 @@ def check_determinism(arg):
     return res
 
 
-CHECKS = {"selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism}
+TRACE_SLOTS = ["issuer_r: h_ready seen", "issuer_r: MMAs queued + commit", "issuer_n: rz_issued seen",
+               "issuer_n: MMAs queued + commit", "gate: acc_ready (r,z) seen", "gate: r,z tcgen05.ld done",
+               "gate: sigmoids done", "gate: acc_n seen", "gate: n tcgen05.ld done", "gate: h tile written",
+               "gate: proxy fence done", "gate: arrived on h_ready", "gate: end of step (global stores queued)"]
+
+
+def check_rec_trace(arg):
+    """Cycle stamps of the recurrent kernel's hand-off points on CTA (0,0), steps 512..527 (NT = 1 shapes only)."""
+    from medaka_b200 import libmedaka as lm, models
+    from oracle import synth
+    B, T = (int(x) for x in arg.split(","))
+    lib, ffi = lm.load(), lm.ffi
+    m = models.GRUModel()
+    m.load_state_dict(synth.synth_state_dict(0))
+    feats = synth.synth_features_fast(B, T, 10, seed=3)
+    m.forward_arrays(feats)                                        # warm-up, untraced
+    base = m.last_timings()
+    lm.check(lib.mdk_debug_rec_trace(0, 1, ffi.NULL))
+    m.forward_arrays(feats)
+    traced = m.last_timings()
+    buf = np.zeros((2, 16, 16), dtype=np.uint64)
+    lm.check(lib.mdk_debug_rec_trace(0, 0, ffi.cast("uint64_t *", ffi.from_buffer(buf))))
+    res = {"untraced_ms": base, "traced_ms": traced}
+    for layer in (0, 1):
+        t = buf[layer].astype(np.int64)
+        # every stamp relative to the moment the r issuer saw h_ready of the same step
+        rel = t[:, :13] - t[:, :1]
+        period = np.diff(t[:, 0])
+        res["layer%d" % layer] = {
+            "step_cycles_median": float(np.median(period)),
+            "median_offset_from_h_ready_seen": {TRACE_SLOTS[k]: float(np.median(rel[:, k])) for k in range(13)},
+            "raw_first_step": [int(x) for x in rel[1]],
+        }
+    return res
+
+
+CHECKS = {"selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism,
+          "rec_trace": check_rec_trace}
 
 PLAN = [
     ("determinism", "fp32,20,64"), ("determinism", "fp32,37,130"), ("determinism", "tc,200,300"),
