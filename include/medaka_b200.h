@@ -217,7 +217,7 @@ int mdk_selftest_umma(int device, const float *A, const float *B, float *D, int 
 /* ---- diagnostics: cycle stamps of the recurrent kernel's hand-off points ------------------
  * enable != 0 switches the (slower, instrumented) recurrent kernels on for subsequent forwards on `device` at batch
  * sizes that run one tile per CTA; enable == 0 switches back.  If out is not NULL it first receives the stamps of
- * the last traced forward: uint64 [2 layers][16 time steps (512..527)][16 slots] of %clock64 on CTA (0,0); the slot
+ * the last traced forward: uint64 [2 layers][16 time steps (512..527)][32 slots] of %clock64 on CTA (0,0); the slot
  * meanings are listed in tools/diag.py.  Not part of the hot path. */
 int mdk_debug_rec_trace(int device, int enable, uint64_t *out);
 

@@ -111,7 +111,9 @@ struct RecX {
 
 // Diagnostics (TRACE instantiations only, selected by mdk_debug_rec_trace): CTA (0,0) stamps %clock64 at the hand-off
 // points of time steps [RT_TRACE_STEP0, +RT_TRACE_STEPS) into trace[step][slot]; slots are listed in tools/diag.py.
-constexpr int RT_TRACE_STEP0 = 512, RT_TRACE_STEPS = 16, RT_TRACE_SLOTS = 16;
+constexpr int GI_PREFETCH_STEPS = 3;
+constexpr int X_PREFETCH_EVERY = 8, X_PREFETCH_AHEAD = 16;   // feature rows: 8 steps at a time, 16..23 steps ahead
+constexpr int RT_TRACE_STEP0 = 512, RT_TRACE_STEPS = 16, RT_TRACE_SLOTS = 32;
 #define REC_STAMP(slot)                                       \
     do {                                                      \
         if (TRACE && tr) tr[slot] = (unsigned long long)clock64(); \
@@ -258,6 +260,37 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                     }
                     if (g == 0) REC_STAMP(1);
                     if (g == 2) REC_STAMP(3);
+                    if (FUSE_X && g == 2 && (step & (X_PREFETCH_EVERY - 1)) == 0) {
+                        // feature rows of this tile, X_PREFETCH_AHEAD.. steps from now, into L2: the gate warps load
+                        // them two steps ahead of use, which covers an L2 hit but not always a DRAM miss
+                        const int64_t wt = (int64_t)blockIdx.x * NT + tile;
+                        const int64_t s0 = step + X_PREFETCH_AHEAD;                    // first step covered
+                        const int64_t s1 = s0 + X_PREFETCH_EVERY <= T ? s0 + X_PREFETCH_EVERY : T;   // one past the last
+                        if (s0 < T) {
+                            const int64_t t_lo = dir ? (T - s1) : s0;                  // lowest time index of the span
+                            const int64_t nbytes = (s1 - s0) * xin.F * 4;
+                            for (int w = 0; w < WT; ++w) {
+                                if (wt * WT + w >= B) break;
+                                const uintptr_t a = reinterpret_cast<uintptr_t>(xin.feats + ((wt * WT + w) * T + t_lo) * xin.F);
+                                const uintptr_t a0 = a & ~(uintptr_t)15;
+                                bulk_prefetch_l2(reinterpret_cast<const void *>(a0),
+                                                 (uint32_t)(((a + nbytes - a0) + 15) & ~(uintptr_t)15));
+                            }
+                        }
+                    }
+                    if (!FUSE_X && g == 2 && step + GI_PREFETCH_STEPS < T) {
+                        // pull the pre-activation rows the gate warps will load GI_PREFETCH_STEPS steps from now into
+                        // L2 (16 rows x 1.5 KiB of this direction): their register prefetch runs one step ahead, which
+                        // covers an L2 hit but not a DRAM miss (measured: ~600 cycles per step exposed without this)
+                        const int64_t wt = (int64_t)blockIdx.x * NT + tile;
+                        if (wt * WT < B) {
+                            const int64_t sp = step + GI_PREFETCH_STEPS;
+                            const int64_t t = dir ? (T - 1 - sp) : sp;
+                            const float *row = gi + ((wt * T + t) * WT) * GI_COLS + (int64_t)dir * G3;
+#pragma unroll
+                            for (int w = 0; w < WT; ++w) bulk_prefetch_l2(row + (int64_t)w * GI_COLS, G3 * 4);
+                        }
+                    }
                 }
                 __syncwarp();
             }
@@ -312,6 +345,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         int64_t orow = row0 + t_first * WT;                    // OUT_TILES: row -> (tile, row in tile)
         __half *o16 = reinterpret_cast<__half *>(h_out) + (int64_t)(kcol >> 3) * (XT_ROWS * 8) + (kcol & 7);
 
+        constexpr float EXP_CLAMP = 60.0f;
         const F2 one2 = f2_make(1.0f, 1.0f), neg2 = f2_make(-2.0f, -2.0f), negone2 = f2_make(-1.0f, -1.0f);
         const F2 knl2 = f2_make(-1.4426950408889634f, -1.4426950408889634f);     // -log2(e)
         const F2 k2l2 = f2_make(2.8853900817779268f, 2.8853900817779268f);       // 2 log2(e)
@@ -380,12 +414,14 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 const F2 accz = f2_make(__uint_as_float(az[2 * q]), __uint_as_float(az[2 * q + 1]));
                 const F2 pre_r = f2_add(FUSE_X ? br2 : g2[0][q], accr);
                 const F2 pre_z = f2_add(FUSE_X ? bz2 : g2[1][q], accz);
-                // r = sigmoid(pre_r), z = sigmoid(pre_z) with one reciprocal per element: 1/((1+e^-a)(1+e^-b))
+                // r = sigmoid(pre_r), z = sigmoid(pre_z) with one reciprocal per element: 1/((1+e^-a)(1+e^-b)).
+                // (Sharing one reciprocal between the two elements of a packed pair was tried: it saves 4 of 20 MUFU ops
+                // per thread-step but measured no gain, and it makes a window's bits depend on its batch neighbour.)
                 float a0, a1, b0, b1;
                 f2_get(f2_mul(pre_r, knl2), a0, a1);
                 f2_get(f2_mul(pre_z, knl2), b0, b1);
-                const F2 ea = f2_add(f2_make(ex2_approx(fminf(a0, 60.0f)), ex2_approx(fminf(a1, 60.0f))), one2);
-                const F2 eb = f2_add(f2_make(ex2_approx(fminf(b0, 60.0f)), ex2_approx(fminf(b1, 60.0f))), one2);
+                const F2 ea = f2_add(f2_make(ex2_approx(fminf(a0, EXP_CLAMP)), ex2_approx(fminf(a1, EXP_CLAMP))), one2);
+                const F2 eb = f2_add(f2_make(ex2_approx(fminf(b0, EXP_CLAMP)), ex2_approx(fminf(b1, EXP_CLAMP))), one2);
                 float p0, p1;
                 f2_get(f2_mul(ea, eb), p0, p1);
                 const F2 inv = f2_make(rcp_approx(p0), rcp_approx(p1));
@@ -418,7 +454,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 float t0, t1;
                 f2_get(f2_mul(f2_fma(r, f2_add(accn, bhn2), gin), k2l2), t0, t1);
                 float e0, e1;
-                f2_get(f2_add(f2_make(ex2_approx(fminf(t0, 60.0f)), ex2_approx(fminf(t1, 60.0f))), one2), e0, e1);
+                f2_get(f2_add(f2_make(ex2_approx(fminf(t0, EXP_CLAMP)), ex2_approx(fminf(t1, EXP_CLAMP))), one2), e0, e1);
                 const F2 nn = f2_fma(neg2, f2_make(rcp_approx(e0), rcp_approx(e1)), one2);
                 // h = (h_prev - n) * z + n   (ATen's gru_cell form)
                 const F2 h2 = f2_fma(f2_fma(nn, negone2, hprev2[q]), z, nn);
@@ -451,6 +487,15 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             REC_STAMP(10);
             mbar_arrive(&h_ready[tile]);
             REC_STAMP(11);
+            if (FUSE_X && xok && step + 2 < T) {
+                // feature value staged during the NEXT step (for the step after it); issued before this step's
+                // output stores so that it is not queued behind them
+                const int64_t t = dir ? (T - 1 - step) : step;
+                xreg = xsrc[(dir ? (t - 2) : (t + 2)) * (int64_t)xin.F];
+            }
+            if (TRACE && trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && step >= RT_TRACE_STEP0 &&
+                step < RT_TRACE_STEP0 + RT_TRACE_STEPS)     // slots 16..31: when each gate warp arrived
+                trace[(step - RT_TRACE_STEP0) * RT_TRACE_SLOTS + 16 + warp] = (unsigned long long)clock64();
             if (tile_ok) {
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
@@ -477,10 +522,6 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             }
             o32 += tstep * H2;
             orow += tstep;
-            if (FUSE_X && xok && step + 2 < T) {
-                const int64_t t = dir ? (T - 1 - step) : step;
-                xreg = xsrc[(dir ? (t - 2) : (t + 2)) * (int64_t)xin.F];
-            }
             REC_STAMP(12);
         }
     }

@@ -67,6 +67,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// L2 prefetch of a contiguous range (16-B aligned, size % 16 == 0); no destination, no completion tracking
+__device__ __forceinline__ void bulk_prefetch_l2(const void *gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---------------------------------------------------------------- bulk async copy (TMA engine, 1-D)
 // global -> shared, completion counted in bytes on an mbarrier.  16-B aligned, size % 16 == 0.
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {

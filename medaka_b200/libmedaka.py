@@ -16,7 +16,8 @@ import threading
 import cffi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmedaka_b200.so")
+# MDK_LIB_PATH points the binding at another build of the same library (A/B measurements)
+LIB_PATH = os.environ.get("MDK_LIB_PATH") or os.path.join(_HERE, "libmedaka_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "medaka_b200.h")
 
 ffi = cffi.FFI()

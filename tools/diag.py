@@ -145,7 +145,7 @@ def check_rec_trace(arg):
     lm.check(lib.mdk_debug_rec_trace(0, 1, ffi.NULL))
     m.forward_arrays(feats)
     traced = m.last_timings()
-    buf = np.zeros((2, 16, 16), dtype=np.uint64)
+    buf = np.zeros((2, 16, 32), dtype=np.uint64)
     lm.check(lib.mdk_debug_rec_trace(0, 0, ffi.cast("uint64_t *", ffi.from_buffer(buf))))
     res = {"untraced_ms": base, "traced_ms": traced}
     for layer in (0, 1):
@@ -157,6 +157,7 @@ def check_rec_trace(arg):
             "step_cycles_median": float(np.median(period)),
             "median_offset_from_h_ready_seen": {TRACE_SLOTS[k]: float(np.median(rel[:, k])) for k in range(13)},
             "raw_first_step": [int(x) for x in rel[1]],
+            "gate_warp_arrivals_median": [float(x) for x in np.median(t[:, 16:32] - t[:, :1], axis=0)],
         }
     return res
 
