@@ -51,6 +51,19 @@ constexpr int WT = 16;
 __host__ __device__ inline int64_t tiled_rows(int64_t B, int64_t T) { return ((B + WT - 1) / WT) * WT * T; }
 __host__ __device__ inline int64_t tiled_row(int64_t w, int64_t t, int64_t T) { return ((w / WT) * T + t) * WT + (w % WT); }
 
+// gi (gate pre-activations) on the tensor-core path is stored in QUAD layout: per tile-step ts = tiled row / 16 (the 16
+// windows of a tile at one time step) a 48 KiB block  [blk = dir*3 + gate (6)][cg = window quad (4)][j (128)][w4 (4)]
+// of floats.  A recurrent-kernel thread (hidden unit j, window quad cg) then reads its 3 gates x 4 windows as three
+// 16-byte loads that are contiguous across the warp (512 B per load), the projection GEMM's epilogue thread (row j of
+// block blk) writes 16-byte vectors that are contiguous across its warp, and the (ts, dir) block a CTA needs next is
+// one contiguous 24 KiB range for the L2 prefetch.
+constexpr int GI_TS_FLOATS = 6 * 4 * H * 4;   // 12288 floats per tile-step
+__host__ __device__ inline int64_t gi_quad_index(int64_t tiled_row, int col) {
+    const int64_t ts = tiled_row >> 4;
+    const int w = (int)(tiled_row & 15), blk = col / H, j = col % H;
+    return ((((ts * 6 + blk) * 4 + (w >> 2)) * H + j) << 2) + (w & 3);
+}
+
 struct LayerWeights {
     // fp32 originals (device), torch layout
     float *w_ih[NDIR] = {nullptr, nullptr};  // [3H][in]

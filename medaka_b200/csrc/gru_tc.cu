@@ -47,6 +47,20 @@ __device__ __forceinline__ float tanh_fast(float x) {
     return fmaf(-2.0f, rcp_approx(1.0f + e), 1.0f);
 }
 
+// 1 / d for d = -nd >= 1 on the FMA pipe (packed pairs): integer seed (5 % error), one cubic step, one Newton step
+// -> 1.7e-8 relative.  The gate phase is bound by the MUFU (XU) pipe - ncu: mio_throttle is its top stall, XU 33 % of
+// the whole step while the FMA pipe sits at 13 % (profiles/r01e_*) - so the reciprocals that are on the critical path
+// are moved off it.  Takes -d because the callers get the negation for free from an FMA.
+__device__ __forceinline__ F2 rcp_neg_fma2(F2 nd, F2 one2) {
+    float a, b;
+    f2_get(nd, a, b);
+    F2 y = f2_make(__uint_as_float(0xFEF311C7u - __float_as_uint(a)), __uint_as_float(0xFEF311C7u - __float_as_uint(b)));
+    F2 e = f2_fma(nd, y, one2);          // 1 - d*y
+    y = f2_fma(y, f2_fma(e, e, e), y);   // y * (1 + e + e^2)
+    e = f2_fma(nd, y, one2);
+    return f2_fma(y, e, y);
+}
+
 // =====================================================================================================
 // Recurrent kernel.  One CTA = NT tiles of 16 windows of one direction, for the whole sequence.
 //   warps 0-15  : gate warps (TMEM -> registers -> gate math -> next h into smem + global output); warp w reads
@@ -76,6 +90,27 @@ constexpr int RT_XBUF = 2 * RT_XPLANE;                   // hi + lo
 constexpr int RT_GATE_WARPS = 16;                        // 4 per scheduler: the gate phase is latency-bound
 constexpr int RT_MMA_WARPS = 3;                          // one issuer per gate block (24 MMAs each per tile-step)
 constexpr int RT_THREADS = 32 * (RT_GATE_WARPS + RT_MMA_WARPS);
+// Hand-off protocol.  MDK_REC_NB = 1 (default): the gate warps -> issuers hand-off ("h tile written") is a NAMED hardware
+// barrier (bar.arrive by the 16 gate warps, bar.sync by the issuers): the cycle trace (profiles/r01e) shows the issuers
+// released ~70 cycles after the last gate warp arrives, against ~190 with 512 per-thread mbarrier arrivals.  The
+// accumulator hand-off stays an mbarrier (tcgen05.commit needs one) polled by the gate warps directly: relaying it
+// through an issuer warp and a named barrier measured slower.  MDK_REC_NB = 0 keeps the all-mbarrier protocol (A/B).
+#ifndef MDK_REC_NB
+#define MDK_REC_NB 1
+#endif
+constexpr bool RT_NB = MDK_REC_NB != 0;
+#ifndef MDK_REC_POLL1
+#define MDK_REC_POLL1 1
+#endif
+#if MDK_REC_POLL1
+#define GATE_WAIT(bar, par) mbar_wait_warp(bar, par)
+#else
+#define GATE_WAIT(bar, par) mbar_wait(bar, par)
+#endif
+constexpr int RT_BAR_H = 1;        // ids 1, 2: h tile of tile 0 / 1 written (gate warps arrive, issuers sync)
+constexpr int RT_BAR_R = 3;        // NT == 1: r / z / n accumulators complete (relay warp arrives, gate warps sync)
+constexpr int RT_BAR_Z = 4;
+constexpr int RT_BAR_N = 5;
 constexpr int RT_WT_COLS = 2 * 3 * (H / 2);              // W_hh hi+lo as TMEM A operand: 384 columns
 constexpr int RT_WX_COLS = 2 * 3 * 8;                    // W_ih (K = 16) hi+lo as TMEM A operand: 48 columns
 constexpr int RT_WX_BLOCK = H * 16 * 2;                  // one (part, gate) block of W_ih in smem: [kg 2][row 128][8] = 4 KiB
@@ -83,6 +118,7 @@ constexpr int RT_WX_BLOCK = H * 16 * 2;                  // one (part, gate) blo
 template <int NT, bool FUSE_X>
 struct RecCfg {
     static constexpr bool wx_tmem = FUSE_X && NT == 1;
+    // accumulator columns per tile: r, z, n (16 each) [+ W_in.x of the n gate]
     static constexpr int acc_per_tile = FUSE_X ? 64 : 48;
     static constexpr uint32_t wx_col0 = RT_WT_COLS;
     static constexpr uint32_t acc_col0 = RT_WT_COLS + (wx_tmem ? RT_WX_COLS : 0);
@@ -95,10 +131,19 @@ struct RecCfg {
     static constexpr bool split = (NT == 1);
     static constexpr int bar_off = wx_off + 6 * RT_WX_BLOCK;               // acc_ready[NT], h_ready[NT], acc_n[NT], rz_issued[NT]
     static constexpr int tmem_off = bar_off + 4 * NT * 8;
+    // NT == 1 reading gi (layer 1): the 24 KiB block of (tile-step, direction) is staged in shared memory by a bulk
+    // async copy two steps ahead (3 buffers), so the gate warps read their pre-activations with three LDS.128 instead of
+    // streaming 24 KiB per step through the LSU global path, which cost them 400-900 cycles per step (cycle trace)
+    static constexpr bool gi_smem = !FUSE_X && NT == 1;
+    static constexpr int GI_BUFS = 3;
+    static constexpr int GI_BLOCK = (GI_TS_FLOATS / 2) * 4;                // 24 576 bytes
+    static constexpr int gibar_off = tmem_off + 16;                        // gi_full[GI_BUFS]
+    static constexpr int gi_off = ((gibar_off + GI_BUFS * 8 + 127) / 128) * 128;
+    static constexpr int gi_end = gi_off + (gi_smem ? GI_BUFS * GI_BLOCK : 0);
     // the CTA owns all 512 TMEM columns of its SM, so a second co-resident CTA could only spin in tcgen05.alloc;
     // ask for > half of the shared memory to keep residency at one CTA per SM.
-    static constexpr int total = 120 * 1024;
-    static_assert(tmem_off + 16 <= total, "smem budget");
+    static constexpr int total = gi_end > 120 * 1024 ? gi_end : 120 * 1024;
+    static_assert(total <= 227 * 1024, "smem budget");
 };
 
 // arguments of the fused input projection (layer 0)
@@ -113,7 +158,7 @@ struct RecX {
 // points of time steps [RT_TRACE_STEP0, +RT_TRACE_STEPS) into trace[step][slot]; slots are listed in tools/diag.py.
 constexpr int GI_PREFETCH_STEPS = 3;
 constexpr int X_PREFETCH_EVERY = 8, X_PREFETCH_AHEAD = 16;   // feature rows: 8 steps at a time, 16..23 steps ahead
-constexpr int RT_TRACE_STEP0 = 512, RT_TRACE_STEPS = 16, RT_TRACE_SLOTS = 32;
+constexpr int RT_TRACE_STEP0 = 512, RT_TRACE_STEPS = 16, RT_TRACE_SLOTS = 40;
 #define REC_STAMP(slot)                                       \
     do {                                                      \
         if (TRACE && tr) tr[slot] = (unsigned long long)clock64(); \
@@ -126,6 +171,14 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
               unsigned long long *__restrict__ trace) {
     extern __shared__ __align__(128) uint8_t smem[];
     using L = RecCfg<NT, FUSE_X>;
+    // NT == 1 writing operand tiles (layer 0): the h tile the gate warps publish in shared memory already IS the tile
+    // image the projection GEMM wants (per k-group 16 rows x 16 B contiguous), so warp 18 copies it out with 32 bulk
+    // async copies per step instead of 8 two-byte global stores per gate thread.
+    constexpr bool BULK_OUT = OUT_TILES && NT == 1;
+    constexpr int NB_N_COUNT = 32 * RT_GATE_WARPS + (BULK_OUT ? 64 : 32);   // BAR_N: gate warps + relay (+ copy-out warp)
+    constexpr bool GI_SMEM = L::gi_smem;
+    constexpr int NB_R_COUNT = 32 * RT_GATE_WARPS + (GI_SMEM ? 64 : 32);    // BAR_R: gate warps + relay (+ gi staging warp)
+    uint64_t *gi_full = reinterpret_cast<uint64_t *>(smem + L::gibar_off);
     uint64_t *acc_ready = reinterpret_cast<uint64_t *>(smem + L::bar_off);   // split: r and z blocks only
     uint64_t *h_ready = acc_ready + NT;
     uint64_t *acc_n = h_ready + NT;          // split: n block(s)
@@ -154,11 +207,13 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
     }
     if (tid == 0) {
         for (int i = 0; i < NT; ++i) {
-            mbar_init(&acc_ready[i], L::split ? 2 : RT_MMA_WARPS);
+            // split (NT == 1): acc_ready / rz_issued / acc_n = commit of the r / z / n block, one arrival each
+            mbar_init(&acc_ready[i], L::split ? 1 : RT_MMA_WARPS);
             mbar_init(&h_ready[i], 32 * RT_GATE_WARPS / NT);
             mbar_init(&acc_n[i], 1);
-            mbar_init(&rz_issued[i], 2);
+            mbar_init(&rz_issued[i], 1);
         }
+        for (int i = 0; i < L::GI_BUFS; ++i) mbar_init(&gi_full[i], 1);
         fence_mbar_init();
     }
     if (warp == RT_GATE_WARPS) {
@@ -201,16 +256,85 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
     tc_fence_after_sync();
 
     if (warp >= RT_GATE_WARPS) {
-        // ================= MMA issuers (warp 16 + g issues gate block g) =================
+        // ================= MMA issuers =================
         // Every operand must sit in UNIFORM registers, otherwise the compiler wraps each tcgen05.mma in an
         // R2UR + elect waterfall loop (~50 issue cycles per MMA, measured).  So: TMEM addresses are literals,
         // shared-memory descriptors derive from the constant dynamic-smem base, and the issue is predicated by
         // elect.sync, not by `lane == 0`.
+        //
+        // NT == 2: warp 16 + g issues gate block g of both tiles and all three commit to acc_ready[tile].
+        // NT == 1: ONE issuer (warp 16) queues r, z, n in that order with a commit after each block, so the r
+        // accumulators complete after 24 of the 72 MMAs and sigmoid(r), then sigmoid(z), run under the rest of the MMA
+        // phase.  Warp 17 is the RELAY: it alone waits on the three commit barriers and releases the 16 gate warps
+        // through named barriers - an idle single waiter sees a commit ~100 cycles after the MMAs finish, while 16 warps
+        // blocked in mbarrier.try_wait were released another 100-250 cycles later, and even an already-completed
+        // try_wait cost 75-160 cycles on the critical path (cycle trace, profiles/r01e_*).  Warp 18 prefetches.
         const int g = warp - RT_GATE_WARPS;
         const uint32_t idesc = make_idesc_f16(128, RT_N);
         const uint64_t b_desc0 = make_smem_desc(smem_u32(smem + L::h_off), RT_KG, 128);
         const uint64_t x_desc0 = make_smem_desc(smem_u32(smem + L::x_off), RT_KG, 128);
         const uint64_t wx_desc0 = make_smem_desc(smem_u32(smem + L::wx_off), H * 16, 128);
+        // W_hh[gate] (K steps [ks0, ks1)) . h of `tile`, three fp16 products, into accumulator columns d
+        auto issue_h = [&](uint32_t d, int gate, int ks0, int ks1, int tile, bool fresh) {
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {
+                const int pa = (prod == 2) ? 1 : 0;   // W part: hi, hi, lo
+                const int pb = (prod == 1) ? 1 : 0;   // activation part: hi, lo, hi
+#pragma unroll
+                for (int ks = ks0; ks < ks1; ++ks) {
+                    const uint64_t bd = b_desc0 + (uint64_t)(((tile * 2 + pb) * RT_HPLANE + ks * 2 * RT_KG) >> 4);
+                    umma_f16_ts(d, (uint32_t)(((pa * 3 + gate) * 8 + ks) * 8), bd, idesc,
+                                (fresh && prod == 0 && ks == ks0) ? 0u : 1u);
+                }
+            }
+        };
+        // + W_ih[gate] . x_t (fused layer-0 input projection)
+        auto issue_x = [&](uint32_t d, int gate, int tile, uint32_t par, bool fresh) {
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {
+                const int pa = (prod == 2) ? 1 : 0;
+                const int pb = (prod == 1) ? 1 : 0;
+                const uint64_t xd = x_desc0 + (uint64_t)(((tile * 2 + (int)par) * RT_XBUF + pb * RT_XPLANE) >> 4);
+                const uint32_t acc = (fresh && prod == 0) ? 0u : 1u;
+                if (L::wx_tmem) {
+                    umma_f16_ts(d, L::wx_col0 + (uint32_t)((pa * 3 + gate) * 8), xd, idesc, acc);
+                } else {
+                    umma_f16(d, wx_desc0 + (uint64_t)(((pa * 3 + gate) * RT_WX_BLOCK) >> 4), xd, idesc, acc);
+                }
+            }
+        };
+        // L2 prefetch duty (one elected thread): feature rows X_PREFETCH_AHEAD.. steps ahead (fused layer 0) or the
+        // pre-activation rows GI_PREFETCH_STEPS ahead (layer 1).  The gate warps' own register prefetch runs 1-2 steps
+        // ahead, which covers an L2 hit but not a DRAM miss (measured: ~600 cycles per step exposed without this).
+        auto prefetch = [&](int64_t step, int tile) {
+            const int64_t wt = (int64_t)blockIdx.x * NT + tile;
+            if (FUSE_X) {
+                if ((step & (X_PREFETCH_EVERY - 1)) != 0) return;
+                const int64_t s0 = step + X_PREFETCH_AHEAD;                    // first step covered
+                const int64_t s1 = s0 + X_PREFETCH_EVERY <= T ? s0 + X_PREFETCH_EVERY : T;   // one past the last
+                if (s0 >= T) return;
+                const int64_t t_lo = dir ? (T - s1) : s0;                      // lowest time index of the span
+                const int64_t nbytes = (s1 - s0) * xin.F * 4;
+                for (int w = 0; w < WT; ++w) {
+                    if (wt * WT + w >= B) break;
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(xin.feats + ((wt * WT + w) * T + t_lo) * xin.F);
+                    const uintptr_t a0 = a & ~(uintptr_t)15;
+                    bulk_prefetch_l2(reinterpret_cast<const void *>(a0),
+                                     (uint32_t)(((a + nbytes - a0) + 15) & ~(uintptr_t)15));
+                }
+            } else {
+                if (step + GI_PREFETCH_STEPS >= T || wt * WT >= B) return;
+                const int64_t sp = step + GI_PREFETCH_STEPS;
+                const int64_t t = dir ? (T - 1 - sp) : sp;
+                // quad layout: the three gate blocks of (tile-step, direction) are one contiguous 24 KiB range
+                // (issued as 2 KiB pieces: a single 24 KiB prefetch measured as if it had not been issued at all)
+                const float *blk = gi + (wt * T + t) * GI_TS_FLOATS + (int64_t)dir * (GI_TS_FLOATS / 2);
+#pragma unroll
+                for (int i = 0; i < 12; ++i) bulk_prefetch_l2(blk + i * 512, 2048);
+            }
+        };
+        constexpr int HCOUNT = 32 * RT_GATE_WARPS / NT + 32 * RT_MMA_WARPS;
+#pragma unroll 1
         for (int64_t step = 0; step < T; ++step) {
             const uint32_t par = (uint32_t)(step & 1);
             unsigned long long *tr = nullptr;
@@ -219,80 +343,112 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 tr = trace + (step - RT_TRACE_STEP0) * RT_TRACE_SLOTS;
 #pragma unroll
             for (int tile = 0; tile < NT; ++tile) {
-                mbar_wait(&h_ready[tile], par);
-                if (L::split && g == 2) mbar_wait(&rz_issued[tile], par);   // let the r/z MMAs into the pipe first
+                if (RT_NB) {
+                    if (tile == 0) named_bar_sync<RT_BAR_H, HCOUNT>(); else named_bar_sync<RT_BAR_H + 1, HCOUNT>();
+                } else {
+                    mbar_wait(&h_ready[tile], par);
+                }
                 tc_fence_after_sync();
+                if (GI_SMEM && g == 2 && step > 0) {
+                    // this step's gi block landed long ago (requested two steps back): release the gate warps' BAR_R
+                    // before doing anything else (step 0: after the first blocks are requested, below)
+                    mbar_wait(&gi_full[step % L::GI_BUFS], (uint32_t)((step / L::GI_BUFS) & 1));
+                    named_bar_arrive<RT_BAR_R, NB_R_COUNT>();
+                    if (TRACE && tr && lane == 0) tr[35] = (unsigned long long)clock64();
+                }
                 if (elect_one()) {
-                    if (g == 0) REC_STAMP(0);
-                    if (g == 2) REC_STAMP(2);
-                    const uint32_t d = L::acc_col0 + (uint32_t)(tile * L::acc_per_tile + g * 16);
+                    const uint32_t d0 = L::acc_col0 + (uint32_t)(tile * L::acc_per_tile);
+                    if (L::split) {
+                        if (g == 0) {
+                            REC_STAMP(0);
+                            issue_h(d0, 0, 0, H / 16, tile, true);
+                            if (FUSE_X) issue_x(d0, 0, tile, par, false);
+                            umma_commit(&acc_ready[tile]);
+                            REC_STAMP(1);
+                            issue_h(d0 + 16, 1, 0, H / 16, tile, true);
+                            if (FUSE_X) issue_x(d0 + 16, 1, tile, par, false);
+                            umma_commit(&rz_issued[tile]);
+                            REC_STAMP(2);
+                            issue_h(d0 + 32, 2, 0, H / 16, tile, true);
+                            if (FUSE_X) issue_x(d0 + 48, 2, tile, par, true);
+                            umma_commit(&acc_n[tile]);
+                            REC_STAMP(3);
+                        } else if (g == 2) {
+                            if (BULK_OUT && step > 0) {
+                                // h_{step-1} (published through BAR_H) -> its rows of the GEMM operand tiles
+                                const int64_t orow = ((int64_t)blockIdx.x * T + (dir ? (T - step) : (step - 1))) * WT;
+                                uint8_t *dst = reinterpret_cast<uint8_t *>(h_out) + (orow >> 7) * (int64_t)XT_TILE_BYTES +
+                                               (int64_t)(dir * (H / 8)) * (XT_ROWS * 16) + (orow & (XT_ROWS - 1)) * 16;
 #pragma unroll
-                    for (int prod = 0; prod < 3; ++prod) {
-                        const int pa = (prod == 2) ? 1 : 0;   // W part: hi, hi, lo
-                        const int pb = (prod == 1) ? 1 : 0;   // activation part: hi, lo, hi
+                                for (int plane = 0; plane < 2; ++plane)
 #pragma unroll
-                        for (int ks = 0; ks < H / 16; ++ks) {
-                            const uint64_t bd = b_desc0 + (uint64_t)(((tile * 2 + pb) * RT_HPLANE + ks * 2 * RT_KG) >> 4);
-                            umma_f16_ts(d, (uint32_t)(((pa * 3 + g) * 8 + ks) * 8), bd, idesc, (prod | ks) ? 1u : 0u);
-                        }
-                    }
-                    if (FUSE_X) {
-                        // + W_ih[g] . x_t ; r and z accumulate onto the recurrent sum, n keeps its own columns
-                        const uint32_t dx = (g == 2) ? d + 16 : d;
-#pragma unroll
-                        for (int prod = 0; prod < 3; ++prod) {
-                            const int pa = (prod == 2) ? 1 : 0;
-                            const int pb = (prod == 1) ? 1 : 0;
-                            const uint64_t xd = x_desc0 + (uint64_t)(((tile * 2 + (int)par) * RT_XBUF + pb * RT_XPLANE) >> 4);
-                            const uint32_t acc = (g == 2 && prod == 0) ? 0u : 1u;
-                            if (L::wx_tmem) {
-                                umma_f16_ts(dx, L::wx_col0 + (uint32_t)((pa * 3 + g) * 8), xd, idesc, acc);
-                            } else {
-                                umma_f16(dx, wx_desc0 + (uint64_t)(((pa * 3 + g) * RT_WX_BLOCK) >> 4), xd, idesc, acc);
+                                    for (int kg = 0; kg < H / 8; ++kg)
+                                        bulk_s2g(dst + plane * XT_PLANE_BYTES + kg * (XT_ROWS * 16),
+                                                 smem + L::h_off + plane * RT_HPLANE + kg * RT_KG, WT * 16);
+                                bulk_commit_group();
                             }
+                            if (GI_SMEM) {
+                                // stage the gi block of step + 2 into the buffer step - 1 used (free: every gate warp
+                                // has passed BAR_H of this step, i.e. finished step - 1); steps 0 and 1 on the first pass
+                                const int64_t s0 = step == 0 ? 0 : step + 2, s1 = step + 2;
+                                for (int64_t sp = s0; sp <= s1 && sp < T; ++sp) {
+                                    const int64_t t = dir ? (T - 1 - sp) : sp;
+                                    const float *src = gi + ((int64_t)blockIdx.x * T + t) * GI_TS_FLOATS +
+                                                       (int64_t)dir * (GI_TS_FLOATS / 2);
+                                    const int b = (int)(sp % L::GI_BUFS);
+                                    mbar_arrive_expect_tx(&gi_full[b], L::GI_BLOCK);
+                                    bulk_g2s(smem + L::gi_off + b * L::GI_BLOCK, src, L::GI_BLOCK, &gi_full[b]);
+                                }
+                            }
+                            REC_STAMP(32);
+                            prefetch(step, tile);
+                            REC_STAMP(33);
+                            // the gate warps overwrite the tile after BAR_N: the copies must have read it by then
+                            if (BULK_OUT && step > 0) bulk_wait_read_all();
+                            REC_STAMP(34);
                         }
-                    }
-                    if (L::split && g == 2) {
-                        umma_commit(&acc_n[tile]);
                     } else {
+                        // one issuer per gate block; r and z accumulate the input projection onto the recurrent sum,
+                        // n keeps W_in.x in its own columns
+                        if (g == 0) {
+                            issue_h(d0, 0, 0, H / 16, tile, true);
+                            if (FUSE_X) issue_x(d0, 0, tile, par, false);
+                        } else if (g == 1) {
+                            issue_h(d0 + 16, 1, 0, H / 16, tile, true);
+                            if (FUSE_X) issue_x(d0 + 16, 1, tile, par, false);
+                        } else {
+                            issue_h(d0 + 32, 2, 0, H / 16, tile, true);
+                            if (FUSE_X) issue_x(d0 + 48, 2, tile, par, true);
+                        }
                         umma_commit(&acc_ready[tile]);
-                        if (L::split) mbar_arrive(&rz_issued[tile]);
-                    }
-                    if (g == 0) REC_STAMP(1);
-                    if (g == 2) REC_STAMP(3);
-                    if (FUSE_X && g == 2 && (step & (X_PREFETCH_EVERY - 1)) == 0) {
-                        // feature rows of this tile, X_PREFETCH_AHEAD.. steps from now, into L2: the gate warps load
-                        // them two steps ahead of use, which covers an L2 hit but not always a DRAM miss
-                        const int64_t wt = (int64_t)blockIdx.x * NT + tile;
-                        const int64_t s0 = step + X_PREFETCH_AHEAD;                    // first step covered
-                        const int64_t s1 = s0 + X_PREFETCH_EVERY <= T ? s0 + X_PREFETCH_EVERY : T;   // one past the last
-                        if (s0 < T) {
-                            const int64_t t_lo = dir ? (T - s1) : s0;                  // lowest time index of the span
-                            const int64_t nbytes = (s1 - s0) * xin.F * 4;
-                            for (int w = 0; w < WT; ++w) {
-                                if (wt * WT + w >= B) break;
-                                const uintptr_t a = reinterpret_cast<uintptr_t>(xin.feats + ((wt * WT + w) * T + t_lo) * xin.F);
-                                const uintptr_t a0 = a & ~(uintptr_t)15;
-                                bulk_prefetch_l2(reinterpret_cast<const void *>(a0),
-                                                 (uint32_t)(((a + nbytes - a0) + 15) & ~(uintptr_t)15));
-                            }
-                        }
-                    }
-                    if (!FUSE_X && g == 2 && step + GI_PREFETCH_STEPS < T) {
-                        // pull the pre-activation rows the gate warps will load GI_PREFETCH_STEPS steps from now into
-                        // L2 (16 rows x 1.5 KiB of this direction): their register prefetch runs one step ahead, which
-                        // covers an L2 hit but not a DRAM miss (measured: ~600 cycles per step exposed without this)
-                        const int64_t wt = (int64_t)blockIdx.x * NT + tile;
-                        if (wt * WT < B) {
-                            const int64_t sp = step + GI_PREFETCH_STEPS;
-                            const int64_t t = dir ? (T - 1 - sp) : sp;
-                            const float *row = gi + ((wt * T + t) * WT) * GI_COLS + (int64_t)dir * G3;
-#pragma unroll
-                            for (int w = 0; w < WT; ++w) bulk_prefetch_l2(row + (int64_t)w * GI_COLS, G3 * 4);
-                        }
+                        if (g == 2) prefetch(step, tile);
                     }
                 }
                 __syncwarp();
+                if (BULK_OUT && g == 2) named_bar_arrive<RT_BAR_N, NB_N_COUNT>();
+                if (GI_SMEM && g == 2 && step == 0) {
+                    mbar_wait(&gi_full[0], 0u);
+                    named_bar_arrive<RT_BAR_R, NB_R_COUNT>();
+                }
+
+                if (L::split && g == 1) {
+                    constexpr int RC = 32 * RT_GATE_WARPS + 32;
+                    mbar_wait(&acc_ready[tile], par);
+                    tc_fence_after_sync();
+                    tc_fence_before_sync();
+                    named_bar_arrive<RT_BAR_R, NB_R_COUNT>();
+                    if (TRACE && tr && lane == 0) tr[13] = (unsigned long long)clock64();
+                    mbar_wait(&rz_issued[tile], par);
+                    tc_fence_after_sync();
+                    tc_fence_before_sync();
+                    named_bar_arrive<RT_BAR_Z, RC>();
+                    if (TRACE && tr && lane == 0) tr[14] = (unsigned long long)clock64();
+                    mbar_wait(&acc_n[tile], par);
+                    tc_fence_after_sync();
+                    tc_fence_before_sync();
+                    named_bar_arrive<RT_BAR_N, NB_N_COUNT>();
+                    if (TRACE && tr && lane == 0) tr[15] = (unsigned long long)clock64();
+                }
             }
         }
     } else {
@@ -318,8 +474,23 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         const int64_t t_first = dir ? (T - 1) : 0;
 
         // unfused path: pre-activations from the gi buffer, prefetched one step ahead into registers
-        const float *gptr = FUSE_X ? nullptr : gi + (row0 + t_first * WT) * GI_COLS + (int64_t)dir * G3 + j;
+        // (quad layout, common.cuh: this thread's 3 gates x NC windows are 3 x NC/4 16-byte loads)
+        const float4 *gptr = FUSE_X ? nullptr
+                                    : reinterpret_cast<const float4 *>(gi) + (wtile * T + t_first) * (GI_TS_FLOATS / 4) +
+                                          (int64_t)((dir * 3) * 4 + (col0 >> 2)) * H + j;
+        const int64_t gstep = dir ? -(int64_t)(GI_TS_FLOATS / 4) : (int64_t)(GI_TS_FLOATS / 4);
         F2 g2[3][NP];
+        int gbuf = 0;                                          // GI_SMEM: staging buffer of the current step
+        auto load_gi = [&]() {
+#pragma unroll
+            for (int gt = 0; gt < 3; ++gt)
+#pragma unroll
+                for (int c = 0; c < NC / 4; ++c) {
+                    const float4 v = ld_stream4(reinterpret_cast<const float *>(gptr + (gt * 4 + c) * H));
+                    g2[gt][2 * c] = f2_make(v.x, v.y);
+                    g2[gt][2 * c + 1] = f2_make(v.z, v.w);
+                }
+        };
         // fused path: folded biases, and this thread's share of the x_t staging (16 x F values per tile-step)
         const F2 bhn2 = f2_make(b_hn[dir * H + j], b_hn[dir * H + j]);
         F2 br2 = f2_make(0.f, 0.f), bz2 = br2, bn2 = br2;
@@ -346,7 +517,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         __half *o16 = reinterpret_cast<__half *>(h_out) + (int64_t)(kcol >> 3) * (XT_ROWS * 8) + (kcol & 7);
 
         constexpr float EXP_CLAMP = 60.0f;
-        const F2 one2 = f2_make(1.0f, 1.0f), neg2 = f2_make(-2.0f, -2.0f), negone2 = f2_make(-1.0f, -1.0f);
+        const F2 one2 = f2_make(1.0f, 1.0f), negone2 = f2_make(-1.0f, -1.0f);
         const F2 knl2 = f2_make(-1.4426950408889634f, -1.4426950408889634f);     // -log2(e)
         const F2 k2l2 = f2_make(2.8853900817779268f, 2.8853900817779268f);       // 2 log2(e)
         F2 hprev2[NP];
@@ -356,10 +527,8 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
 #pragma unroll
             for (int q = 0; q < NP; ++q)
 #pragma unroll
-                for (int gt = 0; gt < 3; ++gt)
-                    g2[gt][q] = tile_ok ? f2_make(ldg_stream(gptr + (2 * q) * GI_COLS + gt * H),
-                                                  ldg_stream(gptr + (2 * q + 1) * GI_COLS + gt * H))
-                                        : f2_make(0.f, 0.f);
+                for (int gt = 0; gt < 3; ++gt) g2[gt][q] = f2_make(0.f, 0.f);
+            if (tile_ok && !GI_SMEM) load_gi();
         } else if (xown) {
             // x of step 0 -> buffer 0; x of step 1 -> register
             const float x0 = xok ? xsrc[t_first * (int64_t)xin.F] : 0.f;
@@ -369,79 +538,112 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             *reinterpret_cast<__half *>(xdst + RT_XPLANE) = lo;
             if (T > 1 && xok) xreg = xsrc[(dir ? (T - 2) : 1) * (int64_t)xin.F];
         }
+        // running pointer to the feature value of step + 2 (loaded while step is in its epilogue)
+        const float *xnext = (FUSE_X && xown) ? xsrc + (dir ? (T - 3) : 2) * (int64_t)xin.F : nullptr;
+        const int64_t xadv = dir ? -(int64_t)xin.F : (int64_t)xin.F;
         // h_{-1} = 0 (and x_0) are in smem: publish.  (Per-thread arrivals and all-lane polling are deliberate: electing
         // one lane per warp for the barrier traffic measured 35 % SLOWER - the extra __syncwarp sits on the critical
         // path while the mbarrier unit absorbs 512 arrivals without trouble.)
+        constexpr int HCOUNT = 32 * RT_GATE_WARPS / NT + 32 * RT_MMA_WARPS;
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        mbar_arrive(&h_ready[tile]);
+        if (RT_NB) {
+            if (tile == 0) named_bar_arrive<RT_BAR_H, HCOUNT>(); else named_bar_arrive<RT_BAR_H + 1, HCOUNT>();
+        } else {
+            mbar_arrive(&h_ready[tile]);
+        }
 
+#pragma unroll 1
         for (int64_t step = 0; step < T; ++step) {
             const bool more = step + 1 < T;
             unsigned long long *tr = nullptr;
             if (TRACE && trace && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && step >= RT_TRACE_STEP0 &&
                 step < RT_TRACE_STEP0 + RT_TRACE_STEPS)
                 tr = trace + (step - RT_TRACE_STEP0) * RT_TRACE_SLOTS;
-            mbar_wait(&acc_ready[tile], (uint32_t)(step & 1));
-            REC_STAMP(4);
-            tc_fence_after_sync();
             uint32_t ar[NC], az[NC], an[NC], ax[NC];
-            if constexpr (NC == 8) {
-                tmem_ld_x8(t_lane + 0 * 16, ar);
-                tmem_ld_x8(t_lane + 1 * 16, az);
-                if (!L::split) {
-                    tmem_ld_x8(t_lane + 2 * 16, an);
-                    if (FUSE_X) tmem_ld_x8(t_lane + 3 * 16, ax);
-                }
-            } else {
-                tmem_ld_x4(t_lane + 0 * 16, ar);
-                tmem_ld_x4(t_lane + 1 * 16, az);
-                if (!L::split) {
-                    tmem_ld_x4(t_lane + 2 * 16, an);
-                    if (FUSE_X) tmem_ld_x4(t_lane + 3 * 16, ax);
-                }
-            }
-            tmem_ld_wait();
-            REC_STAMP(5);
-            if (!FUSE_X) gptr += tstep * GI_COLS;          // rows of the next time step
             __half hh[NC], hl[NC];
             __half *tb = nullptr;
-            if (OUT_TILES) tb = o16 + (orow >> 7) * (int64_t)(XT_TILE_BYTES / 2) + (orow & (XT_ROWS - 1)) * 8;
-            F2 r2[NP], z2[NP];
+            F2 r2[NP], eb2[NP], nzb2[NP];    // r ; e^{-pre_z} ; -(1 + e^{-pre_z})
+            if constexpr (L::split) {
+                // three hand-offs per step, each a named barrier released by the relay warp: r, then z, then n
+                constexpr int RC = 32 * RT_GATE_WARPS + 32;
+                named_bar_sync<RT_BAR_R, NB_R_COUNT>();
+                tc_fence_after_sync();
+                tmem_ld_x4(t_lane + 0 * 16, ar);
+                if (GI_SMEM) {
+                    const float4 *gs = reinterpret_cast<const float4 *>(smem + L::gi_off + gbuf * L::GI_BLOCK) + (col0 >> 2) * H + j;
 #pragma unroll
-            for (int q = 0; q < NP; ++q) {
-                const F2 accr = f2_make(__uint_as_float(ar[2 * q]), __uint_as_float(ar[2 * q + 1]));
-                const F2 accz = f2_make(__uint_as_float(az[2 * q]), __uint_as_float(az[2 * q + 1]));
-                const F2 pre_r = f2_add(FUSE_X ? br2 : g2[0][q], accr);
-                const F2 pre_z = f2_add(FUSE_X ? bz2 : g2[1][q], accz);
-                // r = sigmoid(pre_r), z = sigmoid(pre_z) with one reciprocal per element: 1/((1+e^-a)(1+e^-b)).
-                // (Sharing one reciprocal between the two elements of a packed pair was tried: it saves 4 of 20 MUFU ops
-                // per thread-step but measured no gain, and it makes a window's bits depend on its batch neighbour.)
-                float a0, a1, b0, b1;
-                f2_get(f2_mul(pre_r, knl2), a0, a1);
-                f2_get(f2_mul(pre_z, knl2), b0, b1);
-                const F2 ea = f2_add(f2_make(ex2_approx(fminf(a0, EXP_CLAMP)), ex2_approx(fminf(a1, EXP_CLAMP))), one2);
-                const F2 eb = f2_add(f2_make(ex2_approx(fminf(b0, EXP_CLAMP)), ex2_approx(fminf(b1, EXP_CLAMP))), one2);
-                float p0, p1;
-                f2_get(f2_mul(ea, eb), p0, p1);
-                const F2 inv = f2_make(rcp_approx(p0), rcp_approx(p1));
-                r2[q] = f2_mul(eb, inv);
-                z2[q] = f2_mul(ea, inv);
-            }
-            REC_STAMP(6);
-            if (L::split) {
-                // the n-gate accumulators arrive while the sigmoids above were running
-                mbar_wait(&acc_n[tile], (uint32_t)(step & 1));
+                    for (int gt = 0; gt < 3; ++gt) {
+                        const float4 v = gs[gt * 4 * H];
+                        g2[gt][0] = f2_make(v.x, v.y);
+                        g2[gt][1] = f2_make(v.z, v.w);
+                    }
+                    gbuf = (gbuf == L::GI_BUFS - 1) ? 0 : gbuf + 1;
+                }
+                tmem_ld_wait();
+                REC_STAMP(4);
+                if (!FUSE_X) gptr += gstep;                    // block of the next time step
+                if (OUT_TILES) tb = o16 + (orow >> 7) * (int64_t)(XT_TILE_BYTES / 2) + (orow & (XT_ROWS - 1)) * 8;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const F2 accr = f2_make(__uint_as_float(ar[2 * q]), __uint_as_float(ar[2 * q + 1]));
+                    float a0, a1, e0, e1;
+                    f2_get(f2_mul(f2_add(FUSE_X ? br2 : g2[0][q], accr), knl2), a0, a1);
+                    f2_get(f2_add(f2_make(ex2_approx(fminf(a0, EXP_CLAMP)), ex2_approx(fminf(a1, EXP_CLAMP))), one2), e0, e1);
+                    r2[q] = f2_make(rcp_approx(e0), rcp_approx(e1));
+                }
+                REC_STAMP(5);
+                named_bar_sync<RT_BAR_Z, RC>();
+                tc_fence_after_sync();
+                tmem_ld_x4(t_lane + 1 * 16, az);
+                tmem_ld_wait();
+                REC_STAMP(6);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    // z = 1 / (1 + eb) is never formed: its reciprocal is shared with the tanh below
+                    const F2 accz = f2_make(__uint_as_float(az[2 * q]), __uint_as_float(az[2 * q + 1]));
+                    float b0, b1;
+                    f2_get(f2_mul(f2_add(FUSE_X ? bz2 : g2[1][q], accz), knl2), b0, b1);
+                    eb2[q] = f2_make(ex2_approx(fminf(b0, EXP_CLAMP)), ex2_approx(fminf(b1, EXP_CLAMP)));
+                    nzb2[q] = f2_fma(eb2[q], negone2, negone2);          // -(1 + eb)
+                }
                 REC_STAMP(7);
+                named_bar_sync<RT_BAR_N, NB_N_COUNT>();
+                tc_fence_after_sync();
+                tmem_ld_x4(t_lane + 2 * 16, an);
+                if (FUSE_X) tmem_ld_x4(t_lane + 3 * 16, ax);
+                tmem_ld_wait();
+            } else {
+                GATE_WAIT(&acc_ready[tile], (uint32_t)(step & 1));
                 tc_fence_after_sync();
                 if constexpr (NC == 8) {
+                    tmem_ld_x8(t_lane + 0 * 16, ar);
+                    tmem_ld_x8(t_lane + 1 * 16, az);
                     tmem_ld_x8(t_lane + 2 * 16, an);
                     if (FUSE_X) tmem_ld_x8(t_lane + 3 * 16, ax);
                 } else {
+                    tmem_ld_x4(t_lane + 0 * 16, ar);
+                    tmem_ld_x4(t_lane + 1 * 16, az);
                     tmem_ld_x4(t_lane + 2 * 16, an);
                     if (FUSE_X) tmem_ld_x4(t_lane + 3 * 16, ax);
                 }
                 tmem_ld_wait();
+                if (!FUSE_X) gptr += gstep;                    // block of the next time step
+                if (OUT_TILES) tb = o16 + (orow >> 7) * (int64_t)(XT_TILE_BYTES / 2) + (orow & (XT_ROWS - 1)) * 8;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const F2 accr = f2_make(__uint_as_float(ar[2 * q]), __uint_as_float(ar[2 * q + 1]));
+                    const F2 accz = f2_make(__uint_as_float(az[2 * q]), __uint_as_float(az[2 * q + 1]));
+                    const F2 pre_r = f2_add(FUSE_X ? br2 : g2[0][q], accr);
+                    const F2 pre_z = f2_add(FUSE_X ? bz2 : g2[1][q], accz);
+                    float a0, a1, b0, b1;
+                    f2_get(f2_mul(pre_r, knl2), a0, a1);
+                    f2_get(f2_mul(pre_z, knl2), b0, b1);
+                    const F2 ea = f2_make(ex2_approx(fminf(a0, EXP_CLAMP)), ex2_approx(fminf(a1, EXP_CLAMP)));
+                    eb2[q] = f2_make(ex2_approx(fminf(b0, EXP_CLAMP)), ex2_approx(fminf(b1, EXP_CLAMP)));
+                    r2[q] = rcp_neg_fma2(f2_fma(ea, negone2, negone2), one2);    // r = 1 / (1 + ea)
+                    nzb2[q] = f2_fma(eb2[q], negone2, negone2);                   // -(1 + eb): see the tanh below
+                }
             }
             REC_STAMP(8);
 #pragma unroll
@@ -449,15 +651,17 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 const F2 accn = f2_make(__uint_as_float(an[2 * q]), __uint_as_float(an[2 * q + 1]));
                 const F2 gin = FUSE_X ? f2_add(bn2, f2_make(__uint_as_float(ax[2 * q]), __uint_as_float(ax[2 * q + 1])))
                                       : g2[2][q];
-                const F2 r = r2[q], z = z2[q];
-                // n = tanh(gi_n + r * (gh_n + b_hn)) = 1 - 2 / (1 + e^{2x})
+                // n = tanh(x), x = gi_n + r * (gh_n + b_hn); with en = e^{2x}: n = (en - 1) / (en + 1); z = 1 / (1 + eb).
+                // h = (1 - z) * n + z * h_prev = (eb * (en - 1) + h_prev * (en + 1)) / ((1 + eb) * (en + 1)):
+                // ONE reciprocal for the z sigmoid and the tanh together, done on the FMA pipe (rcp_neg_fma2); the
+                // exponentials are clamped at 2^60, so the denominator stays below 2^121.  Same ~2.5e-7 absolute error
+                // as ATen's (h_prev - n) * z + n evaluated with approximate exp/rcp (checked against float64).
                 float t0, t1;
-                f2_get(f2_mul(f2_fma(r, f2_add(accn, bhn2), gin), k2l2), t0, t1);
-                float e0, e1;
-                f2_get(f2_add(f2_make(ex2_approx(fminf(t0, EXP_CLAMP)), ex2_approx(fminf(t1, EXP_CLAMP))), one2), e0, e1);
-                const F2 nn = f2_fma(neg2, f2_make(rcp_approx(e0), rcp_approx(e1)), one2);
-                // h = (h_prev - n) * z + n   (ATen's gru_cell form)
-                const F2 h2 = f2_fma(f2_fma(nn, negone2, hprev2[q]), z, nn);
+                f2_get(f2_mul(f2_fma(r2[q], f2_add(accn, bhn2), gin), k2l2), t0, t1);
+                const F2 en = f2_make(ex2_approx(fminf(t0, EXP_CLAMP)), ex2_approx(fminf(t1, EXP_CLAMP)));
+                const F2 enp = f2_add(en, one2);
+                const F2 inv = rcp_neg_fma2(f2_mul(enp, nzb2[q]), one2);
+                const F2 h2 = f2_mul(f2_fma(hprev2[q], enp, f2_mul(f2_add(en, negone2), eb2[q])), inv);
                 hprev2[q] = h2;
                 float h0v, h1v;
                 f2_get(h2, h0v, h1v);
@@ -484,41 +688,43 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             REC_STAMP(9);
             fence_proxy_async_smem();     // h / x tile writes -> visible to the MMA's async-proxy reads
             tc_fence_before_sync();       // order our tcgen05.ld before the next MMA overwrites the accumulators
-            REC_STAMP(10);
-            mbar_arrive(&h_ready[tile]);
+            if (RT_NB) {
+                if (more) {   // nobody waits for the tile written by the last step: leave no arrivals pending at exit
+                    if (tile == 0) named_bar_arrive<RT_BAR_H, HCOUNT>(); else named_bar_arrive<RT_BAR_H + 1, HCOUNT>();
+                }
+            } else {
+                mbar_arrive(&h_ready[tile]);
+            }
             REC_STAMP(11);
             if (FUSE_X && xok && step + 2 < T) {
                 // feature value staged during the NEXT step (for the step after it); issued before this step's
                 // output stores so that it is not queued behind them
-                const int64_t t = dir ? (T - 1 - step) : step;
-                xreg = xsrc[(dir ? (t - 2) : (t + 2)) * (int64_t)xin.F];
+                xreg = *xnext;
+                xnext += xadv;
             }
             if (TRACE && trace && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && step >= RT_TRACE_STEP0 &&
                 step < RT_TRACE_STEP0 + RT_TRACE_STEPS)     // slots 16..31: when each gate warp arrived
                 trace[(step - RT_TRACE_STEP0) * RT_TRACE_SLOTS + 16 + warp] = (unsigned long long)clock64();
             if (tile_ok) {
+                if (!BULK_OUT) {
 #pragma unroll
-                for (int q = 0; q < NP; ++q) {
-                    if (OUT_TILES) {
-                        tb[(2 * q) * 8] = hh[2 * q];
-                        tb[XT_PLANE_BYTES / 2 + (2 * q) * 8] = hl[2 * q];
-                        tb[(2 * q + 1) * 8] = hh[2 * q + 1];
-                        tb[XT_PLANE_BYTES / 2 + (2 * q + 1) * 8] = hl[2 * q + 1];
-                    } else {
-                        float h0v, h1v;
-                        f2_get(hprev2[q], h0v, h1v);
-                        o32[(2 * q) * H2] = h0v;
-                        o32[(2 * q + 1) * H2] = h1v;
-                    }
-                    // software pipeline: this pair's pre-activations of the NEXT step; the loads complete under
-                    // the next step's MMAs
-                    if (!FUSE_X && more) {
-#pragma unroll
-                        for (int gt = 0; gt < 3; ++gt)
-                            g2[gt][q] = f2_make(ldg_stream(gptr + (2 * q) * GI_COLS + gt * H),
-                                                ldg_stream(gptr + (2 * q + 1) * GI_COLS + gt * H));
+                    for (int q = 0; q < NP; ++q) {
+                        if (OUT_TILES) {
+                            tb[(2 * q) * 8] = hh[2 * q];
+                            tb[XT_PLANE_BYTES / 2 + (2 * q) * 8] = hl[2 * q];
+                            tb[(2 * q + 1) * 8] = hh[2 * q + 1];
+                            tb[XT_PLANE_BYTES / 2 + (2 * q + 1) * 8] = hl[2 * q + 1];
+                        } else {
+                            float h0v, h1v;
+                            f2_get(hprev2[q], h0v, h1v);
+                            o32[(2 * q) * H2] = h0v;
+                            o32[(2 * q + 1) * H2] = h1v;
+                        }
                     }
                 }
+                REC_STAMP(10);   // (trace: reuses the slot of the proxy fence stamp) output stores queued
+                // software pipeline: the pre-activations of the NEXT step; the loads complete under its MMAs
+                if (!FUSE_X && !GI_SMEM && more) load_gi();
             }
             o32 += tstep * H2;
             orow += tstep;
@@ -527,6 +733,21 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
     }
     tc_fence_before_sync();
     __syncthreads();
+    if (BULK_OUT && warp == RT_GATE_WARPS + 2) {
+        // the tile written by the last step (its writers fenced it for the async proxy before the barrier above)
+        if (elect_one()) {
+            const int64_t orow = ((int64_t)blockIdx.x * T + (dir ? 0 : (T - 1))) * WT;
+            uint8_t *dst = reinterpret_cast<uint8_t *>(h_out) + (orow >> 7) * (int64_t)XT_TILE_BYTES +
+                           (int64_t)(dir * (H / 8)) * (XT_ROWS * 16) + (orow & (XT_ROWS - 1)) * 16;
+            for (int plane = 0; plane < 2; ++plane)
+                for (int kg = 0; kg < H / 8; ++kg)
+                    bulk_s2g(dst + plane * XT_PLANE_BYTES + kg * (XT_ROWS * 16),
+                             smem + L::h_off + plane * RT_HPLANE + kg * RT_KG, WT * 16);
+            bulk_commit_group();
+            bulk_wait_all();
+        }
+        __syncwarp();
+    }
     if (warp == RT_GATE_WARPS) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 512);
@@ -736,16 +957,23 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
             mbar_wait(&acc_full[as], (tcount >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + GT_W_COLS + as * XT_ROWS;
-            float *out = gi + (tile * XT_ROWS) * (int64_t)GI_COLS + blk * H + j;
-            const int64_t prem = P - tile * XT_ROWS;
+            // quad layout (common.cuh): column c of this tile = tile-step tile*8 + c/16, window c%16; the four windows
+            // of a quad are one 16-byte store, contiguous over the warp's 32 rows j
+            float4 *out = reinterpret_cast<float4 *>(gi) + (tile * (XT_ROWS / WT)) * (int64_t)(GI_TS_FLOATS / 4) +
+                          (int64_t)(blk * 4) * H + j;
+            const int64_t prem = P - tile * XT_ROWS;   // rows of this tile that exist (a multiple of 16)
 #pragma unroll 1
             for (int c32 = 0; c32 < XT_ROWS; c32 += 32) {
                 uint32_t v[32];
                 tmem_ld_x32(t_lane + c32, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (c32 + i < prem) out[(int64_t)(c32 + i) * GI_COLS] = __uint_as_float(v[i]) + bj;
+                for (int i = 0; i < 32; i += 4) {
+                    const int c = c32 + i;
+                    if (c < prem)
+                        out[(int64_t)(c >> 4) * (GI_TS_FLOATS / 4) + ((c & 15) >> 2) * H] =
+                            make_float4(__uint_as_float(v[i]) + bj, __uint_as_float(v[i + 1]) + bj,
+                                        __uint_as_float(v[i + 2]) + bj, __uint_as_float(v[i + 3]) + bj);
                 }
             }
             tc_fence_before_sync();

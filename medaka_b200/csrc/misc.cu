@@ -278,11 +278,17 @@ __global__ void __launch_bounds__(256) inproj0_kernel(const float *__restrict__ 
             a2 = fmaf(x, wr[2][f], a2);
         }
         const int64_t pp = p0 + p;
-        const int64_t orow = tiled ? tiled_row(pp / T, pp % T, T) : pp;
-        float *row = gi + orow * GI_COLS;
-        row[tid] = a0;
-        row[tid + 256] = a1;
-        row[tid + 512] = a2;
+        if (tiled) {   // tensor-core path: quad layout (common.cuh)
+            const int64_t orow = tiled_row(pp / T, pp % T, T);
+            gi[gi_quad_index(orow, tid)] = a0;
+            gi[gi_quad_index(orow, tid + 256)] = a1;
+            gi[gi_quad_index(orow, tid + 512)] = a2;
+        } else {
+            float *row = gi + pp * GI_COLS;
+            row[tid] = a0;
+            row[tid + 256] = a1;
+            row[tid + 512] = a2;
+        }
     }
 }
 
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(256) inproj0_generic_kernel(const float *__res
     for (int c = threadIdx.x; c < GI_COLS; c += 256) {
         float a = bias[c];
         for (int f = 0; f < F; ++f) a = fmaf(feats[p * F + f], w[c * F + f], a);
-        gi[orow * GI_COLS + c] = a;
+        gi[tiled ? gi_quad_index(orow, c) : orow * GI_COLS + c] = a;
     }
 }
 

@@ -51,6 +51,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// Named hardware barriers (ids 1..15; 0 is __syncthreads).  `count` = number of THREADS that take part (multiple of 32);
+// executed by whole warps.  bar.arrive + bar.sync is the PTX producer/consumer pattern: the arriving threads' earlier
+// shared-memory writes are visible to the threads that complete the barrier with bar.sync.  A warp-level arrival is one
+// instruction on the barrier unit, where an mbarrier arrival / try_wait is one SYNCS lane-op per thread.
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_bar_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_bar_arrive() {
+    asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+
 // one lane of the (converged) warp; the compiler keeps operands of code under this predicate in uniform registers
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -60,6 +73,14 @@ __device__ __forceinline__ bool elect_one() {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(pred));
     return pred != 0;
+}
+
+// Whole-warp wait with ONE polling lane: mbarrier.try_wait is one lane-op per thread on the barrier unit, so 16 warps of
+// 32 pollers are released one after the other when the phase flips; one lane per warp + __syncwarp keeps the unit's
+// queue 32x shorter.  (The other lanes get their acquire through the __syncwarp.)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+    if (elect_one()) mbar_wait(bar, parity);
+    __syncwarp();
 }
 
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads, bulk copies)
@@ -81,6 +102,19 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
         "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+
+// shared -> global (bulk-group completion).  16-B aligned, size % 16 == 0.  The source must have been made visible to
+// the async proxy (fence.proxy.async by the writers + a barrier) before the issuing thread gets here.
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have completed entirely
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tcgen05: TMEM management
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_result, uint32_t ncols) {  // whole warp

@@ -125,10 +125,11 @@ def check_determinism(arg):
     return res
 
 
-TRACE_SLOTS = ["issuer_r: h_ready seen", "issuer_r: MMAs queued + commit", "issuer_n: rz_issued seen",
-               "issuer_n: MMAs queued + commit", "gate: acc_ready (r,z) seen", "gate: r,z tcgen05.ld done",
-               "gate: sigmoids done", "gate: acc_n seen", "gate: n tcgen05.ld done", "gate: h tile written",
-               "gate: proxy fence done", "gate: arrived on h_ready", "gate: end of step (global stores queued)"]
+TRACE_SLOTS = ["issuer: h_ready seen", "issuer: r MMAs queued + commit", "issuer: z MMAs queued + commit",
+               "issuer: n MMAs queued + commit", "gate: r tcgen05.ld done", "gate: sigmoid(r) done",
+               "gate: z tcgen05.ld done", "gate: sigmoid(z) done", "gate: n tcgen05.ld done", "gate: h tile written",
+               "gate: proxy fence done", "gate: arrived on h_ready", "gate: end of step (global stores queued)",
+               "relay: r commit seen, arrived", "relay: z commit seen, arrived", "relay: n commit seen, arrived"]
 
 
 def check_rec_trace(arg):
@@ -145,19 +146,20 @@ def check_rec_trace(arg):
     lm.check(lib.mdk_debug_rec_trace(0, 1, ffi.NULL))
     m.forward_arrays(feats)
     traced = m.last_timings()
-    buf = np.zeros((2, 16, 32), dtype=np.uint64)
+    buf = np.zeros((2, 16, 40), dtype=np.uint64)
     lm.check(lib.mdk_debug_rec_trace(0, 0, ffi.cast("uint64_t *", ffi.from_buffer(buf))))
     res = {"untraced_ms": base, "traced_ms": traced}
     for layer in (0, 1):
         t = buf[layer].astype(np.int64)
         # every stamp relative to the moment the r issuer saw h_ready of the same step
-        rel = t[:, :13] - t[:, :1]
+        rel = t[:, :16] - t[:, :1]
         period = np.diff(t[:, 0])
         res["layer%d" % layer] = {
             "step_cycles_median": float(np.median(period)),
-            "median_offset_from_h_ready_seen": {TRACE_SLOTS[k]: float(np.median(rel[:, k])) for k in range(13)},
+            "median_offset_from_h_ready_seen": {TRACE_SLOTS[k]: float(np.median(rel[:, k])) for k in range(16)},
             "raw_first_step": [int(x) for x in rel[1]],
             "gate_warp_arrivals_median": [float(x) for x in np.median(t[:, 16:32] - t[:, :1], axis=0)],
+            "aux_warp (staging issued, prefetch issued, tile copy read, gi landed + arrived)": [float(x) for x in np.median(t[:, 32:36] - t[:, :1], axis=0)],
         }
     return res
 
