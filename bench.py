@@ -355,9 +355,17 @@ def main():
     dom = max(kernels, key=lambda k: kernels[k][2])
     k_ms, k_flop, k_share_ms = kernels[dom]
     achieved = k_flop / (k_ms * 1e-3) / 1e12
+    # DRAM traffic per launch of that kernel: from the committed ncu --set full capture of this same workload
+    # (profiles/ncu_traffic.json, written by tools/ncu_summary.py); null for any other shape
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if (B, T) == (WINDOWS, COLS) and args.precision == "tc" and os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        traffic = tj.get("rec_tc_kernel" if dom.startswith("rec_tc") else "gemm_tc_kernel")
     roofline = {
         "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops_sustained"],
-        "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
         "peak_source": "MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)"
         if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)",
         "note": "algorithmic FLOPs; operands are fp16 hi/lo pairs so the kernel issues 3 MMAs per product "

@@ -66,6 +66,8 @@ static int prepare_weights(mdk_engine *e) {
         if (!lw.w_in_packed && (rc = dev_alloc(&lw.w_in_packed, (size_t)GI_COLS * in))) return rc;
         if (!lw.bias_gi && (rc = dev_alloc(&lw.bias_gi, (size_t)GI_COLS))) return rc;
         if (!lw.b_hn && (rc = dev_alloc(&lw.b_hn, (size_t)NDIR * H))) return rc;
+        if (!lw.bias_gi_tc && (rc = dev_alloc(&lw.bias_gi_tc, (size_t)GI_COLS))) return rc;
+        if (!lw.b_hn_tc && (rc = dev_alloc(&lw.b_hn_tc, (size_t)NDIR * H))) return rc;
         if (!lw.w_hh_t && (rc = dev_alloc(&lw.w_hh_t, (size_t)NDIR * H * G3))) return rc;
         if (!lw.w_hh_tm && (rc = dev_alloc(&lw.w_hh_tm, (size_t)NDIR * 2 * G3 * H))) return rc;
         if (l == 0 && in <= 16 && !lw.w_x_tm && (rc = dev_alloc(&lw.w_x_tm, (size_t)NDIR * 2 * G3 * 16))) return rc;
@@ -136,19 +138,19 @@ static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t
     }
     MDK_CUDA(cudaEventRecord(e->ev[2], s));
     if (tc) {
-        const RecXArgs fx{feats_dev, e->layer[0].w_x_tm, e->layer[0].bias_gi, e->desc.num_features};
-        MDK_CUDA(launch_rec_tc(e->gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn, e->h0, 1, B, T,
+        const RecXArgs fx{feats_dev, e->layer[0].w_x_tm, e->layer[0].bias_gi_tc, e->desc.num_features};
+        MDK_CUDA(launch_rec_tc(e->gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn_tc, e->h0, 1, B, T,
                                e->sm_count, s));
     } else {
         MDK_CUDA(launch_rec_fp32(e->gi, e->layer[0].w_hh_t, e->layer[0].b_hn, (float *)e->h0, B, T, s));
     }
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[3], s));
-    if (tc) MDK_CUDA(launch_gemm_tc(e->h0, e->layer[1].w_in_tc, e->layer[1].bias_gi, e->gi, tiled_rows(B, T), e->sm_count, s));
+    if (tc) MDK_CUDA(launch_gemm_tc(e->h0, e->layer[1].w_in_tc, e->layer[1].bias_gi_tc, e->gi, tiled_rows(B, T), e->sm_count, s));
     else MDK_CUDA(launch_gemm_fp32((const float *)e->h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, e->gi, P, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[4], s));
-    if (tc) MDK_CUDA(launch_rec_tc(e->gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn, e->h1, 0, B, T, e->sm_count, s));
+    if (tc) MDK_CUDA(launch_rec_tc(e->gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, e->h1, 0, B, T, e->sm_count, s));
     else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[1].w_hh_t, e->layer[1].b_hn, e->h1, B, T, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[5], s));
@@ -291,6 +293,7 @@ int mdk_engine_destroy(mdk_engine *e) {
         LayerWeights &lw = e->layer[l];
         for (int d = 0; d < NDIR; ++d) { dev_free(lw.w_ih[d]); dev_free(lw.w_hh[d]); dev_free(lw.b_ih[d]); dev_free(lw.b_hh[d]); }
         dev_free(lw.w_in_packed); dev_free(lw.bias_gi); dev_free(lw.b_hn); dev_free(lw.w_hh_t);
+        dev_free(lw.bias_gi_tc); dev_free(lw.b_hn_tc);
         dev_free(lw.w_hh_tm); dev_free(lw.w_x_tm); dev_free(lw.w_in_tc);
     }
     dev_free(e->lin_w); dev_free(e->lin_b);

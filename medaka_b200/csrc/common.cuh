@@ -64,6 +64,11 @@ __host__ __device__ inline int64_t gi_quad_index(int64_t tiled_row, int col) {
     return ((((ts * 6 + blk) * 4 + (w >> 2)) * H + j) << 2) + (w & 3);
 }
 
+// sigmoid(a) = 1 / (1 + 2^(-log2e * a)),  tanh(x) = (2^(2 log2e * x) - 1) / (2^(2 log2e * x) + 1)
+constexpr float GATE_SCALE_RZ = -1.4426950408889634f;
+constexpr float GATE_SCALE_N = 2.8853900817779268f;
+__host__ __device__ inline float gate_scale(int gate) { return gate < 2 ? GATE_SCALE_RZ : GATE_SCALE_N; }
+
 struct LayerWeights {
     // fp32 originals (device), torch layout
     float *w_ih[NDIR] = {nullptr, nullptr};  // [3H][in]
@@ -75,6 +80,11 @@ struct LayerWeights {
     float *w_in_packed = nullptr;   // [768][in] fp32: rows = dir*384 + gate*128 + j
     float *bias_gi = nullptr;       // [768]: r,z: b_ih+b_hh ; n: b_ih
     float *b_hn = nullptr;          // [2][128]
+    // tensor-core path: the activations' exp2 scale factors are folded into everything that feeds a gate pre-activation
+    // (rows of W_hh / W_ih and the biases of the r and z gates times -log2 e, of the n gate times 2 log2 e), so the gate
+    // math goes straight from the accumulators into ex2 - see gate_scale() and rec_tc_kernel
+    float *bias_gi_tc = nullptr;    // [768] = bias_gi * gate_scale
+    float *b_hn_tc = nullptr;       // [2][128] = b_hn * gate_scale(n)
     float *w_hh_t = nullptr;        // [2][128(k)][384] fp32 (transposed) for the FFMA path
     __half *w_hh_tm = nullptr;      // [2][hi/lo][gate][row128][k128] fp16 row-major: source of the TMEM-resident A operand
     __half *w_x_tm = nullptr;       // layer 0, F <= 16: [2][hi/lo][gate][row128][16] fp16 (K zero-padded): fused input projection

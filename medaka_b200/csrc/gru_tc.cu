@@ -61,6 +61,19 @@ __device__ __forceinline__ F2 rcp_neg_fma2(F2 nd, F2 one2) {
     return f2_fma(y, e, y);
 }
 
+// Phase fence for the gate warps.  ptxas is free to move register-only arithmetic across bar.sync, and it does: it
+// hoisted the z and n barriers above the sigmoid(r) math, so the warp sat in the z / n barrier with that math still
+// to do (ncu source view: 130 + 164 cycles of barrier stall per step inside the r phase).  A trap predicated on the
+// phase's results (never taken: the bit pattern is a NaN the arithmetic cannot produce) makes the barrier that follows
+// control-dependent on them.
+__device__ __forceinline__ void phase_fence(F2 a, F2 b) {
+    float a0, a1, b0, b1;
+    f2_get(a, a0, a1);
+    f2_get(b, b0, b1);
+    const uint32_t u = __float_as_uint(a0) & __float_as_uint(a1) & __float_as_uint(b0) & __float_as_uint(b1);
+    if (u == 0xFFFFFFFFu) __trap();
+}
+
 // =====================================================================================================
 // Recurrent kernel.  One CTA = NT tiles of 16 windows of one direction, for the whole sequence.
 //   warps 0-15  : gate warps (TMEM -> registers -> gate math -> next h into smem + global output); warp w reads
@@ -518,8 +531,6 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
 
         constexpr float EXP_CLAMP = 60.0f;
         const F2 one2 = f2_make(1.0f, 1.0f), negone2 = f2_make(-1.0f, -1.0f);
-        const F2 knl2 = f2_make(-1.4426950408889634f, -1.4426950408889634f);     // -log2(e)
-        const F2 k2l2 = f2_make(2.8853900817779268f, 2.8853900817779268f);       // 2 log2(e)
         F2 hprev2[NP];
 #pragma unroll
         for (int q = 0; q < NP; ++q) hprev2[q] = f2_make(0.f, 0.f);
@@ -586,13 +597,17 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 if (OUT_TILES) tb = o16 + (orow >> 7) * (int64_t)(XT_TILE_BYTES / 2) + (orow & (XT_ROWS - 1)) * 8;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
+                    // (weights and biases carry the -log2 e factor, common.cuh gate_scale: the accumulator is the exponent.)
+                    // The reciprocal runs on the FMA pipe: with MUFU.RCP this phase was bound by the XU pipe (8 MUFU per
+                    // thread, 256 cycles per SM sub-partition) and sits on the r -> z -> n gate chain.
                     const F2 accr = f2_make(__uint_as_float(ar[2 * q]), __uint_as_float(ar[2 * q + 1]));
-                    float a0, a1, e0, e1;
-                    f2_get(f2_mul(f2_add(FUSE_X ? br2 : g2[0][q], accr), knl2), a0, a1);
-                    f2_get(f2_add(f2_make(ex2_approx(fminf(a0, EXP_CLAMP)), ex2_approx(fminf(a1, EXP_CLAMP))), one2), e0, e1);
-                    r2[q] = f2_make(rcp_approx(e0), rcp_approx(e1));
+                    float a0, a1;
+                    f2_get(f2_add(FUSE_X ? br2 : g2[0][q], accr), a0, a1);
+                    const F2 ea = f2_make(ex2_approx(fminf(a0, EXP_CLAMP)), ex2_approx(fminf(a1, EXP_CLAMP)));
+                    r2[q] = rcp_neg_fma2(f2_fma(ea, negone2, negone2), one2);    // r = 1 / (1 + ea)
                 }
                 REC_STAMP(5);
+                phase_fence(r2[0], r2[NP - 1]);
                 named_bar_sync<RT_BAR_Z, RC>();
                 tc_fence_after_sync();
                 tmem_ld_x4(t_lane + 1 * 16, az);
@@ -603,11 +618,12 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                     // z = 1 / (1 + eb) is never formed: its reciprocal is shared with the tanh below
                     const F2 accz = f2_make(__uint_as_float(az[2 * q]), __uint_as_float(az[2 * q + 1]));
                     float b0, b1;
-                    f2_get(f2_mul(f2_add(FUSE_X ? bz2 : g2[1][q], accz), knl2), b0, b1);
+                    f2_get(f2_add(FUSE_X ? bz2 : g2[1][q], accz), b0, b1);
                     eb2[q] = f2_make(ex2_approx(fminf(b0, EXP_CLAMP)), ex2_approx(fminf(b1, EXP_CLAMP)));
                     nzb2[q] = f2_fma(eb2[q], negone2, negone2);          // -(1 + eb)
                 }
                 REC_STAMP(7);
+                phase_fence(nzb2[0], nzb2[NP - 1]);
                 named_bar_sync<RT_BAR_N, NB_N_COUNT>();
                 tc_fence_after_sync();
                 tmem_ld_x4(t_lane + 2 * 16, an);
@@ -637,8 +653,8 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                     const F2 pre_r = f2_add(FUSE_X ? br2 : g2[0][q], accr);
                     const F2 pre_z = f2_add(FUSE_X ? bz2 : g2[1][q], accz);
                     float a0, a1, b0, b1;
-                    f2_get(f2_mul(pre_r, knl2), a0, a1);
-                    f2_get(f2_mul(pre_z, knl2), b0, b1);
+                    f2_get(pre_r, a0, a1);   // (pre-scaled by -log2 e, common.cuh gate_scale)
+                    f2_get(pre_z, b0, b1);
                     const F2 ea = f2_make(ex2_approx(fminf(a0, EXP_CLAMP)), ex2_approx(fminf(a1, EXP_CLAMP)));
                     eb2[q] = f2_make(ex2_approx(fminf(b0, EXP_CLAMP)), ex2_approx(fminf(b1, EXP_CLAMP)));
                     r2[q] = rcp_neg_fma2(f2_fma(ea, negone2, negone2), one2);    // r = 1 / (1 + ea)
@@ -657,17 +673,25 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 // exponentials are clamped at 2^60, so the denominator stays below 2^121.  Same ~2.5e-7 absolute error
                 // as ATen's (h_prev - n) * z + n evaluated with approximate exp/rcp (checked against float64).
                 float t0, t1;
-                f2_get(f2_mul(f2_fma(r2[q], f2_add(accn, bhn2), gin), k2l2), t0, t1);
+                f2_get(f2_fma(r2[q], f2_add(accn, bhn2), gin), t0, t1);   // (pre-scaled by 2 log2 e)
                 const F2 en = f2_make(ex2_approx(fminf(t0, EXP_CLAMP)), ex2_approx(fminf(t1, EXP_CLAMP)));
                 const F2 enp = f2_add(en, one2);
                 const F2 inv = rcp_neg_fma2(f2_mul(enp, nzb2[q]), one2);
                 const F2 h2 = f2_mul(f2_fma(hprev2[q], enp, f2_mul(f2_add(en, negone2), eb2[q])), inv);
                 hprev2[q] = h2;
+                // fp16 hi/lo split by TRUNCATION: hi = h with the low 13 mantissa bits cleared (one LOP3; exactly an fp16
+                // value for |h| >= 2^-14), lo = fp16(h - hi) from one packed subtract.  Same 22+ significant bits as the
+                // round-to-nearest split (|lo| < 2^-10 |h| instead of 2^-11 |h|), 5 FMA-pipe instructions fewer per pair.
                 float h0v, h1v;
                 f2_get(h2, h0v, h1v);
-                __half lo0, lo1;
-                split_f16(h0v, hh[2 * q], lo0);
-                split_f16(h1v, hh[2 * q + 1], lo1);
+                const float t0v = __uint_as_float(__float_as_uint(h0v) & 0xFFFFE000u);
+                const float t1v = __uint_as_float(__float_as_uint(h1v) & 0xFFFFE000u);
+                float l0v, l1v;
+                f2_get(f2_fma(f2_make(t0v, t1v), negone2, h2), l0v, l1v);
+                const __half2 hi2 = __floats2half2_rn(t0v, t1v), lo2 = __floats2half2_rn(l0v, l1v);
+                hh[2 * q] = __low2half(hi2);
+                hh[2 * q + 1] = __high2half(hi2);
+                const __half lo0 = __low2half(lo2), lo1 = __high2half(lo2);
                 hl[2 * q] = lo0;
                 hl[2 * q + 1] = lo1;
                 *reinterpret_cast<__half *>(hrow + (2 * q) * 16) = hh[2 * q];           // B operand of the next step
@@ -971,9 +995,9 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
                 for (int i = 0; i < 32; i += 4) {
                     const int c = c32 + i;
                     if (c < prem)
-                        out[(int64_t)(c >> 4) * (GI_TS_FLOATS / 4) + ((c & 15) >> 2) * H] =
-                            make_float4(__uint_as_float(v[i]) + bj, __uint_as_float(v[i + 1]) + bj,
-                                        __uint_as_float(v[i + 2]) + bj, __uint_as_float(v[i + 3]) + bj);
+                        st_stream4(out + (int64_t)(c >> 4) * (GI_TS_FLOATS / 4) + ((c & 15) >> 2) * H,
+                                   make_float4(__uint_as_float(v[i]) + bj, __uint_as_float(v[i + 1]) + bj,
+                                               __uint_as_float(v[i + 2]) + bj, __uint_as_float(v[i + 3]) + bj));
                 }
             }
             tc_fence_before_sync();

@@ -280,9 +280,10 @@ __global__ void __launch_bounds__(256) inproj0_kernel(const float *__restrict__ 
         const int64_t pp = p0 + p;
         if (tiled) {   // tensor-core path: quad layout (common.cuh)
             const int64_t orow = tiled_row(pp / T, pp % T, T);
-            gi[gi_quad_index(orow, tid)] = a0;
-            gi[gi_quad_index(orow, tid + 256)] = a1;
-            gi[gi_quad_index(orow, tid + 512)] = a2;
+            // (pre-scaled for the exp2-based gate math of rec_tc_kernel, common.cuh gate_scale)
+            gi[gi_quad_index(orow, tid)] = a0 * gate_scale((tid % G3) / H);
+            gi[gi_quad_index(orow, tid + 256)] = a1 * gate_scale(((tid + 256) % G3) / H);
+            gi[gi_quad_index(orow, tid + 512)] = a2 * gate_scale(((tid + 512) % G3) / H);
         } else {
             float *row = gi + pp * GI_COLS;
             row[tid] = a0;
@@ -303,7 +304,8 @@ __global__ void __launch_bounds__(256) inproj0_generic_kernel(const float *__res
     for (int c = threadIdx.x; c < GI_COLS; c += 256) {
         float a = bias[c];
         for (int f = 0; f < F; ++f) a = fmaf(feats[p * F + f], w[c * F + f], a);
-        gi[tiled ? gi_quad_index(orow, c) : orow * GI_COLS + c] = a;
+        if (tiled) gi[gi_quad_index(orow, c)] = a * gate_scale((c % G3) / H);
+        else gi[orow * GI_COLS + c] = a;
     }
 }
 
@@ -425,7 +427,7 @@ cudaError_t launch_head(const float *h1, const float *lin_w, const float *lin_b,
 __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const float *w_hh0, const float *w_hh1,
                                   const float *b_ih0, const float *b_ih1, const float *b_hh0, const float *b_hh1,
                                   int in_features, float *w_in_packed, float *bias_gi, float *b_hn, float *w_hh_t,
-                                  __half *w_hh_tm, __half *w_x_tm, __half *w_in_tc) {
+                                  __half *w_hh_tm, __half *w_x_tm, __half *w_in_tc, float *bias_gi_tc, float *b_hn_tc) {
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const float *w_ih[2] = {w_ih0, w_ih1}, *w_hh[2] = {w_hh0, w_hh1};
@@ -439,10 +441,12 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
     for (int64_t i = tid; i < GI_COLS; i += stride) {
         const int d = (int)i / G3, r = (int)i % G3;
         bias_gi[i] = (r < 2 * H) ? (b_ih[d][r] + b_hh[d][r]) : b_ih[d][r];
+        bias_gi_tc[i] = bias_gi[i] * gate_scale(r / H);
     }
     for (int64_t i = tid; i < NDIR * H; i += stride) {
         const int d = (int)i / H, j = (int)i % H;
         b_hn[i] = b_hh[d][2 * H + j];
+        b_hn_tc[i] = b_hn[i] * GATE_SCALE_N;
     }
     // recurrent weights, transposed fp32 [d][k][384] and fp16 hi/lo blocks [d][part][gate][kg][row][8]
     for (int64_t i = tid; i < (int64_t)NDIR * G3 * H; i += stride) {
@@ -451,9 +455,9 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
         const int c = rem / H, k = rem % H;          // c = gate row, k = input unit
         const float v = w_hh[d][c * H + k];
         w_hh_t[((int64_t)d * H + k) * G3 + c] = v;
-        __half hi, lo;
-        split_f16(v, hi, lo);
         const int g = c / H, j = c % H;
+        __half hi, lo;
+        split_f16(v * gate_scale(g), hi, lo);
         const int64_t blk_halfs = (int64_t)H * H;   // 128x128 block
         w_hh_tm[(((int64_t)d * 2 + 0) * 3 + g) * blk_halfs + j * H + k] = hi;
         w_hh_tm[(((int64_t)d * 2 + 1) * 3 + g) * blk_halfs + j * H + k] = lo;
@@ -464,9 +468,9 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
             const int rem = (int)(i % (G3 * 16));
             const int c = rem / 16, k = rem % 16;
             const float v = (k < in_features) ? w_ih[d][(int64_t)c * in_features + k] : 0.f;
-            __half hi, lo;
-            split_f16(v, hi, lo);
             const int g = c / H, j = c % H;
+            __half hi, lo;
+            split_f16(v * gate_scale(g), hi, lo);
             w_x_tm[((((int64_t)d * 2 + 0) * 3 + g) * H + j) * 16 + k] = hi;
             w_x_tm[((((int64_t)d * 2 + 1) * 3 + g) * H + j) * 16 + k] = lo;
         }
@@ -477,7 +481,7 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
             const int d = row / G3, r = row % G3;
             const float v = w_ih[d][(int64_t)r * H2 + k];
             __half hi, lo;
-            split_f16(v, hi, lo);
+            split_f16(v * gate_scale(r / H), hi, lo);
             const int blk = row / H, j = row % H;
             const int64_t plane = (int64_t)H * H2;   // 128 x 256 halfs
             w_in_tc[((int64_t)blk * 2 + 0) * plane + (int64_t)j * H2 + k] = hi;
@@ -489,7 +493,8 @@ __global__ void pack_layer_kernel(const float *w_ih0, const float *w_ih1, const 
 cudaError_t launch_prepare_layer(const LayerWeights &lw, int in_features, bool build_in_tc, cudaStream_t s) {
     pack_layer_kernel<<<296, 256, 0, s>>>(lw.w_ih[0], lw.w_ih[1], lw.w_hh[0], lw.w_hh[1], lw.b_ih[0], lw.b_ih[1],
                                           lw.b_hh[0], lw.b_hh[1], in_features, lw.w_in_packed, lw.bias_gi,
-                                          lw.b_hn, lw.w_hh_t, lw.w_hh_tm, lw.w_x_tm, build_in_tc ? lw.w_in_tc : nullptr);
+                                          lw.b_hn, lw.w_hh_t, lw.w_hh_tm, lw.w_x_tm, build_in_tc ? lw.w_in_tc : nullptr,
+                                          lw.bias_gi_tc, lw.b_hn_tc);
     return cudaGetLastError();
 }
 

@@ -284,4 +284,10 @@ __device__ __forceinline__ float4 ld_stream4(const float *p) {
     return v;
 }
 
+// 16-byte store of data that is written once and read much later (gi: 34 GB per launch): evict-first in L2 so that it
+// does not push out the activation tiles the other weight-block CTAs of the GEMM are about to re-read
+__device__ __forceinline__ void st_stream4(float4 *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 }  // namespace mdk
