@@ -120,6 +120,25 @@ def host_cores():
     return n
 
 
+# stdout carries exactly ONE line (the JSON): libraries that chat on fd 1 (NCCL prints its version there under torchrun)
+# are sent to stderr for the whole run, and the line is written to the saved descriptor at the end
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def log(msg):
     print("[bench %.1fs] %s" % (time.perf_counter() - T_START, msg), file=sys.stderr, flush=True)
 
@@ -189,7 +208,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": rate, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name():
@@ -213,6 +232,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -410,7 +430,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
