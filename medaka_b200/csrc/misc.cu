@@ -346,12 +346,30 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1,
     const int cls = lane & 7;                      // class owned by this lane after the reduction
     const float my_bias = cls < NCLS ? lin_b[cls] : 0.f;
     constexpr int PU = 4;
-    for (int64_t pb = warp * PU; pb < P; pb += nwarps * PU) {
+    // Each warp walks a CONTIGUOUS chunk of row quads of h1 (rows = the tensor-core path's tile-interleaved order, or plain
+    // position order): the row -> (window, t) -> output position mapping is then one 64-bit division per warp and an
+    // increment per iteration, where a grid-stride loop paid two divisions per position (the kernel is instruction-bound:
+    // 170 instructions per position before this change, profiles/r01f_ncu_full.md).
+    const int64_t rows = tiled ? tiled_rows(B, T) : P;            // multiple of 16 when tiled
+    const int64_t quads = (rows + PU - 1) / PU;
+    const int64_t per_warp = (quads + nwarps - 1) / nwarps;
+    const int64_t q0 = warp * per_warp, q1 = min(quads, q0 + per_warp);
+    // position of the first row of the chunk: tiled row r = ((w / 16) * T + t) * 16 + w % 16
+    int64_t wt = 0, t = 0;      // window tile, time step
+    int wl = 0;                 // window within the tile (multiple of 4 at quad granularity)
+    if (tiled && q0 < q1) {
+        const int64_t r0 = q0 * PU;
+        wt = r0 / (T * WT);
+        const int64_t rem = r0 - wt * (T * WT);
+        t = rem / WT;
+        wl = (int)(rem - t * WT);
+    }
+    for (int64_t q = q0; q < q1; ++q) {
+        const int64_t rb = q * PU;                 // first row of the quad
         float4 va[PU], vb[PU];
 #pragma unroll
         for (int u = 0; u < PU; ++u) {
-            const int64_t pp = min(pb + u, P - 1);
-            const int64_t r = tiled ? tiled_row(pp / T, pp % T, T) : pp;
+            const int64_t r = min(rb + u, rows - 1);
             va[u] = ld_stream4(h1 + r * H2 + lane * 8);
             vb[u] = ld_stream4(h1 + r * H2 + lane * 8 + 4);
         }
@@ -400,8 +418,23 @@ __global__ void __launch_bounds__(256) head_kernel(const float *__restrict__ h1,
             const int oa = __shfl_xor_sync(0xffffffffu, arg, m);
             if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
         }
-        const int64_t p = pb + (lane >> 3);
-        if (p < P) {
+        // output position of this lane's row (quad row lane >> 3)
+        int64_t p;
+        bool ok;
+        if (tiled) {
+            const int64_t win = wt * WT + wl + (lane >> 3);
+            p = win * T + t;
+            ok = win < B;                            // padding windows of a ragged last tile are real rows, never copied out
+            wl += PU;
+            if (wl == WT) {
+                wl = 0;
+                if (++t == T) { t = 0; ++wt; }
+            }
+        } else {
+            p = rb + (lane >> 3);
+            ok = p < P;
+        }
+        if (ok) {
             if (cls < NCLS) {
                 probs[p * NCLS + cls] = pr;
                 if (logits) logits[p * NCLS + cls] = logit;
