@@ -14,6 +14,7 @@
 //
 // Shared-memory operand layout (K-major, SWIZZLE_NONE): [k-group = k/8][row][8 halfs]; a core matrix is 8 rows
 // x 16 B = 128 contiguous bytes, LBO = rows*16 B (next k-group), SBO = 128 B (next 8 rows).
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -879,9 +880,14 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int blk = blockIdx.y;                 // weight block: dir*3 + gate
-    const int64_t tile0 = blockIdx.x;
-    const int64_t tstride = gridDim.x;
+    // The weight block is the FAST grid dimension: the six CTAs that stream the same activation tiles then have consecutive
+    // block ids and land next to each other (same GPC / die), so five of the six reads of a tile hit L2.  With the tile index
+    // fast (the round-1 layout) the six sat 24 block ids apart, spread over both dies, and DRAM read 30.3 GB per launch
+    // instead of 12.5 GB (11.4 algorithmic); the kernel is at the power cap, so the saved HBM energy is clock for the whole
+    // step: 10.7 -> 9.65 ms for this kernel and +7 % end to end (profiles/r01h_gemm_cta_order.md).
+    const int blk = blockIdx.x;                 // weight block: dir*3 + gate
+    const int64_t tile0 = blockIdx.y;
+    const int64_t tstride = gridDim.y;
 
     if (tid == 0) {
         for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -1025,7 +1031,7 @@ cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const flo
     int64_t ct = sm_count / 6;
     if (ct < 1) ct = 1;
     if (ct > ntiles) ct = ntiles;
-    dim3 grid((unsigned)ct, 6);
+    dim3 grid(6, (unsigned)ct);
     gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, s>>>(reinterpret_cast<const uint8_t *>(x_tiles), w_in_tm, bias, gi,
                                                      P, ntiles);
     return cudaGetLastError();
