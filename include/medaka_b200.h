@@ -138,6 +138,11 @@ int mdk_engine_timer_stop(mdk_engine *e, float *elapsed_ms);
 int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_t n_floats);
 /* number of kernels launched by this engine since creation (bench.py "gpu_launches") */
 int64_t mdk_engine_launch_count(mdk_engine *e);
+/* Number of windows per predict_on_batch call that fills the device exactly once: the recurrent kernel runs one CTA per
+ * (16-window tile, direction), so 16 * (SMs / 2) windows = 1184 on a B200 is one full wave (the reference's --batch_size
+ * default, medaka/prediction.py:14 / medaka.py, is sized for its own GPUs' memory; a 200-window batch uses 26 of 148 SMs).
+ * Callers that own the batching (run_prediction) should coalesce to this size. */
+int64_t mdk_engine_preferred_windows(mdk_engine *e);
 
 /* ---- featuriser seam: replaces CountsFeatureEncoder._post_process_pileup --------------------
  * (medaka/features.py:871-935): depth = sum of counts, minor columns take the depth of their

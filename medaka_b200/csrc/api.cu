@@ -527,6 +527,11 @@ int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_
 
 int64_t mdk_engine_launch_count(mdk_engine *e) { return e ? e->launches : 0; }
 
+int64_t mdk_engine_preferred_windows(mdk_engine *e) {
+    const int sms = e ? e->sm_count : 148;
+    return (int64_t)mdk::WT * (sms / mdk::NDIR);
+}
+
 // ---------------------------------------------------------------------------- featuriser seam
 int mdk_normalise_counts_dev(int device, const uint64_t *counts_dev, const int64_t *major_dev,
                              const int64_t *minor_dev, int64_t n, int32_t num_dtypes, int32_t mode,

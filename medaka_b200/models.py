@@ -303,6 +303,11 @@ class GRUModel(object):
     def launch_count(self):
         return int(_lm.lib.mdk_engine_launch_count(self._engine))
 
+    def preferred_batch_size(self):
+        """Windows per batch that fill the device in one wave (1184 on a B200); ``batch_size="auto"`` in
+        ``prediction.run_prediction`` / ``predict_regions`` resolves to this."""
+        return int(_lm.lib.mdk_engine_preferred_windows(self._engine))
+
     @property
     def engine(self):
         return self._engine

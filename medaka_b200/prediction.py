@@ -128,6 +128,8 @@ def run_prediction(output, bam, regions, model, feature_encoder, chunk_len, chun
                    save_features=False, enable_chunking=True, bam_workers=2):
     """Inference worker (medaka/prediction.py:14-81): returns the remainder regions."""
     logger = common.get_named_logger('PWorker')
+    if batch_size == "auto":   # the engine's one-wave batch instead of the reference's CLI default
+        batch_size = model.preferred_batch_size() if hasattr(model, "preferred_batch_size") else 200
     loader = DataLoader(
         bam, regions, batch_size, batch_cache_size=8, bam_workers=bam_workers,
         feature_encoder=feature_encoder, chunk_len=chunk_len, chunk_overlap=chunk_ovlp,

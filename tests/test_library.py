@@ -37,6 +37,13 @@ def test_constants_match_reference_library():
     assert lib.MDK_PREC_TC == 0 and lib.MDK_NORM_FWD_REV == 1
 
 
+def test_preferred_windows_is_one_wave():
+    # 16 windows per tile x (148 SMs / 2 directions): host logic only, no device needed
+    from medaka_b200 import libmedaka as lm
+    lib = lm.load()
+    assert lib.mdk_engine_preferred_windows(lm.ffi.NULL) == 16 * 74
+
+
 def test_sass_contains_tcgen05_and_bulk_copy(built_lib):
     """The tensor-core kernels really are tcgen05 (UTCHMMA / LDTM) with TMA-engine bulk copies (UBLKCP)."""
     sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
