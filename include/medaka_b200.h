@@ -136,6 +136,9 @@ int mdk_engine_timer_stop(mdk_engine *e, float *elapsed_ms);
 /* debugging / layer-wise parity: copy an internal activation of the last forward to host.
  * which: 0 = layer-0 output [B][T][2H] fp32, 1 = layer-1 output [B][T][2H] fp32 */
 int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_t n_floats);
+/* keep != 0: leave the layer-1 output in HBM (for mdk_engine_read_activation(e, 1, ...)) by running the 5-class head as
+ * its own kernel; default 0: the head is fused into the layer-1 recurrence whenever the batch is one tile per CTA */
+int mdk_engine_keep_activations(mdk_engine *e, int keep);
 /* number of kernels launched by this engine since creation (bench.py "gpu_launches") */
 int64_t mdk_engine_launch_count(mdk_engine *e);
 /* Number of windows per predict_on_batch call that fills the device exactly once: the recurrent kernel runs one CTA per

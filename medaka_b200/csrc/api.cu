@@ -75,6 +75,12 @@ static int prepare_weights(mdk_engine *e) {
         MDK_CUDA(launch_prepare_layer(lw, in, l == 1, e->stream));
         e->launches++;
     }
+    {
+        int rc;
+        if (!e->lin_w_tc && (rc = dev_alloc(&e->lin_w_tc, (size_t)NDIR * 2 * 16 * 64 * 8))) return rc;
+        MDK_CUDA(launch_pack_linear(e->lin_w, e->lin_w_tc, e->stream));
+        e->launches++;
+    }
     MDK_CUDA(cudaStreamSynchronize(e->stream));
     e->prepared = true;
     return MDK_OK;
@@ -89,11 +95,13 @@ static int ensure_workspace(mdk_engine *e, int64_t B, int64_t T) {
     dev_free(e->gi);
     if (e->h0) { cudaFree(e->h0); e->h0 = nullptr; }
     dev_free(e->h1);
+    dev_free(e->plog);
     e->cap_pos = 0;
     int rc;
     if ((rc = dev_alloc(&e->gi, (size_t)need * GI_COLS))) return rc;
     MDK_CUDA(cudaMalloc(&e->h0, (size_t)need * H2 * sizeof(float)));
     if ((rc = dev_alloc(&e->h1, (size_t)need * H2))) return rc;
+    if ((rc = dev_alloc(&e->plog, (size_t)NDIR * (need / WT) * PLOG_TS_FLOATS))) return rc;
     e->cap_pos = need;
     return MDK_OK;
 }
@@ -150,11 +158,17 @@ static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t
     else MDK_CUDA(launch_gemm_fp32((const float *)e->h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, e->gi, P, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[4], s));
-    if (tc) MDK_CUDA(launch_rec_tc(e->gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, e->h1, 0, B, T, e->sm_count, s));
+    // one tile per CTA (the common case): the linear head rides inside the layer-1 recurrence as extra MMAs and only
+    // 40 B/position of partial logits reach HBM instead of the 1 KiB/position h1 round trip
+    const bool fuse_head = tc && !e->keep_act && rec_tc_can_fuse_logits(B, e->sm_count);
+    if (tc) MDK_CUDA(launch_rec_tc(e->gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, e->h1, 0, B, T, e->sm_count, s,
+                                   fuse_head ? e->lin_w_tc : nullptr, fuse_head ? e->plog : nullptr));
     else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[1].w_hh_t, e->layer[1].b_hn, e->h1, B, T, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[5], s));
-    MDK_CUDA(launch_head(e->h1, e->lin_w, e->lin_b, B, T, tc ? 1 : 0, probs_dev, logits_dev, labels_dev, s));
+    if (fuse_head) MDK_CUDA(launch_head_plog(e->plog, e->lin_b, B, T, probs_dev, logits_dev, labels_dev, s));
+    else MDK_CUDA(launch_head(e->h1, e->lin_w, e->lin_b, B, T, tc ? 1 : 0, probs_dev, logits_dev, labels_dev, s));
+    e->last_fused_head = fuse_head;
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[6], s));
     e->launches += launches;
@@ -296,7 +310,7 @@ int mdk_engine_destroy(mdk_engine *e) {
         dev_free(lw.bias_gi_tc); dev_free(lw.b_hn_tc);
         dev_free(lw.w_hh_tm); dev_free(lw.w_x_tm); dev_free(lw.w_in_tc);
     }
-    dev_free(e->lin_w); dev_free(e->lin_b);
+    dev_free(e->lin_w); dev_free(e->lin_b); dev_free(e->lin_w_tc); dev_free(e->plog);
     dev_free(e->gi); dev_free(e->h1);
     if (e->h0) cudaFree(e->h0);
     for (auto &sl : e->io) {
@@ -505,6 +519,9 @@ int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_
     MDK_REQUIRE(which == 0 || which == 1, MDK_ERR_ARG, "read_activation: which must be 0 or 1");
     const int64_t P = e->last_B * e->last_T;
     MDK_REQUIRE(P > 0 && n_floats == P * H2, MDK_ERR_ARG, "read_activation: size must be B*T*256 of the last forward");
+    MDK_REQUIRE(!(which == 1 && e->last_fused_head), MDK_ERR_STATE,
+                "read_activation(1): the last forward fused the head into layer 1 (h1 never reached HBM); call "
+                "mdk_engine_keep_activations(e, 1) before the forward");
     MDK_CUDA(cudaSetDevice(e->device));
     MDK_CUDA(cudaStreamSynchronize(e->stream));
     if (e->last_precision == MDK_PREC_FP32) {
@@ -526,6 +543,12 @@ int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_
 }
 
 int64_t mdk_engine_launch_count(mdk_engine *e) { return e ? e->launches : 0; }
+
+int mdk_engine_keep_activations(mdk_engine *e, int keep) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "NULL engine");
+    e->keep_act = keep != 0;
+    return MDK_OK;
+}
 
 int64_t mdk_engine_preferred_windows(mdk_engine *e) {
     const int sms = e ? e->sm_count : 148;

@@ -109,6 +109,11 @@ struct mdk_engine {
     mdk::LayerWeights layer[2];
     float *lin_w = nullptr, *lin_b = nullptr;
     bool lin_loaded = false;
+    __half *lin_w_tc = nullptr;   // [dir][hi/lo][k-group 16][row 64][8 halfs]: W_lin half of one direction as an M=64 smem A
+                                  // operand (rows >= 5 zero) for the logits MMAs fused into the layer-1 recurrence
+    float *plog = nullptr;        // fused path: per-direction partial logits [dir][tile-step][class 5][16 windows]
+    bool keep_act = false;        // debugging: keep h1 (layer-1 output) in HBM, i.e. run the unfused head
+    bool last_fused_head = false; // the last forward took the fused path (no h1)
     bool prepared = false;
     // workspace
     int64_t cap_pos = 0;       // capacity in positions (B*T, rounded up to XT_ROWS)
@@ -166,8 +171,17 @@ struct RecXArgs {            // fused layer-0 input projection (rec_tc FUSE_X)
     int F;
 };
 cudaError_t rec_trace_control(int enable, unsigned long long *host_out);
+// lin_w_tc != nullptr (layer 1, one tile per CTA): the 5-class linear head runs inside the recurrence as extra MMAs and
+// the kernel writes partial logits to plog instead of h_out; *fused_logits tells the caller whether it did
+bool rec_tc_can_fuse_logits(int64_t B, int sm_count);
 cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
-                          void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, cudaStream_t s);
+                          void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, cudaStream_t s,
+                          const __half *lin_w_tc = nullptr, float *plog = nullptr);
+// head on the partial logits of the fused path: sum of the two directions + bias -> softmax / argmax
+cudaError_t launch_head_plog(const float *plog, const float *lin_b, int64_t B, int64_t T, float *probs, float *logits,
+                             uint8_t *labels, cudaStream_t s);
+cudaError_t launch_pack_linear(const float *lin_w, __half *lin_w_tc, cudaStream_t s);
+constexpr int PLOG_TS_FLOATS = NCLS * WT;     // 80 floats per (tile-step, direction)
 cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const float *bias, float *gi, int64_t P,
                            int sm_count, cudaStream_t s);
 int selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant);

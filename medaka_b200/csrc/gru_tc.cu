@@ -129,7 +129,7 @@ constexpr int RT_WT_COLS = 2 * 3 * (H / 2);              // W_hh hi+lo as TMEM A
 constexpr int RT_WX_COLS = 2 * 3 * 8;                    // W_ih (K = 16) hi+lo as TMEM A operand: 48 columns
 constexpr int RT_WX_BLOCK = H * 16 * 2;                  // one (part, gate) block of W_ih in smem: [kg 2][row 128][8] = 4 KiB
 
-template <int NT, bool FUSE_X>
+template <int NT, bool FUSE_X, bool LOGITS = false>
 struct RecCfg {
     static constexpr bool wx_tmem = FUSE_X && NT == 1;
     // accumulator columns per tile: r, z, n (16 each) [+ W_in.x of the n gate]
@@ -156,7 +156,20 @@ struct RecCfg {
     static constexpr int gi_end = gi_off + (gi_smem ? GI_BUFS * GI_BLOCK : 0);
     // the CTA owns all 512 TMEM columns of its SM, so a second co-resident CTA could only spin in tcgen05.alloc;
     // ask for > half of the shared memory to keep residency at one CTA per SM.
-    static constexpr int total = gi_end > 120 * 1024 ? gi_end : 120 * 1024;
+    // LOGITS (layer 1, NT == 1): the linear head runs as 24 extra M64 N16 K16 MMAs per step on the h tile.  They execute
+    // while the gate warps are already producing the next h, so the tile is DOUBLE BUFFERED (HB = distance between the
+    // buffers; the tile read by step t's MMAs is only overwritten in the tail of step t + 1, after that step's n commit,
+    // which the in-order tensor pipe completes after these MMAs).  W_lin (fp16 hi/lo, 64 rows, 5 used) is a shared-memory
+    // A operand image [plane][k-group 16][row 64][8 halfs].
+    static constexpr int h2_off = ((gi_end + 127) / 128) * 128;
+    static constexpr int HB = LOGITS ? h2_off - h_off : 0;
+    static constexpr int WL_PLANE = 16 * 64 * 16;                          // 16 KiB
+    static constexpr int wl_off = h2_off + (LOGITS ? ((NT * 2 * RT_HPLANE + 127) / 128) * 128 : 0);
+    static constexpr int logbar_off = wl_off + (LOGITS ? 2 * WL_PLANE : 0);
+    static constexpr uint32_t log_col = acc_col0 + NT * acc_per_tile;      // 16 accumulator columns of the logits MMAs
+    static_assert(!LOGITS || log_col + 16 <= 512, "TMEM budget");
+    static constexpr int end_ = logbar_off + 16;
+    static constexpr int total = end_ > 120 * 1024 ? end_ : 120 * 1024;
     static_assert(total <= 227 * 1024, "smem budget");
 };
 
@@ -178,13 +191,15 @@ constexpr int RT_TRACE_STEP0 = 512, RT_TRACE_STEPS = 16, RT_TRACE_SLOTS = 40;
         if (TRACE && tr) tr[slot] = (unsigned long long)clock64(); \
     } while (0)
 
-template <int NT, bool OUT_TILES, bool FUSE_X, bool TRACE = false>
+template <int NT, bool OUT_TILES, bool FUSE_X, bool TRACE = false, bool LOGITS = false>
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__ w_hh,
               const float *__restrict__ b_hn, void *__restrict__ h_out, int64_t B, int64_t T,
-              unsigned long long *__restrict__ trace) {
+              unsigned long long *__restrict__ trace, const __half *__restrict__ lin_w_tc, float *__restrict__ plog) {
     extern __shared__ __align__(128) uint8_t smem[];
-    using L = RecCfg<NT, FUSE_X>;
+    using L = RecCfg<NT, FUSE_X, LOGITS>;
+    static_assert(!LOGITS || (NT == 1 && !FUSE_X && !OUT_TILES), "fused logits: layer 1, one tile per CTA");
+    uint64_t *log_bar = reinterpret_cast<uint64_t *>(smem + L::logbar_off);
     // NT == 1 writing operand tiles (layer 0): the h tile the gate warps publish in shared memory already IS the tile
     // image the projection GEMM wants (per k-group 16 rows x 16 B contiguous), so warp 18 copies it out with 32 bulk
     // async copies per step instead of 8 two-byte global stores per gate thread.
@@ -219,6 +234,11 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             dst[pg * (RT_WX_BLOCK / 2) + (k >> 3) * (H * 8) + r * 8 + (k & 7)] = src[i];
         }
     }
+    if (LOGITS) {   // this direction's half of W_lin, already in operand layout
+        const int4 *src = reinterpret_cast<const int4 *>(lin_w_tc + (size_t)dir * 2 * (L::WL_PLANE / 2));
+        int4 *dst = reinterpret_cast<int4 *>(smem + L::wl_off);
+        for (int i = tid; i < 2 * L::WL_PLANE / 16; i += RT_THREADS) dst[i] = src[i];
+    }
     if (tid == 0) {
         for (int i = 0; i < NT; ++i) {
             // split (NT == 1): acc_ready / rz_issued / acc_n = commit of the r / z / n block, one arrival each
@@ -228,6 +248,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             mbar_init(&rz_issued[i], 1);
         }
         for (int i = 0; i < L::GI_BUFS; ++i) mbar_init(&gi_full[i], 1);
+        if (LOGITS) mbar_init(log_bar, 1);
         fence_mbar_init();
     }
     if (warp == RT_GATE_WARPS) {
@@ -289,6 +310,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         const uint64_t x_desc0 = make_smem_desc(smem_u32(smem + L::x_off), RT_KG, 128);
         const uint64_t wx_desc0 = make_smem_desc(smem_u32(smem + L::wx_off), H * 16, 128);
         // W_hh[gate] (K steps [ks0, ks1)) . h of `tile`, three fp16 products, into accumulator columns d
+        uint64_t b_cur = b_desc0;      // descriptor of the h tile buffer this step's MMAs read (LOGITS: alternates)
         auto issue_h = [&](uint32_t d, int gate, int ks0, int ks1, int tile, bool fresh) {
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {
@@ -296,12 +318,46 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 const int pb = (prod == 1) ? 1 : 0;   // activation part: hi, lo, hi
 #pragma unroll
                 for (int ks = ks0; ks < ks1; ++ks) {
-                    const uint64_t bd = b_desc0 + (uint64_t)(((tile * 2 + pb) * RT_HPLANE + ks * 2 * RT_KG) >> 4);
+                    const uint64_t bd = b_cur + (uint64_t)(((tile * 2 + pb) * RT_HPLANE + ks * 2 * RT_KG) >> 4);
                     umma_f16_ts(d, (uint32_t)(((pa * 3 + gate) * 8 + ks) * 8), bd, idesc,
                                 (fresh && prod == 0 && ks == ks0) ? 0u : 1u);
                 }
             }
         };
+        // logits of the position whose h is in the current tile: W_lin (M = 64 rows, 5 used; A from shared memory) . h
+        const uint64_t wl_desc0 = make_smem_desc(smem_u32(smem + L::wl_off), 64 * 16, 128);
+        const uint32_t idesc64 = make_idesc_f16(64, RT_N);
+        auto issue_logits = [&]() {
+#pragma unroll
+            for (int prod = 0; prod < 3; ++prod) {
+                const int pa = (prod == 2) ? 1 : 0;
+                const int pb = (prod == 1) ? 1 : 0;
+#pragma unroll
+                for (int ks = 0; ks < H / 16; ++ks) {
+                    const uint64_t ad = wl_desc0 + (uint64_t)((pa * L::WL_PLANE + ks * 2 * (64 * 16)) >> 4);
+                    const uint64_t bd = b_cur + (uint64_t)((pb * RT_HPLANE + ks * 2 * RT_KG) >> 4);
+                    umma_f16(L::log_col, ad, bd, idesc64, (prod | ks) ? 1u : 0u);
+                }
+            }
+            umma_commit(log_bar);
+        };
+        // TMEM -> plog[dir][tile-step][class][16 windows]: lanes 0..4 of this warp (TMEM lanes 0..4 = classes) hold one row
+        auto store_logits = [&](int64_t t_idx) {
+            uint32_t v[16];
+            tc_fence_after_sync();
+            tmem_ld_x16(L::log_col, v);
+            tmem_ld_wait();
+            if (lane < NCLS) {
+                float4 *dst = reinterpret_cast<float4 *>(
+                    plog + (((int64_t)dir * gridDim.x + blockIdx.x) * T + t_idx) * PLOG_TS_FLOATS + lane * WT);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
+            tc_fence_before_sync();
+        };
+        uint32_t log_par = 0;
         // + W_ih[gate] . x_t (fused layer-0 input projection)
         auto issue_x = [&](uint32_t d, int gate, int tile, uint32_t par, bool fresh) {
 #pragma unroll
@@ -355,6 +411,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             if (TRACE && trace && blockIdx.x == 0 && blockIdx.y == 0 && step >= RT_TRACE_STEP0 &&
                 step < RT_TRACE_STEP0 + RT_TRACE_STEPS)
                 tr = trace + (step - RT_TRACE_STEP0) * RT_TRACE_SLOTS;
+            if (LOGITS) b_cur = b_desc0 + (uint64_t)((par * L::HB) >> 4);
 #pragma unroll
             for (int tile = 0; tile < NT; ++tile) {
                 if (RT_NB) {
@@ -387,6 +444,8 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                             if (FUSE_X) issue_x(d0 + 48, 2, tile, par, true);
                             umma_commit(&acc_n[tile]);
                             REC_STAMP(3);
+                            // the tile holds h of the previous step: its logits ride in the gate phase's shadow
+                            if (LOGITS && step > 0) issue_logits();
                         } else if (g == 2) {
                             if (BULK_OUT && step > 0) {
                                 // h_{step-1} (published through BAR_H) -> its rows of the GEMM operand tiles
@@ -439,6 +498,11 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                     }
                 }
                 __syncwarp();
+                if (LOGITS && g == 0 && step > 0) {
+                    mbar_wait(log_bar, log_par);
+                    log_par ^= 1u;
+                    store_logits(dir ? (T - step) : (step - 1));
+                }
                 if (BULK_OUT && g == 2) named_bar_arrive<RT_BAR_N, NB_N_COUNT>();
                 if (GI_SMEM && g == 2 && step == 0) {
                     mbar_wait(&gi_full[0], 0u);
@@ -464,6 +528,16 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                     if (TRACE && tr && lane == 0) tr[15] = (unsigned long long)clock64();
                 }
             }
+        }
+        if (LOGITS && g == 0) {
+            // h of the last step: wait for every gate warp's final tile (named barrier id 6), then one more round
+            named_bar_sync<6, 32 * RT_GATE_WARPS + 32>();
+            tc_fence_after_sync();
+            b_cur = b_desc0 + (uint64_t)((((uint32_t)T & 1u) * L::HB) >> 4);
+            if (elect_one()) issue_logits();
+            __syncwarp();
+            mbar_wait(log_bar, log_par);
+            store_logits(dir ? 0 : (T - 1));
         }
     } else {
         // ================= gate warps =================
@@ -695,10 +769,11 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 const __half lo0 = __low2half(lo2), lo1 = __high2half(lo2);
                 hl[2 * q] = lo0;
                 hl[2 * q + 1] = lo1;
-                *reinterpret_cast<__half *>(hrow + (2 * q) * 16) = hh[2 * q];           // B operand of the next step
-                *reinterpret_cast<__half *>(hrow + RT_HPLANE + (2 * q) * 16) = lo0;
-                *reinterpret_cast<__half *>(hrow + (2 * q + 1) * 16) = hh[2 * q + 1];
-                *reinterpret_cast<__half *>(hrow + RT_HPLANE + (2 * q + 1) * 16) = lo1;
+                uint8_t *hw = hrow + (((int)step + 1) & 1) * L::HB;                     // (LOGITS: the buffer not being read)
+                *reinterpret_cast<__half *>(hw + (2 * q) * 16) = hh[2 * q];             // B operand of the next step
+                *reinterpret_cast<__half *>(hw + RT_HPLANE + (2 * q) * 16) = lo0;
+                *reinterpret_cast<__half *>(hw + (2 * q + 1) * 16) = hh[2 * q + 1];
+                *reinterpret_cast<__half *>(hw + RT_HPLANE + (2 * q + 1) * 16) = lo1;
             }
             if (FUSE_X && xown && more) {
                 // stage x_{step+1} (loaded a step ago) into the other x buffer
@@ -716,6 +791,8 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
             if (RT_NB) {
                 if (more) {   // nobody waits for the tile written by the last step: leave no arrivals pending at exit
                     if (tile == 0) named_bar_arrive<RT_BAR_H, HCOUNT>(); else named_bar_arrive<RT_BAR_H + 1, HCOUNT>();
+                } else if (LOGITS) {
+                    named_bar_arrive<6, 32 * RT_GATE_WARPS + 32>();   // ... except the issuer, for the last position's logits
                 }
             } else {
                 mbar_arrive(&h_ready[tile]);
@@ -731,7 +808,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 step < RT_TRACE_STEP0 + RT_TRACE_STEPS)     // slots 16..31: when each gate warp arrived
                 trace[(step - RT_TRACE_STEP0) * RT_TRACE_SLOTS + 16 + warp] = (unsigned long long)clock64();
             if (tile_ok) {
-                if (!BULK_OUT) {
+                if (!BULK_OUT && !LOGITS) {
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         if (OUT_TILES) {
@@ -799,8 +876,14 @@ cudaError_t rec_trace_control(int enable, unsigned long long *host_out) {
     return cudaSuccess;
 }
 
+bool rec_tc_can_fuse_logits(int64_t B, int sm_count) {
+    const int64_t tiles = (B + RT_N - 1) / RT_N;
+    return tiles > 0 && tiles * NDIR <= (int64_t)sm_count;      // one tile per CTA (NT == 1)
+}
+
 cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
-                          void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, cudaStream_t s) {
+                          void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, cudaStream_t s,
+                          const __half *lin_w_tc, float *plog) {
     if (B == 0 || T == 0) return cudaSuccess;
     const int64_t tiles = (B + RT_N - 1) / RT_N;
     // ping-pong (2 tiles per CTA) only pays once there are more tiles than SMs to run them one per CTA
@@ -809,25 +892,37 @@ cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w
     if (fuse) xin = RecX{fuse->feats, fuse->w_x, fuse->bias, fuse->F};
     cudaError_t e;
     unsigned long long *trace = nullptr;
-#define MDK_LAUNCH_REC_T(NTV, OT, FX, TR)                                                                    \
+#define MDK_LAUNCH_REC_T(NTV, OT, FX, TR, LG)                                                                \
     do {                                                                                                     \
-        auto kern = rec_tc_kernel<NTV, OT, FX, TR>;                                                          \
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RecCfg<NTV, FX>::total); \
+        auto kern = rec_tc_kernel<NTV, OT, FX, TR, LG>;                                                      \
+        constexpr int smem_bytes = RecCfg<NTV, FX, LG>::total;                                               \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);             \
         if (e != cudaSuccess) return e;                                                                      \
         dim3 grid((unsigned)((tiles + NTV - 1) / NTV), NDIR);                                                \
-        kern<<<grid, RT_THREADS, RecCfg<NTV, FX>::total, s>>>(gi, xin, w_hh_tm, b_hn, h_out, B, T, trace);   \
+        kern<<<grid, RT_THREADS, smem_bytes, s>>>(gi, xin, w_hh_tm, b_hn, h_out, B, T, trace, lin_w_tc, plog); \
     } while (0)
-#define MDK_LAUNCH_REC(NTV, OT, FX) MDK_LAUNCH_REC_T(NTV, OT, FX, false)
+#define MDK_LAUNCH_REC(NTV, OT, FX) MDK_LAUNCH_REC_T(NTV, OT, FX, false, false)
+    if (lin_w_tc) {
+        // layer 1 with the linear head fused in (partial logits instead of h1)
+        if (fuse || out_tiles || two || !plog) return cudaErrorInvalidValue;
+        if (g_rec_trace && T >= RT_TRACE_STEP0 + RT_TRACE_STEPS) {
+            trace = g_rec_trace + RT_TRACE_STEPS * RT_TRACE_SLOTS;
+            MDK_LAUNCH_REC_T(1, false, false, true, true);
+        } else {
+            MDK_LAUNCH_REC_T(1, false, false, false, true);
+        }
+        return cudaGetLastError();
+    }
     if (g_rec_trace && !two && T >= RT_TRACE_STEP0 + RT_TRACE_STEPS) {
         // diagnostics: the two shapes the engine uses at NT = 1 (fused layer 0 -> tiles, layer 1 -> fp32 rows)
         if (fuse && out_tiles) {
             trace = g_rec_trace;
-            MDK_LAUNCH_REC_T(1, true, true, true);
+            MDK_LAUNCH_REC_T(1, true, true, true, false);
             return cudaGetLastError();
         }
         if (!fuse && !out_tiles) {
             trace = g_rec_trace + RT_TRACE_STEPS * RT_TRACE_SLOTS;
-            MDK_LAUNCH_REC_T(1, false, false, true);
+            MDK_LAUNCH_REC_T(1, false, false, true, false);
             return cudaGetLastError();
         }
     }

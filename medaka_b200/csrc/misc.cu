@@ -531,6 +531,69 @@ cudaError_t launch_prepare_layer(const LayerWeights &lw, int in_features, bool b
     return cudaGetLastError();
 }
 
+// W_lin [5][256] -> per direction an M = 64 (rows >= 5 zero), K = 128 K-major shared-memory A operand image, fp16 hi/lo
+__global__ void pack_linear_kernel(const float *__restrict__ lin_w, __half *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // [dir 2][kg 16][row 64][8]
+    if (i >= NDIR * 16 * 64 * 8) return;
+    const int k8 = i & 7, row = (i >> 3) & 63, kg = (i >> 9) & 15, d = i >> 13;
+    const float v = row < NCLS ? lin_w[row * H2 + d * H + kg * 8 + k8] : 0.f;
+    __half hi, lo;
+    split_f16(v, hi, lo);
+    const int plane = 16 * 64 * 8;
+    out[(d * 2 + 0) * plane + (i & (plane - 1))] = hi;
+    out[(d * 2 + 1) * plane + (i & (plane - 1))] = lo;
+}
+
+cudaError_t launch_pack_linear(const float *lin_w, __half *lin_w_tc, cudaStream_t s) {
+    pack_linear_kernel<<<(NDIR * 16 * 64 * 8 + 255) / 256, 256, 0, s>>>(lin_w, lin_w_tc);
+    return cudaGetLastError();
+}
+
+// Head of the fused path (gru.py:53-55,67-71): logits = fwd partial + rev partial + bias, softmax, first-max argmax.
+// One thread per (window of the tile, time step); blockIdx.y = window tile.  41 B written per position, 40 B read.
+__global__ void __launch_bounds__(256) head_plog_kernel(const float *__restrict__ plog, const float *__restrict__ lin_b,
+                                                        int64_t B, int64_t T, int64_t n_ts, float *__restrict__ probs,
+                                                        float *__restrict__ logits, uint8_t *__restrict__ labels) {
+    const int64_t wt = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // t * 16 + w
+    const int64_t t = i >> 4;
+    const int w = (int)(i & 15);
+    if (t >= T) return;
+    const int64_t win = wt * WT + w;
+    const float *p0 = plog + (wt * T + t) * PLOG_TS_FLOATS + w;
+    const float *p1 = p0 + n_ts * PLOG_TS_FLOATS;
+    float lg[NCLS];
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) lg[c] = (ldg_stream(p0 + c * WT) + ldg_stream(p1 + c * WT)) + lin_b[c];
+    if (win >= B) return;                          // padding windows of a ragged last tile
+    float mx = lg[0];
+#pragma unroll
+    for (int c = 1; c < NCLS; ++c) mx = fmaxf(mx, lg[c]);
+    float e[NCLS], sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) { e[c] = expf(lg[c] - mx); sum += e[c]; }   // class order, like a sequential softmax
+    const int64_t p = win * T + t;
+    float best = -1.f;
+    int arg = 0;
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) {
+        const float pr = e[c] / sum;
+        probs[p * NCLS + c] = pr;
+        if (logits) logits[p * NCLS + c] = lg[c];
+        if (pr > best) { best = pr; arg = c; }     // first maximum wins (np.argmax, labels.py:1063)
+    }
+    if (labels) labels[p] = (uint8_t)arg;
+}
+
+cudaError_t launch_head_plog(const float *plog, const float *lin_b, int64_t B, int64_t T, float *probs, float *logits,
+                             uint8_t *labels, cudaStream_t s) {
+    if (B == 0 || T == 0) return cudaSuccess;
+    const int64_t tiles = (B + WT - 1) / WT;
+    dim3 grid((unsigned)((T * WT + 255) / 256), (unsigned)tiles);
+    head_plog_kernel<<<grid, 256, 0, s>>>(plog, lin_b, B, T, tiles * T, probs, logits, labels);
+    return cudaGetLastError();
+}
+
 // fp16 hi/lo activation tiles (tile-interleaved rows) -> fp32 [B*T][256] in position order (debug / layer-wise parity)
 __global__ void unpack_h0_kernel(const __half *__restrict__ tiles, float *__restrict__ out, int64_t B, int64_t T) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

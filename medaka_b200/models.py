@@ -303,6 +303,10 @@ class GRUModel(object):
     def launch_count(self):
         return int(_lm.lib.mdk_engine_launch_count(self._engine))
 
+    def keep_activations(self, keep=True):
+        """Debugging: keep the layer-1 output in HBM for ``read_activation(1)`` (runs the head as its own kernel)."""
+        _lm.check(_lm.lib.mdk_engine_keep_activations(self._engine, 1 if keep else 0))
+
     def preferred_batch_size(self):
         """Windows per batch that fill the device in one wave (1184 on a B200); ``batch_size="auto"`` in
         ``prediction.run_prediction`` / ``predict_regions`` resolves to this."""

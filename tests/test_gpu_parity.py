@@ -103,6 +103,7 @@ def test_layerwise_activations_match_oracle(precision):
     feats = synth.synth_features(37, 130, 10, seed=5)     # ragged: 37 windows (partial tiles), T not a multiple of 128
     man = gru_oracle.manual_forward(sd, feats)
     m = _make_model(sd, 10, precision)
+    m.keep_activations(True)        # the default tensor-core path fuses the head into layer 1 and never writes h1
     out = m.forward_arrays(feats, want_logits=True)
     h0 = m.read_activation(0)
     h1 = m.read_activation(1)
@@ -138,6 +139,26 @@ def test_forward_pingpong_path(B, T, F):
     flips, tie_flips, ties = label_parity(out.labels, ref_probs)
     print("NT=2 %dx%dx%d: scaled logit err %.3e, label mismatches %d (+%d among %d near-ties)" % (B, T, F, err, flips, tie_flips, ties))
     assert err <= LOGIT_TOL and flips == 0
+    m.close()
+
+
+def test_fused_and_unfused_head_agree():
+    """Default path (linear head as MMAs inside the layer-1 recurrence, partial logits) vs keep_activations (h1 to HBM,
+    separate head kernel): same logits up to summation order, same labels away from ties; read_activation(1) refuses on
+    the fused path."""
+    sd = synth.synth_state_dict(5)
+    feats = synth.synth_features(45, 257, 10, seed=77)
+    m = _make_model(sd, 10, "tc")
+    fused = m.forward_arrays(feats, want_logits=True, want_labels=True)
+    with pytest.raises(Exception):
+        m.read_activation(1)
+    m.keep_activations(True)
+    plain = m.forward_arrays(feats, want_logits=True, want_labels=True)
+    assert m.read_activation(1).shape == (45, 257, 256)
+    err = _scaled_err(fused.logits, plain.logits)
+    print("fused vs unfused head: scaled logit diff %.3e" % err)
+    assert err < 1e-5
+    assert label_parity(fused.labels, plain.probs)[0] == 0
     m.close()
 
 

@@ -43,6 +43,7 @@ def _forward(precision, B, T, seed=0, F=10):
     m = models.GRUModel(num_features=F)
     m.load_state_dict(sd)
     m.set_precision(precision)
+    m.keep_activations(True)
     t0 = time.time()
     out = m.forward_arrays(feats, want_logits=True)
     dt = time.time() - t0
@@ -103,6 +104,7 @@ def check_determinism(arg):
         m = models.GRUModel(num_features=10)
         m.load_state_dict(sd)
         m.set_precision(precision)
+        m.keep_activations(True)
         for call in range(2):
             out = m.forward_arrays(feats, want_logits=True)
             h0 = m.read_activation(0)
