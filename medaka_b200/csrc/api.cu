@@ -77,7 +77,7 @@ static int prepare_weights(mdk_engine *e) {
     }
     {
         int rc;
-        if (!e->lin_w_tc && (rc = dev_alloc(&e->lin_w_tc, (size_t)NDIR * 2 * 16 * 64 * 8))) return rc;
+        if (!e->lin_w_tc && (rc = dev_alloc(&e->lin_w_tc, (size_t)NDIR * 2 * 16 * 64 * 8 + (size_t)NDIR * H * H))) return rc;
         MDK_CUDA(launch_pack_linear(e->lin_w, e->lin_w_tc, e->stream));
         e->launches++;
     }

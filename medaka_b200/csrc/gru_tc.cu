@@ -167,7 +167,8 @@ struct RecCfg {
     static constexpr int wl_off = h2_off + (LOGITS ? ((NT * 2 * RT_HPLANE + 127) / 128) * 128 : 0);
     static constexpr int logbar_off = wl_off + (LOGITS ? 2 * WL_PLANE : 0);
     static constexpr uint32_t log_col = acc_col0 + NT * acc_per_tile;      // 16 accumulator columns of the logits MMAs
-    static_assert(!LOGITS || log_col + 16 <= 512, "TMEM budget");
+    static constexpr uint32_t wl_col = log_col + 16;                       // W_lin hi plane as a TMEM A operand (64 columns)
+    static_assert(!LOGITS || wl_col + H / 2 <= 512, "TMEM budget");
     static constexpr int end_ = logbar_off + 16;
     static constexpr int total = end_ > 120 * 1024 ? end_ : 120 * 1024;
     static_assert(total <= 227 * 1024, "smem budget");
@@ -277,6 +278,17 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
                 tmem_st_x8(t_w + (uint32_t)((pg * 8 + ks) * 8), v);
             }
+            if (LOGITS && pg == 0) {
+                // W_lin hi plane (rows >= 5 zero), row-major copy behind the two shared-memory images
+                const uint4 *sl = reinterpret_cast<const uint4 *>(lin_w_tc + (size_t)NDIR * 2 * (L::WL_PLANE / 2) +
+                                                                  ((size_t)dir * H + jrow) * H);
+#pragma unroll
+                for (int ks = 0; ks < H / 16; ++ks) {
+                    const uint4 lo4 = sl[2 * ks], hi4 = sl[2 * ks + 1];
+                    const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                    tmem_st_x8(t_w + L::wl_col + (uint32_t)(ks * 8), v);
+                }
+            }
             if (L::wx_tmem) {
                 const uint4 *sx = reinterpret_cast<const uint4 *>(xin.w_x + (((size_t)dir * 6 + pg) * H + jrow) * 16);
                 const uint4 lo4 = sx[0], hi4 = sx[1];
@@ -334,9 +346,15 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
                 const int pb = (prod == 1) ? 1 : 0;
 #pragma unroll
                 for (int ks = 0; ks < H / 16; ++ks) {
-                    const uint64_t ad = wl_desc0 + (uint64_t)((pa * L::WL_PLANE + ks * 2 * (64 * 16)) >> 4);
                     const uint64_t bd = b_cur + (uint64_t)((pb * RT_HPLANE + ks * 2 * RT_KG) >> 4);
-                    umma_f16(L::log_col, ad, bd, idesc64, (prod | ks) ? 1u : 0u);
+                    if (pa == 0) {
+                        // W_lin hi from tensor memory (M = 128, ~10 cycles, no shared-memory A traffic)
+                        umma_f16_ts(L::log_col, L::wl_col + (uint32_t)(ks * 8), bd, idesc, (prod | ks) ? 1u : 0u);
+                    } else {
+                        // W_lin lo from shared memory (M = 64: rows 0..4 land in the same TMEM lanes 0..4)
+                        const uint64_t ad = wl_desc0 + (uint64_t)((L::WL_PLANE + ks * 2 * (64 * 16)) >> 4);
+                        umma_f16(L::log_col, ad, bd, idesc64, 1u);
+                    }
                 }
             }
             umma_commit(log_bar);

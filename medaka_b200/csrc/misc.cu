@@ -542,6 +542,12 @@ __global__ void pack_linear_kernel(const float *__restrict__ lin_w, __half *__re
     const int plane = 16 * 64 * 8;
     out[(d * 2 + 0) * plane + (i & (plane - 1))] = hi;
     out[(d * 2 + 1) * plane + (i & (plane - 1))] = lo;
+    // second part of the buffer: the hi plane once more, row-major [dir][row 128][k 128] (rows >= 5 zero): source of the
+    // TMEM-resident A operand of the hi x hi and hi x lo products (M = 128, like W_hh)
+    __half *rm = out + NDIR * 2 * plane;
+    const int k = kg * 8 + k8;
+    rm[(d * H + row) * H + k] = hi;
+    rm[(d * H + row + 64) * H + k] = __float2half_rn(0.f);
 }
 
 cudaError_t launch_pack_linear(const float *lin_w, __half *lin_w_tc, cudaStream_t s) {
