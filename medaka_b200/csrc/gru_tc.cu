@@ -31,23 +31,6 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// r = sigmoid(a), z = sigmoid(b) with ONE reciprocal: 1/((1+e^-a)(1+e^-b)).  Exponents are clamped at 2^60 so the
-// product stays finite (sigmoid(-41.6) = 9e-19: the clamp changes nothing at fp32 resolution).  ~2 ulp.
-__device__ __forceinline__ void sigmoid2_fast(float a, float b, float &r, float &z) {
-    constexpr float kNegLog2e = -1.4426950408889634f;
-    const float ea = 1.0f + ex2_approx(fminf(a * kNegLog2e, 60.0f));
-    const float eb = 1.0f + ex2_approx(fminf(b * kNegLog2e, 60.0f));
-    const float inv = rcp_approx(ea * eb);
-    r = eb * inv;
-    z = ea * inv;
-}
-// tanh(x) = 1 - 2/(1+e^{2x}); absolute error ~1e-7, saturates cleanly at +-1
-__device__ __forceinline__ float tanh_fast(float x) {
-    constexpr float k2Log2e = 2.8853900817779268f;
-    const float e = ex2_approx(fminf(x * k2Log2e, 60.0f));
-    return fmaf(-2.0f, rcp_approx(1.0f + e), 1.0f);
-}
-
 // 1 / d for d = -nd >= 1 on the FMA pipe (packed pairs): integer seed (5 % error), one cubic step, one Newton step
 // -> 1.7e-8 relative.  The gate phase is bound by the MUFU (XU) pipe - ncu: mio_throttle is its top stall, XU 33 % of
 // the whole step while the FMA pipe sits at 13 % (profiles/r01e_*) - so the reciprocals that are on the critical path
@@ -79,11 +62,14 @@ __device__ __forceinline__ void phase_fence(F2 a, F2 b) {
 // Recurrent kernel.  One CTA = NT tiles of 16 windows of one direction, for the whole sequence.
 //   warps 0-15  : gate warps (TMEM -> registers -> gate math -> next h into smem + global output); warp w reads
 //                 TMEM lane quarter w%4 and the column group w/4
-//   warps 16-18 : MMA issuers, one per gate block r/z/n (warp 16 also owns the TMEM allocation)
-// NT == 2: gate-warp groups 0,1 own tile 0 and groups 2,3 tile 1 (8 windows per thread); the MMAs of one tile
-//          overlap the gate math of the other (ping-pong).
-// NT == 1: all four groups share tile 0 (4 windows per thread): used when there are too few windows to give
-//          every SM two tiles.
+//   warps 16-18 : service warps (warp 16 also owns the TMEM allocation)
+// NT == 1: all four gate-warp groups share tile 0 (4 windows per thread): used when there are too few windows to give
+//          every SM two tiles - the BASELINE 10 Mb workload.  Warp 16 = the MMA issuer (r, z, n in that order, one commit
+//          each, then - LOGITS - the linear head's MMAs), warp 17 = relay (sole waiter on the commit mbarriers, releases
+//          the gate warps through named barriers), warp 18 = aux (gi staging by bulk copy, L2 prefetch, bulk copy-out
+//          of the h tile).  See the issuer section for the protocol and DESIGN.md section 6 for where the cycles go.
+// NT == 2: gate-warp groups 0,1 own tile 0 and groups 2,3 tile 1 (8 windows per thread); warps 16-18 issue one gate
+//          block each; the MMAs of one tile overlap the gate math of the other (ping-pong).
 //
 // W_hh (fp16 hi+lo, 384 columns) lives in TENSOR MEMORY for the whole sequence and is the A operand of the
 // tcgen05.mma ".ts" form: with N = 16 an SS-mode MMA re-reads a 4 KiB A tile from shared memory for 8 cycles of
@@ -102,7 +88,7 @@ constexpr int RT_HPLANE = (H / 8) * RT_KG;               // one h plane (hi or l
 constexpr int RT_XPLANE = 2 * RT_KG;                     // one x plane (K = 16): 544 B
 constexpr int RT_XBUF = 2 * RT_XPLANE;                   // hi + lo
 constexpr int RT_GATE_WARPS = 16;                        // 4 per scheduler: the gate phase is latency-bound
-constexpr int RT_MMA_WARPS = 3;                          // one issuer per gate block (24 MMAs each per tile-step)
+constexpr int RT_MMA_WARPS = 3;                          // service warps: NT == 2 one issuer per gate block; NT == 1 issuer, relay, aux
 constexpr int RT_THREADS = 32 * (RT_GATE_WARPS + RT_MMA_WARPS);
 // Hand-off protocol.  MDK_REC_NB = 1 (default): the gate warps -> issuers hand-off ("h tile written") is a NAMED hardware
 // barrier (bar.arrive by the 16 gate warps, bar.sync by the issuers): the cycle trace (profiles/r01e) shows the issuers
@@ -645,9 +631,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         // running pointer to the feature value of step + 2 (loaded while step is in its epilogue)
         const float *xnext = (FUSE_X && xown) ? xsrc + (dir ? (T - 3) : 2) * (int64_t)xin.F : nullptr;
         const int64_t xadv = dir ? -(int64_t)xin.F : (int64_t)xin.F;
-        // h_{-1} = 0 (and x_0) are in smem: publish.  (Per-thread arrivals and all-lane polling are deliberate: electing
-        // one lane per warp for the barrier traffic measured 35 % SLOWER - the extra __syncwarp sits on the critical
-        // path while the mbarrier unit absorbs 512 arrivals without trouble.)
+        // h_{-1} = 0 (and x_0) are in smem: publish
         constexpr int HCOUNT = 32 * RT_GATE_WARPS / NT + 32 * RT_MMA_WARPS;
         fence_proxy_async_smem();
         tc_fence_before_sync();
