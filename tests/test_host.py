@@ -165,6 +165,46 @@ def test_datastore_roundtrip_and_resume():
             assert np.array_equal(ds.load_sample(s.name).label_probs, s.label_probs)
 
 
+class StubModel(object):
+    """The model seam without a GPU: records batch shapes, returns uniform probabilities; has the engine's async
+    interface (predict_async / .result()) and its one-wave batch size."""
+
+    def __init__(self, preferred):
+        self.preferred, self.shapes = preferred, []
+
+    def preferred_batch_size(self):
+        return self.preferred
+
+    def predict_async(self, batch):
+        shape = tuple(batch.counts_matrix.shape)
+        self.shapes.append(shape)
+
+        class Handle(object):
+            def result(_self):
+                return np.full(shape[:2] + (5,), 0.2, dtype=np.float32)
+        return Handle()
+
+
+def test_run_prediction_auto_batch_size_and_lookahead():
+    """run_prediction (medaka/prediction.py:14-81) with batch_size="auto": batches take the engine's one-wave size, every
+    window is written once, results come back through the one-batch look-ahead path."""
+    regions = [common.Region("ref", 0, 5000)] * 3
+    model = StubModel(preferred=7)
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "probs.npzstore")
+        rem = prediction.run_prediction(out, None, regions, model, FakeEncoder(), 500, 100, batch_size="auto",
+                                        bam_workers=2)
+        assert rem == []
+        n_windows = sum(s[0] for s in model.shapes)
+        assert all(s[0] <= 7 and s[1:] == (500, 10) for s in model.shapes)
+        assert sum(1 for s in model.shapes if s[0] == 7) >= len(model.shapes) - 1      # only the last batch is short
+        with datastore.DataStore(out, "r") as ds:
+            # identical regions give identical sample names: the store keeps each name once
+            assert ds.n_samples == n_windows // 3
+            name = sorted(ds.sample_registry)[0]
+            assert ds.load_sample(name).label_probs.shape == (500, 5)
+
+
 def test_model_archive_roundtrip():
     from oracle import synth
     sd = synth.synth_state_dict(1)
