@@ -44,6 +44,17 @@ def test_preferred_windows_is_one_wave():
     assert lib.mdk_engine_preferred_windows(lm.ffi.NULL) == 16 * 74
 
 
+def test_layout_helpers_host(tmp_path):
+    """tiled_row / gi_quad_index (the layouts every tensor-core kernel agrees on) are bijections with the block structure
+    the kernels rely on: host-only C++ property check compiled with nvcc."""
+    import __graft_entry__
+    exe = str(tmp_path / "layout_check")
+    src = os.path.join(ROOT, "tests", "native", "layout_check.cu")
+    subprocess.run([__graft_entry__._nvcc(), "-std=c++17", "-O1", "-o", exe, src], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
 def test_sass_contains_tcgen05_and_bulk_copy(built_lib):
     """The tensor-core kernels really are tcgen05 (UTCHMMA / LDTM) with TMA-engine bulk copies (UBLKCP)."""
     sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
