@@ -44,6 +44,11 @@ extern "C" {
 #define MDK_PREC_TC 0    /* tcgen05 tensor cores, fp16 hi/lo split operands (3 MMAs), fp32 accumulate */
 #define MDK_PREC_FP32 1  /* CUDA-core fp32 FFMA path: validation / --full_precision */
 
+/* which recurrent kernel the tensor-core path runs (mdk_engine_set_rec_mode) */
+#define MDK_REC_AUTO 0      /* ping-pong from half a wave of 16-window tiles up, else one tile per CTA */
+#define MDK_REC_ONE_TILE 1  /* rec_tc_kernel: one (two beyond a wave) 16-window tile per CTA */
+#define MDK_REC_PINGPONG 2  /* rec_pp_kernel: two tiles per CTA, their MMA and gate phases interleaved */
+
 /* count normalisation modes: CountsFeatureEncoder._norm_modes_ (medaka/features.py:816) */
 #define MDK_NORM_TOTAL 0
 #define MDK_NORM_FWD_REV 1
@@ -109,21 +114,39 @@ int mdk_engine_load_linear(mdk_engine *e, const float *w, const float *b);
 /* TorchModel.half() / --full_precision (medaka/prediction.py:164-168): MDK_PREC_* */
 int mdk_engine_set_precision(mdk_engine *e, int mode);
 int mdk_engine_get_precision(mdk_engine *e, int *mode);
-/* pre-size the device workspace for up to B windows of T columns (otherwise grown on demand) */
+/* fp16 products per tensor-core contraction, a bit set: 1 = W_hi.x_hi (required), 2 = W_hi.x_lo, 4 = W_lo.x_hi.
+ * 7 (default) reproduces fp32 to ~2e-6; the 2- and 1-product sets trade parity for tensor time - measured in
+ * profiles/precision_r02.md; they do NOT meet the labels-bit-exact bar and are never selected automatically. */
+int mdk_engine_set_products(mdk_engine *e, int mask);
+/* MDK_REC_*: recurrent-kernel selection (A/B measurements; AUTO is the default) */
+int mdk_engine_set_rec_mode(mdk_engine *e, int mode);
+/* pre-size the compute lanes (workspace + staging) for groups of up to B windows of T columns (otherwise grown on
+ * demand, to the size of the batch that opens a group - i.e. without a reserve call nothing is coalesced) */
 int mdk_engine_reserve(mdk_engine *e, int64_t B, int64_t T);
 /* predict_on_batch with HOST buffers: H2D feats, forward, D2H probs (+logits, +labels when
  * non-NULL); returns when outputs are in host memory. */
 int mdk_engine_forward(mdk_engine *e, const float *feats_host, int64_t B, int64_t T,
                        float *probs_host, float *logits_host, uint8_t *labels_host);
-/* asynchronous form of the same call: returns once the work is queued (copy-in, compute and copy-out run on
- * three streams chained by events, two I/O slots), so the H2D of batch k+1 and the D2H of batch k-1 overlap
- * the compute of batch k.  Host buffers must stay valid (and should be page-locked) until mdk_engine_wait
- * (ticket) returns.  At most 2 tickets are in flight; a third submit waits for the oldest. */
+/* asynchronous form of the same call: returns once the batch is queued.  Host buffers must stay valid (and should be
+ * page-locked) until mdk_engine_wait(ticket) returns.
+ * Batches are COALESCED: consecutive submits with the same T collect in a group (their features are copied to the
+ * device as they arrive, behind the previous group's compute) and the group runs as ONE forward over all of its
+ * windows - the reference's default batches (medaka/prediction.py:14, 100-200 windows) are a fraction of what fills a
+ * B200.  A group is launched when it is full (one wave of windows, mdk_engine_preferred_windows, or as far as the
+ * buffers sized by mdk_engine_reserve reach), when a batch with another T arrives, or when somebody waits for one of
+ * its tickets.  Groups alternate between two compute lanes (own stream, own workspace), so the layer-1 pass of one
+ * group shares the GPU with the layer-0 pass of the next; small forwards (<= 2^18 positions: the B = 1 remainder
+ * regions of prediction.py:196-209) rotate over 14 more lanes and run concurrently.  Results are identical to
+ * uncoalesced forwards: windows never interact. */
 int mdk_engine_submit(mdk_engine *e, const float *feats_host, int64_t B, int64_t T,
                       float *probs_host, float *logits_host, uint8_t *labels_host, int64_t *ticket);
 int mdk_engine_wait(mdk_engine *e, int64_t ticket);
-/* same forward with DEVICE buffers (inputs resident in HBM); asynchronous on the engine stream,
- * complete after mdk_engine_sync(). */
+/* launch the group that is still collecting batches (if any) without waiting for it */
+int mdk_engine_flush(mdk_engine *e);
+/* most windows coalesced into one group; 0 (default) = one wave, 1 = never coalesce */
+int mdk_engine_set_group_windows(mdk_engine *e, int64_t windows);
+/* same forward with DEVICE buffers (inputs resident in HBM); asynchronous on the next compute lane (consecutive calls
+ * alternate lanes and may overlap: give them distinct output buffers), complete after mdk_engine_sync(). */
 int mdk_engine_forward_dev(mdk_engine *e, const float *feats_dev, int64_t B, int64_t T,
                            float *probs_dev, float *logits_dev, uint8_t *labels_dev);
 int mdk_engine_sync(mdk_engine *e);

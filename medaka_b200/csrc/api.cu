@@ -86,94 +86,179 @@ static int prepare_weights(mdk_engine *e) {
     return MDK_OK;
 }
 
-static int ensure_workspace(mdk_engine *e, int64_t B, int64_t T) {
+static int ensure_workspace(mdk_engine *e, mdk_lane &ln, int64_t B, int64_t T) {
     // rows of the tile-interleaved intermediates (>= B*T: the last window tile is padded to 16 windows)
     const int64_t rows = tiled_rows(B, T);
     const int64_t need = ((rows + XT_ROWS - 1) / XT_ROWS) * XT_ROWS;
-    if (need <= e->cap_pos) return MDK_OK;
-    MDK_CUDA(cudaStreamSynchronize(e->stream));
-    dev_free(e->gi);
-    if (e->h0) { cudaFree(e->h0); e->h0 = nullptr; }
-    dev_free(e->h1);
-    dev_free(e->plog);
-    e->cap_pos = 0;
+    if (need <= ln.cap_pos) return MDK_OK;
+    MDK_CUDA(cudaStreamSynchronize(ln.stream));
+    dev_free(ln.gi);
+    if (ln.h0) { cudaFree(ln.h0); ln.h0 = nullptr; }
+    dev_free(ln.h1);
+    ln.cap_h1 = 0;
+    dev_free(ln.plog);
+    ln.cap_pos = 0;
     int rc;
-    if ((rc = dev_alloc(&e->gi, (size_t)need * GI_COLS))) return rc;
-    MDK_CUDA(cudaMalloc(&e->h0, (size_t)need * H2 * sizeof(float)));
-    if ((rc = dev_alloc(&e->h1, (size_t)need * H2))) return rc;
-    if ((rc = dev_alloc(&e->plog, (size_t)NDIR * (need / WT) * PLOG_TS_FLOATS))) return rc;
-    e->cap_pos = need;
+    if ((rc = dev_alloc(&ln.gi, (size_t)need * GI_COLS))) return rc;
+    MDK_CUDA(cudaMalloc(&ln.h0, (size_t)need * H2 * sizeof(float)));
+    if ((rc = dev_alloc(&ln.plog, (size_t)NDIR * (need / WT) * PLOG_TS_FLOATS))) return rc;
+    ln.cap_pos = need;
     return MDK_OK;
 }
 
-static int ensure_io(mdk_engine *e, int64_t B, int64_t T) {
+// h1 (the layer-1 output, 1 KiB / position) only exists on the unfused-head paths: allocated on first use
+static int ensure_h1(mdk_lane &ln) {
+    if (ln.cap_h1 >= ln.cap_pos && ln.h1) return MDK_OK;
+    MDK_CUDA(cudaStreamSynchronize(ln.stream));
+    dev_free(ln.h1);
+    ln.cap_h1 = 0;
+    int rc;
+    if ((rc = dev_alloc(&ln.h1, (size_t)ln.cap_pos * H2))) return rc;
+    ln.cap_h1 = ln.cap_pos;
+    return MDK_OK;
+}
+
+static int ensure_io(mdk_engine *e, mdk_lane &ln, int64_t B, int64_t T) {
     const int64_t P = B * T;
     const int64_t feats = P * e->desc.num_features;
-    if (P <= e->cap_io && feats <= e->cap_feats_floats) return MDK_OK;
-    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    if (P <= ln.cap_io && feats <= ln.cap_feats) return MDK_OK;
+    MDK_CUDA(cudaStreamSynchronize(ln.stream));
     MDK_CUDA(cudaStreamSynchronize(e->copy_in));
     MDK_CUDA(cudaStreamSynchronize(e->copy_out));
-    e->cap_io = 0; e->cap_feats_floats = 0;
-    for (auto &sl : e->io) {
-        dev_free(sl.d_feats); dev_free(sl.d_probs); dev_free(sl.d_logits); dev_free(sl.d_labels);
-        sl.busy = false;
-        int rc;
-        if ((rc = dev_alloc(&sl.d_feats, (size_t)feats))) return rc;
-        if ((rc = dev_alloc(&sl.d_probs, (size_t)P * NCLS))) return rc;
-        if ((rc = dev_alloc(&sl.d_logits, (size_t)P * NCLS))) return rc;
-        if ((rc = dev_alloc(&sl.d_labels, (size_t)P))) return rc;
-    }
-    e->cap_io = P; e->cap_feats_floats = feats;
+    ln.cap_io = 0; ln.cap_feats = 0;
+    dev_free(ln.d_feats); dev_free(ln.d_probs); dev_free(ln.d_logits); dev_free(ln.d_labels);
+    int rc;
+    if ((rc = dev_alloc(&ln.d_feats, (size_t)feats))) return rc;
+    if ((rc = dev_alloc(&ln.d_probs, (size_t)P * NCLS))) return rc;
+    if ((rc = dev_alloc(&ln.d_logits, (size_t)P * NCLS))) return rc;
+    if ((rc = dev_alloc(&ln.d_labels, (size_t)P))) return rc;
+    ln.cap_io = P; ln.cap_feats = feats;
     return MDK_OK;
 }
 
-// The forward pipeline on e->stream.  ev[1..6] bracket the stages for mdk_timings.
-static int run_forward(mdk_engine *e, const float *feats_dev, int64_t B, int64_t T, float *probs_dev,
+// Which recurrent kernel runs a batch of B windows (tensor-core path).  One tile per CTA (rec_tc_kernel, NT = 1) is a
+// single dependent chain per SM; two tiles per CTA (rec_pp_kernel) interleave two chains on one SM and need half as many
+// CTAs, so two groups on two lanes share the GPU.  AUTO: ping-pong from half a wave of tiles up.
+static bool use_pingpong(const mdk_engine *e, int64_t B) {
+    const int64_t tiles = (B + WT - 1) / WT;
+    if (e->rec_mode == MDK_REC_PINGPONG) return true;
+    if (e->rec_mode == MDK_REC_ONE_TILE) return false;
+    return tiles * NDIR > (int64_t)e->sm_count / 2;
+}
+
+// The forward pipeline on the lane's stream.  ev[1..6] bracket the stages for mdk_timings.
+static int run_forward(mdk_engine *e, mdk_lane &ln, const float *feats_dev, int64_t B, int64_t T, float *probs_dev,
                        float *logits_dev, uint8_t *labels_dev) {
     int rc;
     if ((rc = prepare_weights(e))) return rc;
-    if ((rc = ensure_workspace(e, B, T))) return rc;
+    if ((rc = ensure_workspace(e, ln, B, T))) return rc;
     const int64_t P = B * T;
-    cudaStream_t s = e->stream;
+    cudaStream_t s = ln.stream;
     const bool tc = e->precision == MDK_PREC_TC;
     int launches = 0;
     const bool fuse_x = tc && e->fuse_x && e->layer[0].w_x_tm != nullptr;
+    const bool pp = tc && use_pingpong(e, B);
+    // the linear head rides inside the layer-1 recurrence as extra MMAs (40 B/position of partial logits reach HBM
+    // instead of the 1 KiB/position h1 round trip): always on the ping-pong path, on the one-tile path when the batch
+    // is one tile per CTA
+    const bool fuse_head = tc && !e->keep_act && (pp || rec_tc_can_fuse_logits(B, e->sm_count));
+    if (!fuse_head && (rc = ensure_h1(ln))) return rc;
     MDK_CUDA(cudaEventRecord(e->ev[1], s));
     if (!fuse_x) {
-        MDK_CUDA(launch_inproj0(feats_dev, e->layer[0].w_in_packed, e->layer[0].bias_gi, e->gi, P,
+        MDK_CUDA(launch_inproj0(feats_dev, e->layer[0].w_in_packed, e->layer[0].bias_gi, ln.gi, P,
                                 e->desc.num_features, T, tc ? 1 : 0, s));
         launches++;
     }
     MDK_CUDA(cudaEventRecord(e->ev[2], s));
     if (tc) {
         const RecXArgs fx{feats_dev, e->layer[0].w_x_tm, e->layer[0].bias_gi_tc, e->desc.num_features};
-        MDK_CUDA(launch_rec_tc(e->gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn_tc, e->h0, 1, B, T,
-                               e->sm_count, s));
+        if (pp) MDK_CUDA(launch_rec_pp(0, ln.gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn_tc, ln.h0, B, T, s,
+                                       nullptr, nullptr, e->prod_mask));
+        else MDK_CUDA(launch_rec_tc(ln.gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn_tc, ln.h0, 1, B, T,
+                                    e->sm_count, s, nullptr, nullptr, e->prod_mask));
     } else {
-        MDK_CUDA(launch_rec_fp32(e->gi, e->layer[0].w_hh_t, e->layer[0].b_hn, (float *)e->h0, B, T, s));
+        MDK_CUDA(launch_rec_fp32(ln.gi, e->layer[0].w_hh_t, e->layer[0].b_hn, (float *)ln.h0, B, T, s));
     }
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[3], s));
-    if (tc) MDK_CUDA(launch_gemm_tc(e->h0, e->layer[1].w_in_tc, e->layer[1].bias_gi_tc, e->gi, tiled_rows(B, T), e->sm_count, s));
-    else MDK_CUDA(launch_gemm_fp32((const float *)e->h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, e->gi, P, s));
+    if (tc) MDK_CUDA(launch_gemm_tc(ln.h0, e->layer[1].w_in_tc, e->layer[1].bias_gi_tc, ln.gi, tiled_rows(B, T), e->sm_count, s,
+                                    e->prod_mask));
+    else MDK_CUDA(launch_gemm_fp32((const float *)ln.h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, ln.gi, P, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[4], s));
-    // one tile per CTA (the common case): the linear head rides inside the layer-1 recurrence as extra MMAs and only
-    // 40 B/position of partial logits reach HBM instead of the 1 KiB/position h1 round trip
-    const bool fuse_head = tc && !e->keep_act && rec_tc_can_fuse_logits(B, e->sm_count);
-    if (tc) MDK_CUDA(launch_rec_tc(e->gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, e->h1, 0, B, T, e->sm_count, s,
-                                   fuse_head ? e->lin_w_tc : nullptr, fuse_head ? e->plog : nullptr));
-    else MDK_CUDA(launch_rec_fp32(e->gi, e->layer[1].w_hh_t, e->layer[1].b_hn, e->h1, B, T, s));
+    if (tc) {
+        if (pp && fuse_head) MDK_CUDA(launch_rec_pp(1, ln.gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, nullptr, B, T, s,
+                                                    e->lin_w_tc, ln.plog, e->prod_mask));
+        else MDK_CUDA(launch_rec_tc(ln.gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, ln.h1, 0, B, T, e->sm_count, s,
+                                    fuse_head ? e->lin_w_tc : nullptr, fuse_head ? ln.plog : nullptr, e->prod_mask));
+    } else {
+        MDK_CUDA(launch_rec_fp32(ln.gi, e->layer[1].w_hh_t, e->layer[1].b_hn, ln.h1, B, T, s));
+    }
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[5], s));
-    if (fuse_head) MDK_CUDA(launch_head_plog(e->plog, e->lin_b, B, T, probs_dev, logits_dev, labels_dev, s));
-    else MDK_CUDA(launch_head(e->h1, e->lin_w, e->lin_b, B, T, tc ? 1 : 0, probs_dev, logits_dev, labels_dev, s));
-    e->last_fused_head = fuse_head;
+    if (fuse_head) MDK_CUDA(launch_head_plog(ln.plog, e->lin_b, B, T, probs_dev, logits_dev, labels_dev, s));
+    else MDK_CUDA(launch_head(ln.h1, e->lin_w, e->lin_b, B, T, tc ? 1 : 0, probs_dev, logits_dev, labels_dev, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[6], s));
     e->launches += launches;
     e->last.launches = launches;
-    e->last_B = B; e->last_T = T; e->last_precision = e->precision;
+    ln.last_fused_head = fuse_head;
+    ln.last_B = B; ln.last_T = T; ln.last_precision = e->precision;
+    e->last_lane = (int)(&ln - e->lane);
+    return MDK_OK;
+}
+
+// Next lane for a forward of P positions, round robin within its size class; the lane's previous group must have left
+// the device before its buffers are reused.
+static int acquire_lane(mdk_engine *e, int64_t P, int *out) {
+    int idx;
+    if (P > mdk_engine::SMALL_POS) {
+        idx = e->next_big;
+        e->next_big = (e->next_big + 1) % mdk_engine::BIG_LANES;
+    } else {
+        idx = mdk_engine::BIG_LANES + e->next_small;
+        e->next_small = (e->next_small + 1) % mdk_engine::SMALL_LANES;
+    }
+    mdk_lane &ln = e->lane[idx];
+    if (ln.busy) {
+        MDK_CUDA(cudaEventSynchronize(ln.ev_out));
+        ln.busy = false;
+    }
+    *out = idx;
+    return MDK_OK;
+}
+
+// Seal the open group: one forward over all of its windows, then the results back to each batch's host buffers.
+static int launch_group(mdk_engine *e) {
+    if (e->open_lane < 0) return MDK_OK;
+    mdk_lane &ln = e->lane[e->open_lane];
+    e->open_lane = -1;
+    ln.open = false;
+    if (ln.items.empty()) return MDK_OK;
+    int rc;
+    cudaStream_t s = ln.stream;
+    e->ev = e->evr[e->fwd_count % mdk_engine::EV_RING];
+    e->fwd_count++;
+    MDK_CUDA(cudaEventRecord(e->ev[0], s));
+    MDK_CUDA(cudaEventRecord(ln.ev_in, e->copy_in));      // every feature copy of the group was queued on copy_in
+    MDK_CUDA(cudaStreamWaitEvent(s, ln.ev_in, 0));
+    if ((rc = run_forward(e, ln, ln.d_feats, ln.gB, ln.gT, ln.d_probs, ln.want_logits ? ln.d_logits : nullptr,
+                          ln.want_labels ? ln.d_labels : nullptr)))
+        return rc;
+    MDK_CUDA(cudaEventRecord(ln.ev_done, s));
+    MDK_CUDA(cudaEventRecord(e->ev[7], s));
+    MDK_CUDA(cudaStreamWaitEvent(e->copy_out, ln.ev_done, 0));
+    int64_t w0 = 0;
+    for (const mdk_lane::Item &it : ln.items) {
+        const size_t P = (size_t)it.B * ln.gT, off = (size_t)w0 * ln.gT;
+        MDK_CUDA(cudaMemcpyAsync(it.probs, ln.d_probs + off * NCLS, P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, e->copy_out));
+        if (it.logits)
+            MDK_CUDA(cudaMemcpyAsync(it.logits, ln.d_logits + off * NCLS, P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, e->copy_out));
+        if (it.labels) MDK_CUDA(cudaMemcpyAsync(it.labels, ln.d_labels + off, P, cudaMemcpyDeviceToHost, e->copy_out));
+        w0 += it.B;
+    }
+    MDK_CUDA(cudaEventRecord(ln.ev_out, e->copy_out));
+    ln.busy = true;
     return MDK_OK;
 }
 
@@ -283,18 +368,25 @@ int mdk_engine_create(int device, const mdk_model_desc *desc, mdk_engine **out) 
     {
         const char *v = getenv("MDK_NO_FUSE_X");
         e->fuse_x = !(v && v[0] == '1');
+        v = getenv("MDK_REC_MODE");          // A/B measurements: "one" / "pp"
+        if (v && v[0] == 'o') e->rec_mode = MDK_REC_ONE_TILE;
+        else if (v && v[0] == 'p') e->rec_mode = MDK_REC_PINGPONG;
+        v = getenv("MDK_PRODUCTS");
+        if (v && v[0] >= '1' && v[0] <= '7') e->prod_mask = ((uint32_t)(v[0] - '0') & 7u) | 1u;
     }
-    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
-    if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
+    for (auto &ln : e->lane) {
+        cudaError_t err = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking);
+        if (err != cudaSuccess) { mdk_engine_destroy(e); return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
+        cudaEventCreateWithFlags(&ln.ev_in, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ln.ev_out, cudaEventDisableTiming);
+    }
+    e->stream = e->lane[0].stream;
     for (auto &set : e->evr) for (auto &ev : set) cudaEventCreate(&ev);
     cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
-    for (auto &sl : e->io) {
-        cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming);
-    }
     for (auto &ev : e->ev_timer) cudaEventCreate(&ev);
+    cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming);
     *out = e;
     return MDK_OK;
 }
@@ -302,7 +394,8 @@ int mdk_engine_create(int device, const mdk_model_desc *desc, mdk_engine **out) 
 int mdk_engine_destroy(mdk_engine *e) {
     if (!e) return MDK_OK;
     cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
+    for (auto &ln : e->lane) if (ln.stream) cudaStreamSynchronize(ln.stream);
+    if (e->copy_out) cudaStreamSynchronize(e->copy_out);
     for (int l = 0; l < 2; ++l) {
         LayerWeights &lw = e->layer[l];
         for (int d = 0; d < NDIR; ++d) { dev_free(lw.w_ih[d]); dev_free(lw.w_hh[d]); dev_free(lw.b_ih[d]); dev_free(lw.b_hh[d]); }
@@ -310,22 +403,31 @@ int mdk_engine_destroy(mdk_engine *e) {
         dev_free(lw.bias_gi_tc); dev_free(lw.b_hn_tc);
         dev_free(lw.w_hh_tm); dev_free(lw.w_x_tm); dev_free(lw.w_in_tc);
     }
-    dev_free(e->lin_w); dev_free(e->lin_b); dev_free(e->lin_w_tc); dev_free(e->plog);
-    dev_free(e->gi); dev_free(e->h1);
-    if (e->h0) cudaFree(e->h0);
-    for (auto &sl : e->io) {
-        dev_free(sl.d_feats); dev_free(sl.d_probs); dev_free(sl.d_logits); dev_free(sl.d_labels);
-        if (sl.ev_in) cudaEventDestroy(sl.ev_in);
-        if (sl.ev_done) cudaEventDestroy(sl.ev_done);
-        if (sl.ev_out) cudaEventDestroy(sl.ev_out);
+    dev_free(e->lin_w); dev_free(e->lin_b); dev_free(e->lin_w_tc);
+    for (auto &ln : e->lane) {
+        dev_free(ln.gi); dev_free(ln.h1); dev_free(ln.plog);
+        if (ln.h0) cudaFree(ln.h0);
+        dev_free(ln.d_feats); dev_free(ln.d_probs); dev_free(ln.d_logits); dev_free(ln.d_labels);
+        if (ln.ev_in) cudaEventDestroy(ln.ev_in);
+        if (ln.ev_done) cudaEventDestroy(ln.ev_done);
+        if (ln.ev_out) cudaEventDestroy(ln.ev_out);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
     }
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
     if (e->copy_out) cudaStreamDestroy(e->copy_out);
     for (auto &set : e->evr) for (auto &ev : set) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->ev_timer) if (ev) cudaEventDestroy(ev);
-    cudaStreamDestroy(e->stream);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
     delete e;
     cudaGetLastError();
+    return MDK_OK;
+}
+
+// weights are read by every lane: quiesce all of them before the packed copies are rebuilt
+static int quiesce(mdk_engine *e) {
+    int rc = launch_group(e);
+    if (rc) return rc;
+    for (auto &ln : e->lane) MDK_CUDA(cudaStreamSynchronize(ln.stream));
     return MDK_OK;
 }
 
@@ -335,7 +437,7 @@ int mdk_engine_load_gru(mdk_engine *e, int layer, int direction, const float *w_
     MDK_REQUIRE(layer >= 0 && layer < 2 && direction >= 0 && direction < 2, MDK_ERR_ARG, "load_gru: bad layer/direction");
     MDK_REQUIRE(w_ih && w_hh && b_ih && b_hh, MDK_ERR_ARG, "load_gru: NULL weight pointer");
     MDK_CUDA(cudaSetDevice(e->device));
-    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    { int rcq = quiesce(e); if (rcq) return rcq; }
     LayerWeights &lw = e->layer[layer];
     const int in = in_features(e, layer);
     int rc;
@@ -351,9 +453,10 @@ int mdk_engine_load_gru(mdk_engine *e, int layer, int direction, const float *w_
 int mdk_engine_load_linear(mdk_engine *e, const float *w, const float *b) {
     MDK_REQUIRE(e && w && b, MDK_ERR_ARG, "load_linear: NULL argument");
     MDK_CUDA(cudaSetDevice(e->device));
-    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    { int rcq = quiesce(e); if (rcq) return rcq; }
     int rc;
     if ((rc = upload(e->stream, &e->lin_w, w, (size_t)NCLS * H2))) return rc;
+    e->prepared = false;
     if ((rc = upload(e->stream, &e->lin_b, b, (size_t)NCLS))) return rc;
     e->lin_loaded = true;
     return MDK_OK;
@@ -371,12 +474,44 @@ int mdk_engine_get_precision(mdk_engine *e, int *mode) {
     return MDK_OK;
 }
 
+int mdk_engine_set_products(mdk_engine *e, int mask) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
+    MDK_REQUIRE(mask >= 1 && mask <= 7 && (mask & 1), MDK_ERR_ARG,
+                "set_products: mask is a bit set of {1: W_hi.x_hi (required), 2: W_hi.x_lo, 4: W_lo.x_hi}");
+    e->prod_mask = (uint32_t)mask;
+    return MDK_OK;
+}
+
+int mdk_engine_set_rec_mode(mdk_engine *e, int mode) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
+    MDK_REQUIRE(mode == MDK_REC_AUTO || mode == MDK_REC_ONE_TILE || mode == MDK_REC_PINGPONG, MDK_ERR_ARG,
+                "set_rec_mode: unknown mode");
+    e->rec_mode = mode;
+    return MDK_OK;
+}
+
+int mdk_engine_set_group_windows(mdk_engine *e, int64_t windows) {
+    MDK_REQUIRE(e && windows >= 0, MDK_ERR_ARG, "set_group_windows: bad arguments");
+    e->group_windows = windows;
+    return MDK_OK;
+}
+
+// Reserve = size the two big lanes (workspace + staging) for groups of up to B windows of T columns.  This is also what
+// switches coalescing on: a group collects submitted batches only as far as its lane's staging buffers reach.
 int mdk_engine_reserve(mdk_engine *e, int64_t B, int64_t T) {
     MDK_REQUIRE(e && B >= 1 && T >= 1, MDK_ERR_ARG, "reserve: bad arguments");
     MDK_CUDA(cudaSetDevice(e->device));
     int rc;
-    if ((rc = ensure_workspace(e, B, T))) return rc;
-    return ensure_io(e, B, T);
+    if ((rc = launch_group(e))) return rc;
+    const bool big = B * T > mdk_engine::SMALL_POS;
+    const int l0 = big ? 0 : mdk_engine::BIG_LANES, l1 = big ? mdk_engine::BIG_LANES : mdk_engine::N_LANES;
+    for (int i = l0; i < l1; ++i) {
+        mdk_lane &ln = e->lane[i];
+        if (ln.busy) { MDK_CUDA(cudaEventSynchronize(ln.ev_out)); ln.busy = false; }
+        if ((rc = ensure_workspace(e, ln, B, T))) return rc;
+        if ((rc = ensure_io(e, ln, B, T))) return rc;
+    }
+    return MDK_OK;
 }
 
 int mdk_engine_forward_dev(mdk_engine *e, const float *feats_dev, int64_t B, int64_t T, float *probs_dev,
@@ -384,11 +519,15 @@ int mdk_engine_forward_dev(mdk_engine *e, const float *feats_dev, int64_t B, int
     int rc;
     if ((rc = check_shapes(e, feats_dev, B, T, probs_dev))) return rc;
     MDK_CUDA(cudaSetDevice(e->device));
+    if ((rc = launch_group(e))) return rc;
+    int li;
+    if ((rc = acquire_lane(e, B * T, &li))) return rc;
+    mdk_lane &ln = e->lane[li];
     e->ev = e->evr[e->fwd_count % mdk_engine::EV_RING];
     e->fwd_count++;
-    MDK_CUDA(cudaEventRecord(e->ev[0], e->stream));
-    if ((rc = run_forward(e, feats_dev, B, T, probs_dev, logits_dev, labels_dev))) return rc;
-    MDK_CUDA(cudaEventRecord(e->ev[7], e->stream));
+    MDK_CUDA(cudaEventRecord(e->ev[0], ln.stream));
+    if ((rc = run_forward(e, ln, feats_dev, B, T, probs_dev, logits_dev, labels_dev))) return rc;
+    MDK_CUDA(cudaEventRecord(e->ev[7], ln.stream));
     return MDK_OK;
 }
 
@@ -398,48 +537,68 @@ int mdk_engine_submit(mdk_engine *e, const float *feats_host, int64_t B, int64_t
     if ((rc = check_shapes(e, feats_host, B, T, probs_host))) return rc;
     MDK_REQUIRE(ticket, MDK_ERR_ARG, "submit: ticket is NULL");
     MDK_CUDA(cudaSetDevice(e->device));
-    if ((rc = ensure_io(e, B, T))) return rc;
-    const int64_t P = B * T;
-    mdk_engine::IoSlot &sl = e->io[e->submit_count % mdk_engine::IO_SLOTS];
-    if (sl.busy) {   // the slot's previous result must have left the device before its buffers are reused
-        MDK_CUDA(cudaEventSynchronize(sl.ev_out));
-        sl.busy = false;
+    const int64_t gmax = e->group_windows > 0 ? e->group_windows : mdk_engine_preferred_windows(e);
+    // does the batch fit the group being collected?  (same window length, the lane's staging reaches, at most one wave)
+    if (e->open_lane >= 0) {
+        mdk_lane &ln = e->lane[e->open_lane];
+        const bool fits = T == ln.gT && ln.gB + B <= gmax && (ln.gB + B) * T <= ln.cap_io &&
+                          (ln.gB + B) * T * e->desc.num_features <= ln.cap_feats &&
+                          tiled_rows(ln.gB + B, T) <= ln.cap_pos;
+        if (!fits && (rc = launch_group(e))) return rc;
     }
-    cudaStream_t s = e->stream;
-    e->ev = e->evr[e->fwd_count % mdk_engine::EV_RING];
-    e->fwd_count++;
-    MDK_CUDA(cudaEventRecord(e->ev[0], s));
-    // copy-in stream: features H2D (asynchronous when feats_host is page-locked)
-    MDK_CUDA(cudaMemcpyAsync(sl.d_feats, feats_host, (size_t)P * e->desc.num_features * sizeof(float),
-                             cudaMemcpyHostToDevice, e->copy_in));
-    MDK_CUDA(cudaEventRecord(sl.ev_in, e->copy_in));
-    MDK_CUDA(cudaStreamWaitEvent(s, sl.ev_in, 0));
-    if ((rc = run_forward(e, sl.d_feats, B, T, sl.d_probs, logits_host ? sl.d_logits : nullptr,
-                          labels_host ? sl.d_labels : nullptr)))
-        return rc;
-    MDK_CUDA(cudaEventRecord(sl.ev_done, s));
-    MDK_CUDA(cudaEventRecord(e->ev[7], s));
-    // copy-out stream: results D2H
-    MDK_CUDA(cudaStreamWaitEvent(e->copy_out, sl.ev_done, 0));
-    MDK_CUDA(cudaMemcpyAsync(probs_host, sl.d_probs, (size_t)P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, e->copy_out));
-    if (logits_host)
-        MDK_CUDA(cudaMemcpyAsync(logits_host, sl.d_logits, (size_t)P * NCLS * sizeof(float), cudaMemcpyDeviceToHost, e->copy_out));
-    if (labels_host) MDK_CUDA(cudaMemcpyAsync(labels_host, sl.d_labels, (size_t)P, cudaMemcpyDeviceToHost, e->copy_out));
-    MDK_CUDA(cudaEventRecord(sl.ev_out, e->copy_out));
-    sl.busy = true;
-    *ticket = e->submit_count++;
+    if (e->open_lane < 0) {
+        int li;
+        if ((rc = acquire_lane(e, B * T, &li))) return rc;
+        mdk_lane &ln = e->lane[li];
+        if ((rc = ensure_io(e, ln, B, T))) return rc;
+        if ((rc = ensure_workspace(e, ln, B, T))) return rc;
+        ln.items.clear();
+        ln.gB = 0; ln.gT = T;
+        ln.want_logits = false; ln.want_labels = false;
+        ln.open = true;
+        ln.group++;
+        e->open_lane = li;
+    }
+    mdk_lane &ln = e->lane[e->open_lane];
+    // copy-in stream: features H2D (asynchronous when feats_host is page-locked), behind the group's earlier batches
+    MDK_CUDA(cudaMemcpyAsync(ln.d_feats + (size_t)ln.gB * T * e->desc.num_features, feats_host,
+                             (size_t)B * T * e->desc.num_features * sizeof(float), cudaMemcpyHostToDevice, e->copy_in));
+    ln.items.push_back(mdk_lane::Item{feats_host, probs_host, logits_host, labels_host, B});
+    ln.gB += B;
+    ln.want_logits = ln.want_logits || logits_host != nullptr;
+    ln.want_labels = ln.want_labels || labels_host != nullptr;
+    const int64_t tk = e->submit_count++;
+    e->ticket_lane[tk % mdk_engine::TICKET_RING] = (int16_t)e->open_lane;
+    e->ticket_group[tk % mdk_engine::TICKET_RING] = ln.group;
+    *ticket = tk;
+    // a group that cannot take another batch of this size is launched right away
+    if (ln.gB + B > gmax || (ln.gB + B) * T > ln.cap_io || tiled_rows(ln.gB + B, T) > ln.cap_pos) return launch_group(e);
     return MDK_OK;
+}
+
+int mdk_engine_flush(mdk_engine *e) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
+    MDK_CUDA(cudaSetDevice(e->device));
+    return launch_group(e);
 }
 
 int mdk_engine_wait(mdk_engine *e, int64_t ticket) {
     MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
     MDK_REQUIRE(ticket >= 0 && ticket < e->submit_count, MDK_ERR_ARG, "wait: unknown ticket");
-    if (ticket < e->submit_count - mdk_engine::IO_SLOTS)
-        return MDK_OK;   // older than the slots in flight: already waited on when its slot was reused
+    if (ticket < e->submit_count - mdk_engine::TICKET_RING) return MDK_OK;   // its lane has been reused many times since
     MDK_CUDA(cudaSetDevice(e->device));
-    mdk_engine::IoSlot &sl = e->io[ticket % mdk_engine::IO_SLOTS];
-    MDK_CUDA(cudaEventSynchronize(sl.ev_out));
-    sl.busy = false;
+    const int li = e->ticket_lane[ticket % mdk_engine::TICKET_RING];
+    const int64_t grp = e->ticket_group[ticket % mdk_engine::TICKET_RING];
+    mdk_lane &ln = e->lane[li];
+    if (ln.group != grp) return MDK_OK;        // a later group runs on the lane: this one was waited for when it was reused
+    if (ln.open) {
+        int rc = launch_group(e);              // still collecting: the caller wants the result now
+        if (rc) return rc;
+    }
+    if (ln.busy) {
+        MDK_CUDA(cudaEventSynchronize(ln.ev_out));
+        ln.busy = false;
+    }
     return MDK_OK;
 }
 
@@ -454,10 +613,12 @@ int mdk_engine_forward(mdk_engine *e, const float *feats_host, int64_t B, int64_
 int mdk_engine_sync(mdk_engine *e) {
     MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
     MDK_CUDA(cudaSetDevice(e->device));
+    int rc = launch_group(e);
+    if (rc) return rc;
     MDK_CUDA(cudaStreamSynchronize(e->copy_in));
-    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    for (auto &ln : e->lane) MDK_CUDA(cudaStreamSynchronize(ln.stream));
     MDK_CUDA(cudaStreamSynchronize(e->copy_out));
-    for (auto &sl : e->io) sl.busy = false;
+    for (auto &ln : e->lane) ln.busy = false;
     return MDK_OK;
 }
 
@@ -479,7 +640,7 @@ int mdk_engine_mean_timings(mdk_engine *e, int n_last, mdk_timings *out) {
     MDK_REQUIRE(n_last >= 1 && n_last <= mdk_engine::EV_RING, MDK_ERR_ARG, "mean_timings: n_last out of range");
     MDK_REQUIRE(e->fwd_count >= n_last, MDK_ERR_STATE, "mean_timings: fewer forwards recorded than requested");
     MDK_CUDA(cudaSetDevice(e->device));
-    MDK_CUDA(cudaStreamSynchronize(e->stream));
+    for (auto &ln : e->lane) MDK_CUDA(cudaStreamSynchronize(ln.stream));
     mdk_timings acc{};
     for (int i = 0; i < n_last; ++i) {
         mdk_timings t{};
@@ -496,18 +657,30 @@ int mdk_engine_mean_timings(mdk_engine *e, int n_last, mdk_timings *out) {
     return MDK_OK;
 }
 
+// The timed region spans every lane: the start event goes on lane 0 after all lanes have drained, the stop event on
+// lane 0 after it has been made to wait for every other lane and for the copy-out stream.
 int mdk_engine_timer_start(mdk_engine *e) {
     MDK_REQUIRE(e, MDK_ERR_ARG, "engine is NULL");
     MDK_CUDA(cudaSetDevice(e->device));
+    int rc = mdk_engine_sync(e);
+    if (rc) return rc;
     MDK_CUDA(cudaEventRecord(e->ev_timer[0], e->stream));
+    // work queued on the other lanes / copy streams after this point must not start before the start event
+    for (int i = 1; i < mdk_engine::N_LANES; ++i) MDK_CUDA(cudaStreamWaitEvent(e->lane[i].stream, e->ev_timer[0], 0));
+    MDK_CUDA(cudaStreamWaitEvent(e->copy_in, e->ev_timer[0], 0));
     return MDK_OK;
 }
 int mdk_engine_timer_stop(mdk_engine *e, float *elapsed_ms) {
     MDK_REQUIRE(e && elapsed_ms, MDK_ERR_ARG, "NULL argument");
     MDK_CUDA(cudaSetDevice(e->device));
-    // the end event must follow every copy-out still in flight, not just the compute stream
-    for (auto &sl : e->io)
-        if (sl.busy) MDK_CUDA(cudaStreamWaitEvent(e->stream, sl.ev_out, 0));
+    int rc = launch_group(e);
+    if (rc) return rc;
+    for (int i = 1; i < mdk_engine::N_LANES; ++i) {
+        MDK_CUDA(cudaEventRecord(e->ev_join, e->lane[i].stream));
+        MDK_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+    }
+    MDK_CUDA(cudaEventRecord(e->ev_join, e->copy_out));     // the end event must follow every copy-out still in flight
+    MDK_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     MDK_CUDA(cudaEventRecord(e->ev_timer[1], e->stream));
     MDK_CUDA(cudaEventSynchronize(e->ev_timer[1]));
     MDK_CUDA(cudaEventElapsedTime(elapsed_ms, e->ev_timer[0], e->ev_timer[1]));
@@ -517,23 +690,24 @@ int mdk_engine_timer_stop(mdk_engine *e, float *elapsed_ms) {
 int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_t n_floats) {
     MDK_REQUIRE(e && out_host, MDK_ERR_ARG, "NULL argument");
     MDK_REQUIRE(which == 0 || which == 1, MDK_ERR_ARG, "read_activation: which must be 0 or 1");
-    const int64_t P = e->last_B * e->last_T;
+    mdk_lane &ln = e->lane[e->last_lane];
+    const int64_t P = ln.last_B * ln.last_T;
     MDK_REQUIRE(P > 0 && n_floats == P * H2, MDK_ERR_ARG, "read_activation: size must be B*T*256 of the last forward");
-    MDK_REQUIRE(!(which == 1 && e->last_fused_head), MDK_ERR_STATE,
+    MDK_REQUIRE(!(which == 1 && ln.last_fused_head), MDK_ERR_STATE,
                 "read_activation(1): the last forward fused the head into layer 1 (h1 never reached HBM); call "
                 "mdk_engine_keep_activations(e, 1) before the forward");
     MDK_CUDA(cudaSetDevice(e->device));
-    MDK_CUDA(cudaStreamSynchronize(e->stream));
-    if (e->last_precision == MDK_PREC_FP32) {
-        MDK_CUDA(cudaMemcpy(out_host, which == 1 ? (const void *)e->h1 : (const void *)e->h0,
+    MDK_CUDA(cudaStreamSynchronize(ln.stream));
+    if (ln.last_precision == MDK_PREC_FP32) {
+        MDK_CUDA(cudaMemcpy(out_host, which == 1 ? (const void *)ln.h1 : (const void *)ln.h0,
                             (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
     } else {
         // tensor-core path: rows are tile-interleaved (and layer 0 is stored as fp16 hi/lo operand tiles)
         float *tmp = nullptr;
         MDK_CUDA(cudaMalloc(&tmp, (size_t)n_floats * sizeof(float)));
-        cudaError_t err = which == 0 ? launch_unpack_h0(e->h0, tmp, e->last_B, e->last_T, e->stream)
-                                     : launch_untile_rows(e->h1, tmp, e->last_B, e->last_T, e->stream);
-        if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+        cudaError_t err = which == 0 ? launch_unpack_h0(ln.h0, tmp, ln.last_B, ln.last_T, ln.stream)
+                                     : launch_untile_rows(ln.h1, tmp, ln.last_B, ln.last_T, ln.stream);
+        if (err == cudaSuccess) err = cudaStreamSynchronize(ln.stream);
         if (err == cudaSuccess) err = cudaMemcpy(out_host, tmp, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost);
         cudaFree(tmp);
         e->launches++;

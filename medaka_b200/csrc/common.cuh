@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../include/medaka_b200.h"
 
@@ -94,49 +95,80 @@ struct LayerWeights {
 
 }  // namespace mdk
 
+// One compute lane of the engine: a stream, the workspace of one forward and the device-side staging of one GROUP of
+// submitted batches.  Groups on different lanes run concurrently: the ping-pong recurrent kernels (gru_pp.cu) need only
+// half of the SMs for a 1184-window group, so the layer-1 pass of group k shares the GPU with the layer-0 pass of group
+// k+1; small forwards (the B = 1 remainder regions of medaka/prediction.py:196-209) spread over the small lanes.
+struct mdk_lane {
+    cudaStream_t stream = nullptr;
+    // workspace (tile-interleaved intermediates, see below)
+    int64_t cap_pos = 0;       // capacity in positions (rounded up to XT_ROWS)
+    float *gi = nullptr;       // [cap_pos][768]
+    void *h0 = nullptr;        // fp32 [cap_pos][256]  or  fp16 hi/lo tiles (same byte size)
+    float *h1 = nullptr;       // [cap_pos][256], allocated on first use (unfused head only)
+    int64_t cap_h1 = 0;
+    float *plog = nullptr;     // fused head: per-direction partial logits [dir][tile-step][class 5][16 windows]
+    // device staging of the group's host buffers
+    int64_t cap_io = 0;        // positions
+    int64_t cap_feats = 0;     // floats
+    float *d_feats = nullptr, *d_probs = nullptr, *d_logits = nullptr;
+    uint8_t *d_labels = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+    // the group being collected (open) or in flight (busy)
+    struct Item {
+        const float *feats;
+        float *probs, *logits;
+        uint8_t *labels;
+        int64_t B;
+    };
+    std::vector<Item> items;
+    int64_t gB = 0, gT = 0;
+    bool want_logits = false, want_labels = false;
+    bool open = false, busy = false;
+    int64_t group = -1;        // serial number of the lane's current (open / in-flight / last finished) group
+    // geometry of the last forward run on this lane (mdk_engine_read_activation)
+    int64_t last_B = 0, last_T = 0;
+    int last_precision = -1;
+    bool last_fused_head = false;
+};
+
 struct mdk_engine {
     int device = 0;
     mdk_model_desc desc{};
     int precision = MDK_PREC_TC;
     int sm_count = 148;
-    bool fuse_x = true;           // layer-0 input projection fused into rec_tc (F <= 16); MDK_NO_FUSE_X=1 disables
-    cudaStream_t stream = nullptr;
+    bool fuse_x = true;           // layer-0 input projection fused into the recurrence (F <= 16); MDK_NO_FUSE_X=1 disables
+    int rec_mode = MDK_REC_AUTO;  // which recurrent kernel the tensor-core path runs (MDK_REC_*)
+    uint32_t prod_mask = 7u;      // fp16 products per contraction (mdk_engine_set_products)
+    static constexpr int BIG_LANES = 2, SMALL_LANES = 14, N_LANES = BIG_LANES + SMALL_LANES;
+    static constexpr int64_t SMALL_POS = 1 << 18;   // forwards up to this many positions run on the small lanes
+    mdk_lane lane[N_LANES];
+    int next_big = 0, next_small = 0;
+    int open_lane = -1;           // lane whose group is still collecting batches (at most one), -1 = none
+    int last_lane = 0;            // lane of the most recent forward
+    int64_t group_windows = 0;    // most windows coalesced into one group (0 = one wave, mdk_engine_preferred_windows)
+    cudaStream_t stream = nullptr;       // == lane[0].stream: weight preparation, timers
     static constexpr int EV_RING = 32;   // per-forward event sets kept for mdk_engine_mean_timings
     cudaEvent_t evr[EV_RING][8] = {};
-    cudaEvent_t *ev = evr[0];            // event set of the forward in flight
+    cudaEvent_t *ev = evr[0];            // event set of the forward being queued
     int64_t fwd_count = 0;
     cudaEvent_t ev_timer[2] = {};
+    cudaEvent_t ev_join = nullptr;
     mdk::LayerWeights layer[2];
     float *lin_w = nullptr, *lin_b = nullptr;
     bool lin_loaded = false;
     __half *lin_w_tc = nullptr;   // [dir][hi/lo][k-group 16][row 64][8 halfs]: W_lin half of one direction as an M=64 smem A
                                   // operand (rows >= 5 zero) for the logits MMAs fused into the layer-1 recurrence
-    float *plog = nullptr;        // fused path: per-direction partial logits [dir][tile-step][class 5][16 windows]
     bool keep_act = false;        // debugging: keep h1 (layer-1 output) in HBM, i.e. run the unfused head
-    bool last_fused_head = false; // the last forward took the fused path (no h1)
     bool prepared = false;
-    // workspace
-    int64_t cap_pos = 0;       // capacity in positions (B*T, rounded up to XT_ROWS)
-    float *gi = nullptr;       // [cap_pos][768]
-    void *h0 = nullptr;        // fp32 [cap_pos][256]  or  fp16 hi/lo tiles (same byte size)
-    float *h1 = nullptr;       // [cap_pos][256]
-    // staging for the host-buffer API: two I/O slots so the H2D of call k+1 and the D2H of call k-1 overlap
-    // the compute of call k (copy-in / compute / copy-out streams chained by events)
-    static constexpr int IO_SLOTS = 2;
-    struct IoSlot {
-        float *d_feats = nullptr, *d_probs = nullptr, *d_logits = nullptr;
-        uint8_t *d_labels = nullptr;
-        cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
-        bool busy = false;
-    } io[IO_SLOTS];
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    // tickets: ticket -> (lane, group) for the last TICKET_RING submits; older ones have completed (their lane was reused)
+    static constexpr int TICKET_RING = 4096;
+    int16_t ticket_lane[TICKET_RING] = {};
+    int64_t ticket_group[TICKET_RING] = {};
     int64_t submit_count = 0;
-    int64_t cap_io = 0;
-    int64_t cap_feats_floats = 0;
     mdk_timings last{};
     int64_t launches = 0;
-    int64_t last_B = 0, last_T = 0;
-    int last_precision = -1;
 };
 
 namespace mdk {
@@ -176,14 +208,20 @@ cudaError_t rec_trace_control(int enable, unsigned long long *host_out);
 bool rec_tc_can_fuse_logits(int64_t B, int sm_count);
 cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
                           void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, cudaStream_t s,
-                          const __half *lin_w_tc = nullptr, float *plog = nullptr);
+                          const __half *lin_w_tc = nullptr, float *plog = nullptr, uint32_t prod_mask = 7u);
+// gru_pp.cu: two tiles per CTA (ping-pong).  layer 0: fused projection when `fuse` is given (F <= 16), else gi in; operand
+// tiles out.  layer 1: gi in, partial logits out (lin_w_tc, plog required).  prod_mask: fp16 products per contraction
+// (bit 0 W_hi.h_hi, bit 1 W_hi.h_lo, bit 2 W_lo.h_hi; 7 = fp32-faithful)
+cudaError_t launch_rec_pp(int layer, const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
+                          void *h_out, int64_t B, int64_t T, cudaStream_t s, const __half *lin_w_tc, float *plog,
+                          uint32_t prod_mask);
 // head on the partial logits of the fused path: sum of the two directions + bias -> softmax / argmax
 cudaError_t launch_head_plog(const float *plog, const float *lin_b, int64_t B, int64_t T, float *probs, float *logits,
                              uint8_t *labels, cudaStream_t s);
 cudaError_t launch_pack_linear(const float *lin_w, __half *lin_w_tc, cudaStream_t s);
 constexpr int PLOG_TS_FLOATS = NCLS * WT;     // 80 floats per (tile-step, direction)
 cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const float *bias, float *gi, int64_t P,
-                           int sm_count, cudaStream_t s);
+                           int sm_count, cudaStream_t s, uint32_t prod_mask = 7u);
 int selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant);
 // pileup.cu
 int pileup_counts_dev(int64_t n_rec, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,

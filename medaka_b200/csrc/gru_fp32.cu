@@ -116,12 +116,9 @@ cudaError_t launch_rec_fp32(const float *gi, const float *w_hh_t, const float *b
                             int64_t T, cudaStream_t s) {
     if (B == 0 || T == 0) return cudaSuccess;
     const size_t smem = (size_t)(H * G3 + 2 * REC_NB * H) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(rec_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // (the attribute is per device: set it on every launch, a process may drive several GPUs from several threads)
+    cudaError_t e = cudaFuncSetAttribute(rec_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     dim3 grid((unsigned)((B + REC_NB - 1) / REC_NB), NDIR);
     rec_fp32_kernel<<<grid, 128, smem, s>>>(gi, w_hh_t, b_hn, h_out, B, T);
     return cudaGetLastError();

@@ -17,46 +17,9 @@
 #include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
+#include "rec_common.cuh"
 
 namespace mdk {
-
-// ---- activations: ex2.approx / rcp.approx only (MUFU is the gate phase's binding pipe: 5 ops per element) ----
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// 1 / d for d = -nd >= 1 on the FMA pipe (packed pairs): integer seed (5 % error), one cubic step, one Newton step
-// -> 1.7e-8 relative.  The gate phase is bound by the MUFU (XU) pipe - ncu: mio_throttle is its top stall, XU 33 % of
-// the whole step while the FMA pipe sits at 13 % (profiles/r01e_*) - so the reciprocals that are on the critical path
-// are moved off it.  Takes -d because the callers get the negation for free from an FMA.
-__device__ __forceinline__ F2 rcp_neg_fma2(F2 nd, F2 one2) {
-    float a, b;
-    f2_get(nd, a, b);
-    F2 y = f2_make(__uint_as_float(0xFEF311C7u - __float_as_uint(a)), __uint_as_float(0xFEF311C7u - __float_as_uint(b)));
-    F2 e = f2_fma(nd, y, one2);          // 1 - d*y
-    y = f2_fma(y, f2_fma(e, e, e), y);   // y * (1 + e + e^2)
-    e = f2_fma(nd, y, one2);
-    return f2_fma(y, e, y);
-}
-
-// Phase fence for the gate warps.  ptxas is free to move register-only arithmetic across bar.sync, and it does: it
-// hoisted the z and n barriers above the sigmoid(r) math, so the warp sat in the z / n barrier with that math still
-// to do (ncu source view: 130 + 164 cycles of barrier stall per step inside the r phase).  A trap predicated on the
-// phase's results (never taken: the bit pattern is a NaN the arithmetic cannot produce) makes the barrier that follows
-// control-dependent on them.
-__device__ __forceinline__ void phase_fence(F2 a, F2 b) {
-    float a0, a1, b0, b1;
-    f2_get(a, a0, a1);
-    f2_get(b, b0, b1);
-    const uint32_t u = __float_as_uint(a0) & __float_as_uint(a1) & __float_as_uint(b0) & __float_as_uint(b1);
-    if (u == 0xFFFFFFFFu) __trap();
-}
 
 // =====================================================================================================
 // Recurrent kernel.  One CTA = NT tiles of 16 windows of one direction, for the whole sequence.
@@ -81,12 +44,6 @@ __device__ __forceinline__ void phase_fence(F2 a, F2 b) {
 // global loads.  The n gate needs W_in.x and W_hn.h apart, hence a 4th 16-column accumulator per tile.
 // TMEM budget: 384 (W_hh) [+ 48 (W_ih, NT == 1 only; NT == 2 reads it from smem in SS mode)] + NT x 48/64 <= 512.
 // =====================================================================================================
-constexpr int RT_N = 16;                                 // windows per tile (UMMA N)
-constexpr int RT_KG = RT_N * 16 + 16;                    // k-group stride of the h tile: 256 B of rows + 16 B pad, so the
-                                                         // 2-byte stores of 8-lane groups land in different banks
-constexpr int RT_HPLANE = (H / 8) * RT_KG;               // one h plane (hi or lo) of a tile: 4352 B
-constexpr int RT_XPLANE = 2 * RT_KG;                     // one x plane (K = 16): 544 B
-constexpr int RT_XBUF = 2 * RT_XPLANE;                   // hi + lo
 constexpr int RT_GATE_WARPS = 16;                        // 4 per scheduler: the gate phase is latency-bound
 constexpr int RT_MMA_WARPS = 3;                          // service warps: NT == 2 one issuer per gate block; NT == 1 issuer, relay, aux
 constexpr int RT_THREADS = 32 * (RT_GATE_WARPS + RT_MMA_WARPS);
@@ -111,8 +68,6 @@ constexpr int RT_BAR_H = 1;        // ids 1, 2: h tile of tile 0 / 1 written (ga
 constexpr int RT_BAR_R = 3;        // NT == 1: r / z / n accumulators complete (relay warp arrives, gate warps sync)
 constexpr int RT_BAR_Z = 4;
 constexpr int RT_BAR_N = 5;
-constexpr int RT_WT_COLS = 2 * 3 * (H / 2);              // W_hh hi+lo as TMEM A operand: 384 columns
-constexpr int RT_WX_COLS = 2 * 3 * 8;                    // W_ih (K = 16) hi+lo as TMEM A operand: 48 columns
 constexpr int RT_WX_BLOCK = H * 16 * 2;                  // one (part, gate) block of W_ih in smem: [kg 2][row 128][8] = 4 KiB
 
 template <int NT, bool FUSE_X, bool LOGITS = false>
@@ -160,18 +115,9 @@ struct RecCfg {
     static_assert(total <= 227 * 1024, "smem budget");
 };
 
-// arguments of the fused input projection (layer 0)
-struct RecX {
-    const float *feats;     // [B][T][F]
-    const __half *w_x;      // [dir][part][gate][row 128][16] fp16, K zero-padded to 16
-    const float *bias;      // [768]: r,z: b_ih + b_hh ; n: b_ih
-    int F;
-};
 
 // Diagnostics (TRACE instantiations only, selected by mdk_debug_rec_trace): CTA (0,0) stamps %clock64 at the hand-off
 // points of time steps [RT_TRACE_STEP0, +RT_TRACE_STEPS) into trace[step][slot]; slots are listed in tools/diag.py.
-constexpr int GI_PREFETCH_STEPS = 3;
-constexpr int X_PREFETCH_EVERY = 8, X_PREFETCH_AHEAD = 16;   // feature rows: 8 steps at a time, 16..23 steps ahead
 constexpr int RT_TRACE_STEP0 = 512, RT_TRACE_STEPS = 16, RT_TRACE_SLOTS = 40;
 #define REC_STAMP(slot)                                       \
     do {                                                      \
@@ -182,7 +128,8 @@ template <int NT, bool OUT_TILES, bool FUSE_X, bool TRACE = false, bool LOGITS =
 __global__ void __launch_bounds__(RT_THREADS, 1)
 rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__ w_hh,
               const float *__restrict__ b_hn, void *__restrict__ h_out, int64_t B, int64_t T,
-              unsigned long long *__restrict__ trace, const __half *__restrict__ lin_w_tc, float *__restrict__ plog) {
+              unsigned long long *__restrict__ trace, const __half *__restrict__ lin_w_tc, float *__restrict__ plog,
+              uint32_t prod_mask) {
     extern __shared__ __align__(128) uint8_t smem[];
     using L = RecCfg<NT, FUSE_X, LOGITS>;
     static_assert(!LOGITS || (NT == 1 && !FUSE_X && !OUT_TILES), "fused logits: layer 1, one tile per CTA");
@@ -312,6 +259,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         auto issue_h = [&](uint32_t d, int gate, int ks0, int ks1, int tile, bool fresh) {
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {
+                if (prod && !(prod_mask & (1u << prod))) continue;   // precision experiments: drop a correction product
                 const int pa = (prod == 2) ? 1 : 0;   // W part: hi, hi, lo
                 const int pb = (prod == 1) ? 1 : 0;   // activation part: hi, lo, hi
 #pragma unroll
@@ -328,6 +276,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         auto issue_logits = [&]() {
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {
+                if (prod && !(prod_mask & (1u << prod))) continue;
                 const int pa = (prod == 2) ? 1 : 0;
                 const int pb = (prod == 1) ? 1 : 0;
 #pragma unroll
@@ -366,6 +315,7 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         auto issue_x = [&](uint32_t d, int gate, int tile, uint32_t par, bool fresh) {
 #pragma unroll
             for (int prod = 0; prod < 3; ++prod) {
+                if (prod && !(prod_mask & (1u << prod))) continue;
                 const int pa = (prod == 2) ? 1 : 0;
                 const int pb = (prod == 1) ? 1 : 0;
                 const uint64_t xd = x_desc0 + (uint64_t)(((tile * 2 + (int)par) * RT_XBUF + pb * RT_XPLANE) >> 4);
@@ -608,7 +558,6 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
         int64_t orow = row0 + t_first * WT;                    // OUT_TILES: row -> (tile, row in tile)
         __half *o16 = reinterpret_cast<__half *>(h_out) + (int64_t)(kcol >> 3) * (XT_ROWS * 8) + (kcol & 7);
 
-        constexpr float EXP_CLAMP = 60.0f;
         const F2 one2 = f2_make(1.0f, 1.0f), negone2 = f2_make(-1.0f, -1.0f);
         F2 hprev2[NP];
 #pragma unroll
@@ -860,6 +809,8 @@ rec_tc_kernel(const float *__restrict__ gi, RecX xin, const __half *__restrict__
 
 static unsigned long long *g_rec_trace = nullptr;   // device buffer [2 layers][steps][slots]; null = tracing off
 
+unsigned long long *rec_trace_buffer() { return g_rec_trace; }
+
 cudaError_t rec_trace_control(int enable, unsigned long long *host_out) {
     const size_t bytes = 2 * RT_TRACE_STEPS * RT_TRACE_SLOTS * sizeof(unsigned long long);
     if (host_out && g_rec_trace) {
@@ -885,8 +836,9 @@ bool rec_tc_can_fuse_logits(int64_t B, int sm_count) {
 
 cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
                           void *h_out, int out_tiles, int64_t B, int64_t T, int sm_count, cudaStream_t s,
-                          const __half *lin_w_tc, float *plog) {
+                          const __half *lin_w_tc, float *plog, uint32_t prod_mask) {
     if (B == 0 || T == 0) return cudaSuccess;
+    prod_mask = (prod_mask & 7u) | 1u;
     const int64_t tiles = (B + RT_N - 1) / RT_N;
     // ping-pong (2 tiles per CTA) only pays once there are more tiles than SMs to run them one per CTA
     const bool two = tiles * NDIR > (int64_t)sm_count;
@@ -901,7 +853,7 @@ cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);             \
         if (e != cudaSuccess) return e;                                                                      \
         dim3 grid((unsigned)((tiles + NTV - 1) / NTV), NDIR);                                                \
-        kern<<<grid, RT_THREADS, smem_bytes, s>>>(gi, xin, w_hh_tm, b_hn, h_out, B, T, trace, lin_w_tc, plog); \
+        kern<<<grid, RT_THREADS, smem_bytes, s>>>(gi, xin, w_hh_tm, b_hn, h_out, B, T, trace, lin_w_tc, plog, prod_mask); \
     } while (0)
 #define MDK_LAUNCH_REC(NTV, OT, FX) MDK_LAUNCH_REC_T(NTV, OT, FX, false, false)
     if (lin_w_tc) {
@@ -966,7 +918,7 @@ constexpr uint32_t GT_W_COLS = 2 * (H2 / 2);                    // weight block 
 // per 64 cycles = the entire 128 B/clk, leaving nothing for the bulk-copy writes) and doubles the pipeline depth.
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w_in_tm,
-               const float *__restrict__ bias, float *__restrict__ gi, int64_t P, int64_t ntiles) {
+               const float *__restrict__ bias, float *__restrict__ gi, int64_t P, int64_t ntiles, uint32_t prod_mask) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + GT_BAR_OFF);
     uint64_t *empty = full + GT_STAGES;
@@ -1059,6 +1011,7 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
                     const uint64_t b_s = b_desc0 + (uint64_t)((stage * GT_STAGE_BYTES) >> 4);
 #pragma unroll
                     for (int prod = 0; prod < 3; ++prod) {
+                        if (prod && !(prod_mask & (1u << prod))) continue;
                         const int pa = (prod == 2) ? 1 : 0;   // W part
                         const int pb = (prod == 1) ? 1 : 0;   // x part
 #pragma unroll
@@ -1116,21 +1069,18 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
 }
 
 cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const float *bias, float *gi, int64_t P,
-                           int sm_count, cudaStream_t s) {
+                           int sm_count, cudaStream_t s, uint32_t prod_mask) {
     if (P == 0) return cudaSuccess;
     const int64_t ntiles = (P + XT_ROWS - 1) / XT_ROWS;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // (the attribute is per device: set it on every launch, a process may drive several GPUs)
+    cudaError_t ea = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
+    if (ea != cudaSuccess) return ea;
     int64_t ct = sm_count / 6;
     if (ct < 1) ct = 1;
     if (ct > ntiles) ct = ntiles;
     dim3 grid(6, (unsigned)ct);
     gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, s>>>(reinterpret_cast<const uint8_t *>(x_tiles), w_in_tm, bias, gi,
-                                                     P, ntiles);
+                                                     P, ntiles, (prod_mask & 7u) | 1u);
     return cudaGetLastError();
 }
 

@@ -239,16 +239,18 @@ class GRUModel(object):
     def wait(self, ticket):
         _lm.check(_lm.lib.mdk_engine_wait(self._engine, ticket))
 
-    def predict_async(self, batch):
+    def predict_async(self, batch, slots=2):
         """Asynchronous predict_on_batch: returns a handle whose ``result()`` is the CPU tensor [B,T,5].
 
-        Two calls may be in flight; ``run_prediction`` uses this with a one-batch look-ahead so the PCIe copies of
-        neighbouring batches hide under the compute of the current one.
+        Up to ``slots`` calls may be in flight (each owns one set of page-locked staging arrays).  The engine
+        coalesces consecutive batches of the same window length into one device forward (mdk_engine_submit), so
+        ``run_prediction`` keeps about two device waves of batches queued: the reference's default 200-window batches
+        then run as ~1000-window groups on alternating compute lanes, with the PCIe copies under the compute.
         """
         import torch
         x = _as_f32(self.get_model_input_features(batch))
         B, T, F = x.shape
-        slot = getattr(self, "_async_n", 0) % 2
+        slot = getattr(self, "_async_n", 0) % max(int(slots), 1)
         self._async_n = getattr(self, "_async_n", 0) + 1
         xin = self.pinned("afeats%d" % slot, (B, T, F), np.float32)
         np.copyto(xin, x)
@@ -261,9 +263,36 @@ class GRUModel(object):
             def result(self_inner):
                 model.wait(ticket)
                 model.last_labels = labels.copy()
+                self_inner.labels = model.last_labels
                 return torch.from_numpy(probs.copy())
 
         return _Handle()
+
+    def lookahead(self, batch_size, window_len=None):
+        """How many ``predict_async`` calls of ``batch_size`` windows to keep in flight (two coalesced groups)."""
+        pref = self.preferred_batch_size()
+        if window_len is not None and batch_size * window_len <= (1 << 18):
+            return 14                                   # small forwards rotate over the engine's small lanes
+        return int(max(2, min(64, 2 * ((pref + batch_size - 1) // max(batch_size, 1)) + 1)))
+
+    def reserve(self, windows, window_len):
+        """Size the engine's compute lanes for coalesced groups of up to ``windows`` windows (mdk_engine_reserve)."""
+        _lm.check(_lm.lib.mdk_engine_reserve(self._engine, int(windows), int(window_len)))
+
+    def flush(self):
+        _lm.check(_lm.lib.mdk_engine_flush(self._engine))
+
+    def set_products(self, mask):
+        """fp16 products per contraction (precision experiments; 7 = fp32-faithful default)."""
+        _lm.check(_lm.lib.mdk_engine_set_products(self._engine, int(mask)))
+
+    def set_rec_mode(self, mode):
+        """'auto' | 'one' | 'pp': recurrent-kernel selection (mdk_engine_set_rec_mode)."""
+        code = {"auto": _lm.lib.MDK_REC_AUTO, "one": _lm.lib.MDK_REC_ONE_TILE, "pp": _lm.lib.MDK_REC_PINGPONG}[mode]
+        _lm.check(_lm.lib.mdk_engine_set_rec_mode(self._engine, code))
+
+    def set_group_windows(self, windows):
+        _lm.check(_lm.lib.mdk_engine_set_group_windows(self._engine, int(windows)))
 
     def forward(self, x):
         """gru.py:58-72 on host tensors: returns probabilities (or logits if normalise is off)."""

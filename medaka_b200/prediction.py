@@ -9,6 +9,7 @@ the GPUs of a box, one process per GPU, each writing its own output store.
 The body of the loop - ``model.predict_on_batch(batch)`` - is the engine call; everything in
 this file is scheduling.
 """
+import collections
 import queue
 import threading
 from timeit import default_timer as now
@@ -138,28 +139,45 @@ def run_prediction(output, bam, regions, model, feature_encoder, chunk_len, chun
     logger.info("Running inference for {:.1f}M draft bases.".format(total_region_mbases))
     n_batches, n_positions = 0, 0
     t0 = now()
-    def _store(ds, data, batch, class_probs):
-        for sample, prob, feat in zip(data, class_probs, batch.features):
+    def _store(ds, data, batch, class_probs, labels=None):
+        # label_probs as the reference stores them, plus the engine's argmax labels (uint8 [T]) in the Sample's
+        # `labels` field: `medaka sequence` / `medaka vcf` read label_probs and ignore it, the GPU stitch / variant
+        # decode of this package can skip the argmax (decode seam)
+        for i, (sample, prob, feat) in enumerate(zip(data, class_probs, batch.features)):
             feats = feat if save_features else None
-            ds.write_sample(sample.amend(label_probs=prob, features=feats))
+            extra = {} if labels is None else {"labels": labels[i]}
+            ds.write_sample(sample.amend(label_probs=prob, features=feats, **extra))
 
     with datastore.DataStore(output, 'a') as ds:
-        # one-batch look-ahead: batch k+1 is queued on the engine (copy-in + compute) before the results of
-        # batch k are collected, so PCIe traffic and the HDF writer overlap the GPU work
-        pending = None
+        # look-ahead: enough batches are queued on the engine for it to coalesce them into device-filling groups
+        # and to keep a second group's copies and compute under the first (mdk_engine_submit); results are collected
+        # in order, so PCIe traffic and the store's writer thread overlap the GPU work
+        pending = collections.deque()
         use_async = hasattr(model, "predict_async")
+        depth = None
+
+        def _collect():
+            data0, batch0, handle = pending.popleft()
+            probs = handle.result()
+            _store(ds, data0, batch0, probs, getattr(handle, "labels", None))
+
         for data, batch in loader:
             n_batches += 1
             n_positions += int(batch.features.shape[0]) * int(batch.features.shape[1])
             if not use_async:
-                _store(ds, data, batch, model.predict_on_batch(batch))
+                _store(ds, data, batch, model.predict_on_batch(batch), getattr(model, "last_labels", None))
                 continue
-            handle = model.predict_async(batch)
-            if pending is not None:
-                _store(ds, pending[0], pending[1], pending[2].result())
-            pending = (data, batch, handle)
-        if pending is not None:
-            _store(ds, pending[0], pending[1], pending[2].result())
+            if depth is None:
+                nb, nt = int(batch.features.shape[0]), int(batch.features.shape[1])
+                depth = model.lookahead(batch_size, nt) if hasattr(model, "lookahead") else 2
+                if hasattr(model, "reserve") and enable_chunking and nb * nt > (1 << 18):
+                    # coalescing needs the lanes sized for a whole group up front
+                    model.reserve(max(model.preferred_batch_size(), nb), nt)
+            while len(pending) >= depth:
+                _collect()
+            pending.append((data, batch, model.predict_async(batch, slots=depth + 1)))
+        while pending:
+            _collect()
     dt = max(now() - t0, 1e-9)
     logger.info("Processed {} batches, {} positions in {:.2f}s ({:.3e} positions/s)".format(
         n_batches, n_positions, dt, n_positions / dt))

@@ -169,25 +169,39 @@ class StubModel(object):
     """The model seam without a GPU: records batch shapes, returns uniform probabilities; has the engine's async
     interface (predict_async / .result()) and its one-wave batch size."""
 
-    def __init__(self, preferred):
-        self.preferred, self.shapes = preferred, []
+    def __init__(self, preferred, depth=3):
+        self.preferred, self.shapes, self.depth = preferred, [], depth
+        self.in_flight, self.max_in_flight, self.reserved = 0, 0, []
 
     def preferred_batch_size(self):
         return self.preferred
 
-    def predict_async(self, batch):
+    def lookahead(self, batch_size, window_len=None):
+        return self.depth
+
+    def reserve(self, windows, window_len):
+        self.reserved.append((windows, window_len))
+
+    def predict_async(self, batch, slots=2):
         shape = tuple(batch.counts_matrix.shape)
         self.shapes.append(shape)
+        assert slots > self.depth            # one staging slot per call in flight, plus the one being queued
+        self.in_flight += 1
+        self.max_in_flight = max(self.max_in_flight, self.in_flight)
+        model = self
 
         class Handle(object):
             def result(_self):
+                model.in_flight -= 1
+                _self.labels = np.full(shape[:2], 3, dtype=np.uint8)
                 return np.full(shape[:2] + (5,), 0.2, dtype=np.float32)
         return Handle()
 
 
 def test_run_prediction_auto_batch_size_and_lookahead():
     """run_prediction (medaka/prediction.py:14-81) with batch_size="auto": batches take the engine's one-wave size, every
-    window is written once, results come back through the one-batch look-ahead path."""
+    window is written once, results come back in order through the look-ahead queue (at most `depth` batches in flight),
+    and the engine's argmax labels are stored next to label_probs."""
     regions = [common.Region("ref", 0, 5000)] * 3
     model = StubModel(preferred=7)
     with tempfile.TemporaryDirectory() as d:
@@ -202,7 +216,10 @@ def test_run_prediction_auto_batch_size_and_lookahead():
             # identical regions give identical sample names: the store keeps each name once
             assert ds.n_samples == n_windows // 3
             name = sorted(ds.sample_registry)[0]
-            assert ds.load_sample(name).label_probs.shape == (500, 5)
+            smp = ds.load_sample(name)
+            assert smp.label_probs.shape == (500, 5)
+            assert smp.labels.shape == (500,) and smp.labels.dtype == np.uint8 and int(smp.labels[0]) == 3
+        assert 1 <= model.max_in_flight <= model.depth and model.in_flight == 0
 
 
 def test_model_archive_roundtrip():

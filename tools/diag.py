@@ -166,7 +166,100 @@ def check_rec_trace(arg):
     return res
 
 
-CHECKS = {"selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism,
+PP_SLOTS = ["issuer: H seen", "issuer: r queued", "issuer: z queued", "issuer: n queued", "relay: r arrived",
+            "relay: z arrived", "relay: n arrived", "gate: r ld done", "gate: r math done", "gate: z ld done",
+            "gate: z math done", "gate: n ld done", "gate: h written", "gate: arrived H", "issuer: logits queued"]
+
+
+def check_pp(arg):
+    """Ping-pong recurrent kernel (gru_pp.cu) against the oracle: 'B,T,F[,mode]'."""
+    from medaka_b200 import models
+    from oracle import gru_oracle, synth
+    parts = arg.split(",")
+    B, T, F = int(parts[0]), int(parts[1]), int(parts[2])
+    mode = parts[3] if len(parts) > 3 else "pp"
+    sd = synth.synth_state_dict(7, num_features=F)
+    feats = synth.synth_features(B, T, F, seed=B * 3 + T)
+    ref_probs, ref_logits = gru_oracle.predict_on_batch(gru_oracle.build(sd, num_features=F), feats)
+    m = models.GRUModel(num_features=F)
+    m.load_state_dict(sd)
+    m.set_rec_mode(mode)
+    out = m.forward_arrays(feats, want_logits=True)
+    res = {"finite": bool(np.isfinite(out.logits).all())}
+    scale = np.abs(ref_logits).max(-1, keepdims=True)
+    err = np.abs(out.logits - ref_logits) / scale
+    res["dlogit_scaled"] = float(np.nanmax(err))
+    res["label_mismatch"] = int((out.labels != np.argmax(ref_probs, -1)).sum())
+    res["n"] = int(out.labels.size)
+    bad = np.argwhere(~(err.max(-1) < 1e-3))
+    res["n_bad_pos"] = int(len(bad))
+    res["bad_windows"] = sorted(set(bad[:, 0].tolist()))[:20]
+    res["bad_t_first"] = sorted(set(bad[:, 1].tolist()))[:10]
+    if T * B <= 400000:
+        man = gru_oracle.manual_forward(sd, feats)
+        h0 = m.read_activation(0)
+        d = np.abs(h0 - man["h0"])
+        res["dh0_fwd"] = float(d[..., :128].max())
+        res["dh0_rev"] = float(d[..., 128:].max())
+        res["dh0_bad_windows"] = sorted(set(np.argwhere(d.max(-1) > 1e-4)[:, 0].tolist()))[:20]
+    res["timings"] = m.last_timings()
+    m.close()
+    return res
+
+
+def check_rec_timing(arg):
+    """'mode,B,T[,reps]' -> mean stage times of forward_dev-style forwards (host buffers, one at a time)."""
+    from medaka_b200 import models
+    from oracle import synth
+    parts = arg.split(",")
+    mode, B, T = parts[0], int(parts[1]), int(parts[2])
+    reps = int(parts[3]) if len(parts) > 3 else 3
+    m = models.GRUModel()
+    m.load_state_dict(synth.synth_state_dict(0))
+    m.set_rec_mode(mode)
+    feats = synth.synth_features_fast(B, T, 10, seed=3)
+    m.forward_arrays(feats)
+    ts = []
+    for _ in range(reps):
+        m.forward_arrays(feats)
+        ts.append(m.last_timings())
+    m.close()
+    return {k: float(np.mean([t[k] for t in ts])) for k in ts[0]}
+
+
+def check_pp_trace(arg):
+    """Cycle stamps of the ping-pong kernel's hand-off points on CTA (0,0), steps 512..527: 'B,T'."""
+    from medaka_b200 import libmedaka as lm, models
+    from oracle import synth
+    B, T = (int(x) for x in arg.split(","))
+    lib, ffi = lm.load(), lm.ffi
+    m = models.GRUModel()
+    m.load_state_dict(synth.synth_state_dict(0))
+    m.set_rec_mode("pp")
+    feats = synth.synth_features_fast(B, T, 10, seed=3)
+    m.forward_arrays(feats)
+    base = m.last_timings()
+    lm.check(lib.mdk_debug_rec_trace(0, 1, ffi.NULL))
+    m.forward_arrays(feats)
+    traced = m.last_timings()
+    buf = np.zeros((2, 16, 40), dtype=np.uint64)
+    lm.check(lib.mdk_debug_rec_trace(0, 0, ffi.cast("uint64_t *", ffi.from_buffer(buf))))
+    res = {"untraced_ms": base, "traced_ms": traced}
+    for layer in (0, 1):
+        t = buf[layer].astype(np.int64)
+        out = {}
+        for X in (0, 1):
+            tt = t[:, X * 20:X * 20 + 15]
+            rel = tt - tt[:, :1]
+            out["tile%d" % X] = {"period": float(np.median(np.diff(tt[:, 0]))),
+                                 "offsets": {PP_SLOTS[k]: float(np.median(rel[:, k])) for k in range(15)}}
+        out["B_minus_A_h_seen"] = float(np.median(t[:, 20] - t[:, 0]))
+        res["layer%d" % layer] = out
+    m.close()
+    return res
+
+
+CHECKS = {"pp": check_pp, "rec_timing": check_rec_timing, "pp_trace": check_pp_trace, "selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism,
           "rec_trace": check_rec_trace}
 
 PLAN = [
