@@ -238,6 +238,24 @@ int mdk_stitch_consensus_dev(int device, const float *probs_dev, int64_t n_rows,
 int mdk_variant_columns(int device, const int64_t *minor, const uint8_t *reference,
                         const uint8_t *prediction, uint8_t *out, int64_t len);
 
+/* Variant decoding (medaka/labels.py:889-1014 `HaploidLabelScheme.decode_variants`, the array half): for one joined
+ * sample of n pileup columns
+ *   pred[i]      = argmax label of probs[i] (gaps kept; labels.py:917)
+ *   is_var[i]    = variant_columns(minor, reference-with-gaps, prediction)   (src/medaka_rnn_variants.c:28-55)
+ *   pred_q[i]    = phred(1 - probs[i][pred[i]]),  ref_q[i] = phred(1 - probs[i][ref_code[i]])   (labels.py:387-401,
+ *                  float32; 'N' is scored as the gap class, labels.py:949-952)
+ *   runs         = maximal runs of variant columns (common.rle, labels.py:928-930): first column, length and the
+ *                  left-to-right float32 sums of pred_q / ref_q over the run (labels.py:957-975; the variant's
+ *                  quality is run_pred_q - run_ref_q)
+ * ref_code[i]: 0..4 = '*ACGT' with 0 on insertion columns (minor != 0), 5 = 'N', 6+ = any other draft symbol.
+ * Strings, the ref == alt / ambiguous-reference filters and VCF normalisation stay on the host (medaka_b200/labels.py).
+ * Host pointers; pred_q_out / ref_q_out may be NULL.  *n_runs_out is always set; if it exceeds max_runs the call
+ * returns MDK_ERR_NOMEM without run data and the caller retries with larger buffers. */
+int mdk_decode_variants(int device, const float *probs, const int64_t *minor, const uint8_t *ref_code, int64_t n,
+                        uint8_t *pred_out, uint8_t *is_var_out, float *pred_q_out, float *ref_q_out, int64_t max_runs,
+                        int64_t *run_start, int64_t *run_len, float *run_pred_q, float *run_ref_q,
+                        int64_t *n_runs_out);
+
 /* ---- self test of the tcgen05 building block (one 128xN tile GEMM), used by tests ----------
  * Computes D[128][N] = A[128][K] * B[N][K]^T with the same smem layouts, descriptors and
  * fp16 hi/lo split the GRU kernels use.  A, B, D are host fp32.  variant selects descriptor
@@ -251,6 +269,9 @@ int mdk_selftest_umma(int device, const float *A, const float *B, float *D, int 
  * the last traced forward: uint64 [2 layers][16 time steps (512..527)][32 slots] of %clock64 on CTA (0,0); the slot
  * meanings are listed in tools/diag.py.  Not part of the hot path. */
 int mdk_debug_rec_trace(int device, int enable, uint64_t *out);
+/* partial logits of the last forward on the fused-head path: float32 [2 directions][tiles][T][5 classes][16 windows]
+ * (what the layer-1 recurrence writes instead of h1); per-direction parity checks of the fused linear head */
+int mdk_debug_read_plog(mdk_engine *e, float *out_host, int64_t n_floats);
 
 #ifdef __cplusplus
 }

@@ -118,6 +118,24 @@ class Sample(_Sample):
         return d
 
     @staticmethod
+    def from_samples(samples):
+        """Concatenate abutting samples into one (medaka/common.py:200-230)."""
+        samples = list(samples)
+        for s1, s2 in zip(samples[:-1], samples[1:]):
+            rel = Sample.relative_position(s1, s2)
+            if rel is not Relationship.forward_abutted:
+                raise ValueError('Refusing to concatenate unordered/non-abutting samples {} and {} with relationship {}.'
+                                 .format(s1.name, s2.name, repr(rel)))
+        fields = {}
+        for attr in Sample._fields:
+            vals = [getattr(s, attr) for s in samples]
+            if attr == 'ref_name':
+                fields[attr] = vals[0]
+            else:
+                fields[attr] = None if all(v is None for v in vals) else np.concatenate(vals)
+        return Sample(**fields)
+
+    @staticmethod
     def relative_position(s1, s2):
         """Classify how two samples sit relative to each other (cf. medaka/common.py:231-325).
 

@@ -716,6 +716,18 @@ int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_
     return MDK_OK;
 }
 
+int mdk_debug_read_plog(mdk_engine *e, float *out_host, int64_t n_floats) {
+    MDK_REQUIRE(e && out_host, MDK_ERR_ARG, "NULL argument");
+    mdk_lane &ln = e->lane[e->last_lane];
+    MDK_REQUIRE(ln.last_fused_head, MDK_ERR_STATE, "read_plog: the last forward did not run the fused head");
+    const int64_t tiles = (ln.last_B + WT - 1) / WT;
+    MDK_REQUIRE(n_floats == NDIR * tiles * ln.last_T * PLOG_TS_FLOATS, MDK_ERR_ARG, "read_plog: size must be 2*tiles*T*80");
+    MDK_CUDA(cudaSetDevice(e->device));
+    MDK_CUDA(cudaStreamSynchronize(ln.stream));
+    MDK_CUDA(cudaMemcpy(out_host, ln.plog, (size_t)n_floats * sizeof(float), cudaMemcpyDeviceToHost));
+    return MDK_OK;
+}
+
 int64_t mdk_engine_launch_count(mdk_engine *e) { return e ? e->launches : 0; }
 
 int mdk_engine_keep_activations(mdk_engine *e, int keep) {

@@ -24,20 +24,20 @@
 //   layer 1:  accumulators r, z, n [384, 432);  logits [432, 448);  W_lin hi plane [448, 512)
 // There is ONE set of accumulators and the two tiles take turns: the tensor pipe executes MMAs in issue order, tile B's
 // r block can only start after tile A's n block, and by then A's gate warps have long since read A's r block.  That
-// "long since" is made a guarantee by the `consumed[g]` mbarriers: the gate warps of a tile arrive after their
-// tcgen05.ld of block g, and the issuer of the OTHER tile waits for that arrival before it queues its own block g.
-// Uses of a block strictly alternate A, B, A, B (each tile's next use needs the other's consumption), so a parity wait
-// is unambiguous.  Sharing is what makes everything fit: with per-tile accumulators neither W_ih (layer 0) nor W_lin
+// "long since" is made a guarantee by the `free_acc[X][g]` mbarriers ("block g may be used by tile X"): the gate warps
+// of the OTHER tile arrive on it after their tcgen05.ld of block g, and issuer X waits for that arrival before it queues
+// its own block g.  Uses of a block strictly alternate A, B, A, B (each tile's next use needs the other's consumption);
+// every barrier has one waiter that asks for consecutive phases, so the parity wait is unambiguous.  Sharing is what makes everything fit: with per-tile accumulators neither W_ih (layer 0) nor W_lin
 // (layer 1) could stay resident, and an SS-mode MMA (A operand from shared memory) costs 40 cycles instead of 10.
 //
 // Per-step protocol of tile X (named barriers H_X, R_X, Z_X, N_X; all counts = 8 gate warps + 1 service warp):
 //   gate warps: ... write h_t (fp16 hi/lo, K-major B-operand image, double buffered) -> fence.proxy.async -> arrive H_X
-//   issuer X:   sync H_X -> [wait consumed[r]] x-part of n (layer 0), r block, commit -> [consumed[z]] z block, commit
-//               -> [consumed[n]] n block, commit -> (layer 1) [log_free] logits of h_{t-1}, commit
+//   issuer X:   sync H_X -> [wait free_acc[X][r]] x-part of n (layer 0), r block, commit -> [free_acc[X][z]] z block,
+//               commit -> [free_acc[X][n]] n block, commit -> (layer 1) [log_free[X]] logits of h_{t-1}, commit
 //   relay X:    wait commit r (+ gi landed) -> arrive R_X;  wait commit z -> arrive Z_X;  wait commit n -> arrive N_X
-//   gate warps: sync R_X -> tcgen05.ld r (+x) -> arrive consumed[r] -> sigmoid(r), r * b_hn + gi_n
-//               sync Z_X -> ld z -> arrive consumed[z] -> e^-z and the z-dependent halves of the h update
-//               sync N_X -> ld n -> arrive consumed[n] -> tanh, h_t, split, store
+//   gate warps: sync R_X -> tcgen05.ld r (+x) -> arrive free_acc[other][r] -> sigmoid(r), r * b_hn + gi_n
+//               sync Z_X -> ld z -> arrive free_acc[other][z] -> e^-z and the z-dependent halves of the h update
+//               sync N_X -> ld n -> arrive free_acc[other][n] -> tanh, h_t, split, store
 // Every mbarrier wait is bounded and traps (ptx.cuh); the named barriers cannot be bounded, so bring-up runs go under
 // `timeout`.
 #include <cstdlib>
@@ -80,8 +80,8 @@ struct PPCfg {
     static constexpr int wl_off = gi_off + 2 * PP_GI_BUFS * PP_GI_BLOCK;
     static constexpr int data_end = IN_X ? x_off + 2 * 2 * RT_XBUF : wl_off + (OUT_LOG ? PP_WL_PLANE : 0);
     static constexpr int bar_off = ((data_end + 127) / 128) * 128;
-    // mbarriers: acc[2][3], gi_full[2][3], consumed[3], log_full, log_free ; then the TMEM slot
-    static constexpr int n_bars = 6 + 6 + 3 + 2;
+    // mbarriers: acc[2][3], gi_full[2][3], free_acc[2][3], log_full, log_free[2] ; then the TMEM slot
+    static constexpr int n_bars = 6 + 6 + 6 + 1 + 2;
     static constexpr int tmem_off = bar_off + n_bars * 8;
     static constexpr int end_ = tmem_off + 16;
     // the CTA owns all 512 TMEM columns of its SM: ask for more than half of the shared memory so that a second CTA can
@@ -123,8 +123,8 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
     constexpr bool IN_X = L::IN_X, OUT_LOG = L::OUT_LOG;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::bar_off);
     uint64_t *acc = bars + X * 3;
-    uint64_t *consumed = bars + 12;
-    uint64_t *log_full = bars + 15, *log_free = bars + 16;
+    uint64_t *free_acc = bars + 12 + X * 3;        // completed by the other tile's gate warps
+    uint64_t *log_full = bars + 18, *log_free = bars + 19 + X;
     // Operands sit in uniform registers: literal TMEM addresses, descriptors derived from the constant dynamic-smem
     // base, issue predicated by elect.sync (otherwise every tcgen05.mma is wrapped in an R2UR waterfall loop).
     const uint32_t idesc = make_idesc_f16(128, RT_N);
@@ -192,9 +192,10 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
             PP_STAMP(X * 20 + 0);
             const uint64_t hd = hdesc0 + (uint64_t)((par * 2 * RT_HPLANE) >> 4);
             const uint64_t xd = xdesc0 + (uint64_t)((par * RT_XBUF) >> 4);
+            // the use just before this one was the other tile's: B's of step s-1 for A, A's of step s for B
             const bool guard = (X == 1) || s > 0;          // the very first use of the accumulators needs no hand-over
-            constexpr uint32_t gpar = (X == 0) ? 1u : 0u;  // parity of the other tile's consumption phase (see header)
-            if (guard) mbar_wait(&consumed[0], gpar);
+            const uint32_t gpar = (uint32_t)((X == 0 ? s - 1 : s) & 1);
+            if (guard) mbar_wait(&free_acc[0], gpar);
             tc_fence_after_sync();
             if (IN_X) issue_x(L::acc_col + 48, 2, xd, 0u);   // W_in . x of the n gate keeps its own columns
             {
@@ -203,7 +204,7 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
             }
             umma_commit(&acc[0]);
             PP_STAMP(X * 20 + 1);
-            if (guard) mbar_wait(&consumed[1], gpar);
+            if (guard) mbar_wait(&free_acc[1], gpar);
             tc_fence_after_sync();
             {
                 const uint32_t f = issue_h(L::acc_col + 16, 1, hd, 0u);
@@ -211,14 +212,15 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
             }
             umma_commit(&acc[1]);
             PP_STAMP(X * 20 + 2);
-            if (guard) mbar_wait(&consumed[2], gpar);
+            if (guard) mbar_wait(&free_acc[2], gpar);
             tc_fence_after_sync();
             issue_h(L::acc_col + 32, 2, hd, 0u);
             umma_commit(&acc[2]);
             PP_STAMP(X * 20 + 3);
             if (OUT_LOG && s > 0) {
                 // the tile buffer holds h of the previous step: its logits ride in the shadow of the gate phase
-                if (X == 1 || s > 1) mbar_wait(log_free, gpar);
+                // this tile's logits use k = s - 1 follows B's use k-1 (tile A) / A's use k (tile B)
+                if (X == 1 || s > 1) mbar_wait(log_free, (uint32_t)((X == 0 ? s - 2 : s - 1) & 1));
                 tc_fence_after_sync();
                 issue_logits(hd);
                 PP_STAMP(X * 20 + 14);
@@ -232,7 +234,7 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
         tc_fence_after_sync();
         if (elect_one()) {
             const uint64_t hd = hdesc0 + (uint64_t)(((uint32_t)(T & 1) * 2 * RT_HPLANE) >> 4);
-            if (X == 1 || T > 1) mbar_wait(log_free, (X == 0) ? 1u : 0u);
+            if (X == 1 || T > 1) mbar_wait(log_free, (uint32_t)((X == 0 ? T - 2 : T - 1) & 1));   // use k = T - 1
             tc_fence_after_sync();
             issue_logits(hd);
         }
@@ -364,7 +366,7 @@ template <bool TRACE>
 __device__ __forceinline__ void pp_logits(uint8_t *smem, const PPArgs &a, int lane) {
     using L = PPCfg<1>;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::bar_off);
-    uint64_t *log_full = bars + 15, *log_free = bars + 16;
+    uint64_t *log_full = bars + 18, *log_free = bars + 19;
     const int dir = blockIdx.y;
     const int64_t T = a.T;
 #pragma unroll 1
@@ -378,7 +380,7 @@ __device__ __forceinline__ void pp_logits(uint8_t *smem, const PPArgs &a, int la
         tmem_ld_wait();
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(log_free);
+        if (lane == 0) mbar_arrive(&log_free[1 - X]);     // the accumulator is free for the other tile's next logits
         const int64_t tile = (int64_t)blockIdx.x * 2 + X;
         if (tile < a.ntiles && lane < NCLS) {
             const int64_t t = dir ? (T - 1 - sidx) : sidx;
@@ -399,7 +401,7 @@ __device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, 
     constexpr bool L0 = L::IN_X;                            // fused input projection: biases + x staging here, no gi
     constexpr int NP = 4;                                   // 8 windows per thread as 4 packed fp32 pairs
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::bar_off);
-    uint64_t *consumed = bars + 12;
+    uint64_t *freed = bars + 12 + (1 - X) * 3;      // free_acc of the OTHER tile: it may use a block once we have read it
     const int dir = blockIdx.y;
     const int64_t T = a.T;
     const int q = w8 & 3, ch = w8 >> 2;
@@ -483,7 +485,7 @@ __device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, 
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (elected) mbar_arrive(&consumed[0]);
+            if (elected) mbar_arrive(&freed[0]);
             PP_STAMP(X * 20 + 7);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
@@ -519,7 +521,7 @@ __device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, 
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (elected) mbar_arrive(&consumed[1]);
+            if (elected) mbar_arrive(&freed[1]);
             PP_STAMP(X * 20 + 9);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
@@ -546,7 +548,7 @@ __device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, 
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (elected) mbar_arrive(&consumed[2]);
+            if (elected) mbar_arrive(&freed[2]);
             PP_STAMP(X * 20 + 11);
             uint8_t *hw = hrow + (int)((s + 1) & 1) * (2 * RT_HPLANE);      // the buffer the MMAs of this step do not read
 #pragma unroll
@@ -615,9 +617,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) rec_pp_kernel(const __grid_cons
     if (tid == 0) {
         for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);              // acc[X][g]: one tcgen05.commit each
         for (int i = 6; i < 12; ++i) mbar_init(&bars[i], 1);             // gi_full[X][b]: expect_tx + bytes
-        for (int i = 12; i < 15; ++i) mbar_init(&bars[i], PP_TILE_WARPS);   // consumed[g]: one lane per gate warp of a tile
-        mbar_init(&bars[15], 1);                                         // log_full: commit
-        mbar_init(&bars[16], 1);                                         // log_free: the logits warp
+        for (int i = 12; i < 18; ++i) mbar_init(&bars[i], PP_TILE_WARPS);   // free_acc[X][g]: one lane per gate warp of a tile
+        mbar_init(&bars[18], 1);                                         // log_full: commit
+        mbar_init(&bars[19], 1);                                         // log_free[X]: the logits warp
+        mbar_init(&bars[20], 1);
         fence_mbar_init();
     }
     if (warp == PP_W_ISS) {

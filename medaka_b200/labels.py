@@ -63,6 +63,49 @@ def variant_columns(minor, reference, prediction, device=0):
     return out.astype(bool)
 
 
+def decode_variant_arrays(label_probs, minor, ref_codes, device=0, want_quals=True):
+    """The array half of ``decode_variants`` on the GPU (libmedaka_b200 ``mdk_decode_variants``).
+
+    :param label_probs: float [n, 5]; :param minor: pileup minor indices [n]; :param ref_codes: uint8 [n], the draft
+        with gaps as label codes (0..4 '*ACGT', 5 'N', 6 other).
+    :returns: dict(pred uint8 [n], is_var bool [n], pred_q / ref_q float32 [n], run_start / run_len int64 [r],
+        run_pred_q / run_ref_q float32 [r]).
+    """
+    lib, ffi = _lm.load(), _lm.ffi
+    p = np.ascontiguousarray(label_probs.detach().cpu().numpy() if hasattr(label_probs, "detach") else label_probs,
+                             dtype=np.float32)
+    n = len(p)
+    mn = np.ascontiguousarray(minor, dtype=np.int64)
+    rc = np.ascontiguousarray(ref_codes, dtype=np.uint8)
+    if p.ndim != 2 or p.shape[1] != 5 or len(mn) != n or len(rc) != n:
+        raise ValueError("label_probs [n,5], minor [n] and ref_codes [n] expected")
+    pred = np.empty(n, dtype=np.uint8)
+    is_var = np.empty(n, dtype=np.uint8)
+    pq = np.empty(n, dtype=np.float32) if want_quals else None
+    rq = np.empty(n, dtype=np.float32) if want_quals else None
+    max_runs = max(16, n // 8)
+    n_runs = ffi.new("int64_t *")
+    while True:
+        rs, rl = np.empty(max_runs, dtype=np.int64), np.empty(max_runs, dtype=np.int64)
+        rp, rr = np.empty(max_runs, dtype=np.float32), np.empty(max_runs, dtype=np.float32)
+        code = lib.mdk_decode_variants(
+            device, ffi.cast("const float *", ffi.from_buffer(p)), ffi.cast("const int64_t *", ffi.from_buffer(mn)),
+            ffi.cast("const uint8_t *", ffi.from_buffer(rc)), n, ffi.cast("uint8_t *", ffi.from_buffer(pred)),
+            ffi.cast("uint8_t *", ffi.from_buffer(is_var)),
+            ffi.cast("float *", ffi.from_buffer(pq)) if want_quals else ffi.NULL,
+            ffi.cast("float *", ffi.from_buffer(rq)) if want_quals else ffi.NULL, max_runs,
+            ffi.cast("int64_t *", ffi.from_buffer(rs)), ffi.cast("int64_t *", ffi.from_buffer(rl)),
+            ffi.cast("float *", ffi.from_buffer(rp)), ffi.cast("float *", ffi.from_buffer(rr)), n_runs)
+        if code == lib.MDK_ERR_NOMEM and int(n_runs[0]) > max_runs:
+            max_runs = int(n_runs[0])            # enlarge and retry, like enlarge_plp_data for the pileup
+            continue
+        _lm.check(code)
+        break
+    r = int(n_runs[0])
+    return dict(pred=pred, is_var=is_var.astype(bool), pred_q=pq, ref_q=rq, run_start=rs[:r], run_len=rl[:r],
+                run_pred_q=rp[:r], run_ref_q=rr[:r])
+
+
 class HaploidLabelScheme(object):
     """The decode half of the reference's HaploidLabelScheme (labels.py:703-1085)."""
 
@@ -71,6 +114,96 @@ class HaploidLabelScheme(object):
 
     def __init__(self, device=0):
         self.device = device
+        self.verbose = False
+        # draft symbol -> label code; 5 = 'N' (its own symbol when compared, the gap class when scored), 6 = other
+        self._ref_table = np.full(256, 6, dtype=np.uint8)
+        for i, c in enumerate(self.symbols):
+            self._ref_table[ord(c)] = i
+        self._ref_table[ord('N')] = 5
+
+    @staticmethod
+    def _pfmt(p, dp=3):
+        """labels.py:404-416."""
+        if isinstance(p, np.ndarray):
+            return np.char.mod("%.{}f".format(dp), p)
+        return '{:.{dp}f}'.format(round(p, dp), dp=dp)
+
+    def decode_labels(self, sample):
+        """argmax label codes (uint8, gaps kept) of a sample - the integer form of decode_consensus(with_gaps=True)."""
+        return decode_arrays(sample.label_probs, self.device, with_qualities=False)[0]
+
+    def encode_reference(self, ref_seq, majors):
+        """Label codes of the draft at the given major positions."""
+        majors = np.asarray(majors, dtype=np.int64)
+        if len(majors) == 0:
+            return np.zeros(0, dtype=np.uint8)
+        lo, hi = int(majors[0]), int(majors[-1]) + 1
+        window = np.frombuffer(ref_seq[lo:hi].encode('ascii', 'replace'), dtype=np.uint8)
+        return self._ref_table[window[majors - lo]]
+
+    def decode_variants(self, sample, ref_seq, ambig_ref=False, return_all=False):
+        """Convert network output in sample to variant records (medaka/labels.py:889-1014).
+
+        The consensus with gaps, the variant columns, the per-column qualities and the per-run sums come from the GPU
+        (``mdk_decode_variants``); the strings of the (few) variant runs, the ref == alt / ambiguous-draft filters and
+        the VCF normalisation are done here.  Returns a list of ``medaka_b200.variant.Variant``.
+        """
+        from medaka_b200.variant import Variant
+        pos = sample.positions
+        if pos['minor'][0] != 0:
+            raise ValueError("The first position of a sample must not be an insertion.")
+        is_major = pos['minor'] == 0
+        ref_codes = np.zeros(len(pos), dtype=np.uint8)            # '*' on insertion columns (labels.py:920)
+        ref_codes[is_major] = self.encode_reference(ref_seq, pos['major'][is_major])
+        d = decode_variant_arrays(sample.label_probs, pos['minor'], ref_codes, self.device)
+        sym = np.frombuffer((self.symbols + 'N?').encode(), dtype=np.uint8)
+        major0 = int(pos['major'][0])
+        variants = []
+        for rstart, rlen, spq, srq in zip(d['run_start'], d['run_len'], d['run_pred_q'], d['run_ref_q']):
+            rstart, rend = int(rstart), int(rstart + rlen)
+            codes = ref_codes[rstart:rend]
+            if np.any(codes == 6):
+                # spell the run's draft from the sequence itself (any IUPAC symbol)
+                ref_g = ''.join(ref_seq[int(m)] if mi == 0 else '*' for m, mi in zip(pos['major'][rstart:rend],
+                                                                                     pos['minor'][rstart:rend]))
+            else:
+                ref_g = sym[codes].tobytes().decode()
+            pred_g = sym[d['pred'][rstart:rend]].tobytes().decode()
+            var_ref, var_pred = ref_g.replace('*', ''), pred_g.replace('*', '')
+            if var_ref == var_pred:          # deletion followed by insertion of the same base (labels.py:942-944)
+                continue
+            if not set(var_ref).issubset(set(self.symbols)):
+                if not ambig_ref:
+                    continue
+                if set(var_ref) - set(self.symbols) - {'N'}:
+                    raise KeyError("draft symbol outside '*ACGTN' in a variant run at {}:{}".format(
+                        sample.ref_name, int(pos['major'][rstart])))
+            qual = np.float32(spq) - np.float32(srq)          # log likelihood ratio (labels.py:974-975), float32
+            info = {}
+            if self.verbose:
+                info = {'ref_seq': ref_g, 'pred_seq': pred_g,
+                        'ref_qs': ','.join(self._pfmt(float(q)) for q in d['ref_q'][rstart:rend]),
+                        'pred_qs': ','.join(self._pfmt(float(q)) for q in d['pred_q'][rstart:rend]),
+                        'ref_q': self._pfmt(float(srq)), 'pred_q': self._pfmt(float(spq)), 'n_cols': rend - rstart}
+            genotype = {'GT': '1', 'GQ': self._pfmt(float(qual), 0)}
+            var_pos = int(pos['major'][rstart])
+            if pos['minor'][rstart] != 0:    # variant starts on an insertion column: prepend the draft base
+                var_ref = ref_seq[var_pos] + var_ref
+                var_pred = ref_seq[var_pos] + var_pred
+            v = Variant(sample.ref_name, var_pos, var_ref, alt=var_pred, filt='PASS', info=info,
+                        qual=self._pfmt(float(qual)), genotype_data=genotype)
+            variants.append(v.normalize(reference=ref_seq))
+        if return_all:
+            # one record per reference position (labels.py:991-1012)
+            quals = d['ref_q'][is_major]
+            qf, qi = np.char.mod("%.3f", quals), np.char.mod("%d", np.rint(quals))
+            bases = [ref_seq[int(m)] for m in pos['major'][is_major]]
+            for p_, base, f_, i_ in zip(pos['major'][is_major], bases, qf, qi):
+                variants.append(Variant(sample.ref_name, int(p_), base, alt='.', filt='.', info={}, qual=str(f_),
+                                        genotype_data={'GT': '0', 'GQ': str(i_)}))
+            variants.sort(key=lambda x: x.pos)
+        del major0
+        return variants
 
     @property
     def num_classes(self):

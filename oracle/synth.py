@@ -248,3 +248,59 @@ def synth_stitch_stream(seed=0, n_major=3000, first_major=1000, chunk_len=400, o
         if c in nest:
             stream.append(make(lo + chunk_len // 4, lo + chunk_len // 2, seed * 1000 + 500 + c))
     return stream
+
+
+def synth_variant_pileup(seed=0, n_major=3000, first_major=1000, p_ins_col=0.08, p_mut=0.03, p_extend=0.35,
+                         p_ins_call=0.2, n_frac=0.003, ref_name='contig1'):
+    """A pileup with a known draft and a network output that disagrees with it here and there (variant decoding).
+
+    :returns: dict(ref_name, ref_seq (str over 0 .. first_major + n_major + 50, ACGT with a few N), positions
+        (major/minor), label_probs float32 [n, 5] whose argmax is the constructed call).
+
+    Calls on major columns: the draft base, or with probability p_mut the start of a mutated run (each further column
+    joins with p_extend) of substitutions / deletions; minor (insertion) columns call a base with probability p_ins_call
+    (more often right after a mutated major: deletion followed by insertion, the reference's 'CA*cG' case) else gap.
+    """
+    rs = np.random.RandomState(seed)
+    total = first_major + n_major + 50
+    ref = rs.randint(0, 4, total)
+    is_n = rs.uniform(size=total) < n_frac
+    ref_seq = ''.join('N' if is_n[i] else 'ACGT'[ref[i]] for i in range(total))
+    n_ins = np.minimum(rs.geometric(1.0 - p_ins_col, size=n_major) - 1, 3)
+    counts = 1 + n_ins
+    major = np.repeat(np.arange(first_major, first_major + n_major), counts)
+    starts = np.cumsum(counts) - counts
+    minor = np.arange(len(major)) - np.repeat(starts, counts)
+    n = len(major)
+    positions = np.empty(n, dtype=[('major', int), ('minor', int)])
+    positions['major'], positions['minor'] = major, minor
+    call = np.zeros(n, dtype=np.int64)               # label codes: 0 '*', 1..4 ACGT
+    in_run = False
+    for i in range(n):
+        if minor[i] == 0:
+            base = ref[major[i]] + 1
+            in_run = (rs.uniform() < p_extend) if in_run else (rs.uniform() < p_mut)
+            if in_run:
+                kind = rs.uniform()
+                call[i] = 0 if kind < 0.35 else 1 + (base - 1 + rs.randint(1, 4)) % 4
+            else:
+                call[i] = base
+        else:
+            p = 0.6 if in_run else p_ins_call
+            call[i] = rs.randint(1, 5) if rs.uniform() < p else 0
+    top = rs.uniform(0.45, 0.9999, n)
+    top[rs.uniform(size=n) < 0.2] = 0.99999994       # quality cap
+    rest = rs.dirichlet(np.ones(4), n) * (1.0 - top)[:, None]
+    probs = np.empty((n, 5), dtype=np.float64)
+    for c in range(5):
+        sel = call == c
+        others = [k for k in range(5) if k != c]
+        probs[np.ix_(sel, others)] = rest[sel]
+        probs[sel, c] = top[sel]
+    probs = probs.astype(np.float32)
+    # the constructed call must be the unique argmax after the float32 cast
+    fix = np.argmax(probs, -1) != call
+    probs[fix] = np.eye(5, dtype=np.float32)[call[fix]] * np.float32(0.9)
+    probs[fix] += np.float32(0.025)
+    assert np.array_equal(np.argmax(probs, -1), call)
+    return dict(ref_name=ref_name, ref_seq=ref_seq, positions=positions, label_probs=probs, call=call)

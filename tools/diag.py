@@ -202,6 +202,27 @@ def check_pp(arg):
         res["dh0_fwd"] = float(d[..., :128].max())
         res["dh0_rev"] = float(d[..., 128:].max())
         res["dh0_bad_windows"] = sorted(set(np.argwhere(d.max(-1) > 1e-4)[:, 0].tolist()))[:20]
+    if T * B <= 400000:
+        # per-direction partial logits against W_lin[:, half] . h1[half] of the loop-level oracle
+        from medaka_b200 import libmedaka as lm
+        tiles = (B + 15) // 16
+        plog = np.zeros((2, tiles, T, 5, 16), dtype=np.float32)
+        lm.check(lm.lib.mdk_debug_read_plog(m.engine, lm.ffi.cast("float *", lm.ffi.from_buffer(plog)), plog.size))
+        W = sd["linear.weight"].astype(np.float64)
+        for d, name in ((0, "fwd"), (1, "rev")):
+            exp = man["h1"][..., d * 128:(d + 1) * 128].astype(np.float64) @ W[:, d * 128:(d + 1) * 128].T   # [B,T,5]
+            got = np.zeros((tiles * 16, T, 5), dtype=np.float32)
+            got[:] = plog[d].transpose(0, 3, 1, 2).reshape(tiles * 16, T, 5)
+            e = np.abs(got[:B] - exp)
+            bad = np.argwhere(e.max(-1) > 1e-3)
+            res["plog_%s_maxerr" % name] = float(e.max())
+            res["plog_%s_bad_tiles" % name] = sorted(set((bad[:, 0] // 16).tolist()))
+            res["plog_%s_bad_t" % name] = sorted(set(bad[:, 1].tolist()))[:12]
+            if len(bad):
+                w, t = bad[0]
+                # does the bad row match the expected row of a neighbouring time step?
+                cands = {dt: float(np.abs(got[w, t] - exp[w, t + dt]).max()) for dt in (-2, -1, 1, 2) if 0 <= t + dt < T}
+                res["plog_%s_neighbour_match" % name] = cands
     res["timings"] = m.last_timings()
     m.close()
     return res
