@@ -117,8 +117,8 @@ __device__ __forceinline__ unsigned long long *pp_trace_row(const PPArgs &a, int
 }
 
 // ------------------------------------------------------------------------------------------------ issuer of tile X
-template <int LAYER, int X, bool ALLP, bool TRACE>
-__device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
+template <int LAYER, bool ALLP, bool TRACE>
+__device__ __noinline__ void pp_issuer(uint8_t *smem, const PPArgs &a, const int X) {
     using L = PPCfg<LAYER>;
     constexpr bool IN_X = L::IN_X, OUT_LOG = L::OUT_LOG;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::bar_off);
@@ -186,7 +186,7 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
     for (int64_t s = 0; s < T; ++s) {
         const uint32_t par = (uint32_t)(s & 1);
         unsigned long long *tr = pp_trace_row<TRACE>(a, s, true);
-        named_bar_sync<PP_BAR_H + X, PP_NB>();
+        named_bar_sync_id<PP_NB>(PP_BAR_H + X);
         tc_fence_after_sync();
         if (elect_one()) {
             PP_STAMP(X * 20 + 0);
@@ -196,6 +196,7 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
             const bool guard = (X == 1) || s > 0;          // the very first use of the accumulators needs no hand-over
             const uint32_t gpar = (uint32_t)((X == 0 ? s - 1 : s) & 1);
             if (guard) mbar_wait(&free_acc[0], gpar);
+            PP_STAMP(X * 20 + 15);
             tc_fence_after_sync();
             if (IN_X) issue_x(L::acc_col + 48, 2, xd, 0u);   // W_in . x of the n gate keeps its own columns
             {
@@ -205,6 +206,7 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
             umma_commit(&acc[0]);
             PP_STAMP(X * 20 + 1);
             if (guard) mbar_wait(&free_acc[1], gpar);
+            PP_STAMP(X * 20 + 16);
             tc_fence_after_sync();
             {
                 const uint32_t f = issue_h(L::acc_col + 16, 1, hd, 0u);
@@ -213,6 +215,7 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
             umma_commit(&acc[1]);
             PP_STAMP(X * 20 + 2);
             if (guard) mbar_wait(&free_acc[2], gpar);
+            PP_STAMP(X * 20 + 17);
             tc_fence_after_sync();
             issue_h(L::acc_col + 32, 2, hd, 0u);
             umma_commit(&acc[2]);
@@ -221,6 +224,7 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
                 // the tile buffer holds h of the previous step: its logits ride in the shadow of the gate phase
                 // this tile's logits use k = s - 1 follows B's use k-1 (tile A) / A's use k (tile B)
                 if (X == 1 || s > 1) mbar_wait(log_free, (uint32_t)((X == 0 ? s - 2 : s - 1) & 1));
+                PP_STAMP(X * 20 + 18);
                 tc_fence_after_sync();
                 issue_logits(hd);
                 PP_STAMP(X * 20 + 14);
@@ -230,7 +234,7 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
     }
     if (OUT_LOG) {
         // h of the last step: every gate warp of the tile has published it (FIN_X), one more round of logits MMAs
-        named_bar_sync<PP_BAR_FIN + X, PP_NB>();
+        named_bar_sync_id<PP_NB>(PP_BAR_FIN + X);
         tc_fence_after_sync();
         if (elect_one()) {
             const uint64_t hd = hdesc0 + (uint64_t)(((uint32_t)(T & 1) * 2 * RT_HPLANE) >> 4);
@@ -243,8 +247,8 @@ __device__ __forceinline__ void pp_issuer(uint8_t *smem, const PPArgs &a) {
 }
 
 // ------------------------------------------------------------------------------------------------ relay of tile X
-template <int LAYER, int X, bool TRACE>
-__device__ __forceinline__ void pp_relay(uint8_t *smem, const PPArgs &a, int lane) {
+template <int LAYER, bool TRACE>
+__device__ __noinline__ void pp_relay(uint8_t *smem, const PPArgs &a, const int X, int lane) {
     using L = PPCfg<LAYER>;
     constexpr bool IN_X = L::IN_X, OUT_LOG = L::OUT_LOG;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::bar_off);
@@ -313,13 +317,13 @@ __device__ __forceinline__ void pp_relay(uint8_t *smem, const PPArgs &a, int lan
         __syncwarp();
         tc_fence_after_sync();
         tc_fence_before_sync();
-        named_bar_arrive<PP_BAR_R + X, PP_NB>();
+        named_bar_arrive_id<PP_NB>(PP_BAR_R + X);
         PP_STAMP(X * 20 + 4);
         if (lead) mbar_wait(&acc[1], par);
         __syncwarp();
         tc_fence_after_sync();
         tc_fence_before_sync();
-        named_bar_arrive<PP_BAR_Z + X, PP_NB>();
+        named_bar_arrive_id<PP_NB>(PP_BAR_Z + X);
         PP_STAMP(X * 20 + 5);
         if (lead) {
             mbar_wait(&acc[2], par);
@@ -329,7 +333,7 @@ __device__ __forceinline__ void pp_relay(uint8_t *smem, const PPArgs &a, int lan
         __syncwarp();
         tc_fence_after_sync();
         tc_fence_before_sync();
-        named_bar_arrive<PP_BAR_N + X, PP_NB>();
+        named_bar_arrive_id<PP_NB>(PP_BAR_N + X);
         PP_STAMP(X * 20 + 6);
         // ---- idle until the next commit: staging / copy-out / prefetch (one thread) ----
         if (lead && tile_ok) {
@@ -351,7 +355,7 @@ __device__ __forceinline__ void pp_relay(uint8_t *smem, const PPArgs &a, int lan
     }
     if (!OUT_LOG) {
         // h of the last step: published through FIN_X
-        named_bar_sync<PP_BAR_FIN + X, PP_NB>();
+        named_bar_sync_id<PP_NB>(PP_BAR_FIN + X);
         if (lead && tile_ok) {
             fence_proxy_async_smem();
             copy_out(T - 1, (int)(T & 1));
@@ -363,7 +367,7 @@ __device__ __forceinline__ void pp_relay(uint8_t *smem, const PPArgs &a, int lan
 
 // ------------------------------------------------------------------------------------------------ logits warp (layer 1)
 template <bool TRACE>
-__device__ __forceinline__ void pp_logits(uint8_t *smem, const PPArgs &a, int lane) {
+__device__ __noinline__ void pp_logits(uint8_t *smem, const PPArgs &a, int lane) {
     using L = PPCfg<1>;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::bar_off);
     uint64_t *log_full = bars + 18, *log_free = bars + 19;
@@ -395,8 +399,8 @@ __device__ __forceinline__ void pp_logits(uint8_t *smem, const PPArgs &a, int la
 }
 
 // ------------------------------------------------------------------------------------------------ gate warps of tile X
-template <int LAYER, int X, bool TRACE>
-__device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, int lane) {
+template <int LAYER, bool TRACE>
+__device__ __noinline__ void pp_gate(uint8_t *smem, const PPArgs &a, const int X, int w8, int lane) {
     using L = PPCfg<LAYER>;
     constexpr bool L0 = L::IN_X;                            // fused input projection: biases + x staging here, no gi
     constexpr int NP = 4;                                   // 8 windows per thread as 4 packed fp32 pairs
@@ -457,7 +461,7 @@ __device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, 
     // h_{-1} = 0 (zeroed tile) and x_0 are in shared memory: publish
     fence_proxy_async_smem();
     tc_fence_before_sync();
-    named_bar_arrive<PP_BAR_H + X, PP_NB>();
+    named_bar_arrive_id<PP_NB>(PP_BAR_H + X);
 
 #pragma unroll 1
     for (int64_t s = 0; s < T; ++s) {
@@ -468,7 +472,7 @@ __device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, 
         {
             uint32_t ar[8], ax[8];
             F2 gr[NP], gn[NP];
-            named_bar_sync<PP_BAR_R + X, PP_NB>();
+            named_bar_sync_id<PP_NB>(PP_BAR_R + X);
             tc_fence_after_sync();
             tmem_ld_x8(t_lane + 0, ar);
             if (L0) tmem_ld_x8(t_lane + 48, ax);
@@ -507,7 +511,7 @@ __device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, 
         {
             uint32_t az[8];
             F2 gz[NP];
-            named_bar_sync<PP_BAR_Z + X, PP_NB>();
+            named_bar_sync_id<PP_NB>(PP_BAR_Z + X);
             tc_fence_after_sync();
             tmem_ld_x8(t_lane + 16, az);
             if (!L0) {
@@ -542,7 +546,7 @@ __device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, 
         // ---------------- n, h ----------------
         {
             uint32_t an[8];
-            named_bar_sync<PP_BAR_N + X, PP_NB>();
+            named_bar_sync_id<PP_NB>(PP_BAR_N + X);
             tc_fence_after_sync();
             tmem_ld_x8(t_lane + 32, an);
             tmem_ld_wait();
@@ -586,8 +590,8 @@ __device__ __forceinline__ void pp_gate(uint8_t *smem, const PPArgs &a, int w8, 
             PP_STAMP(X * 20 + 12);
             fence_proxy_async_smem();     // h / x tile writes -> visible to the MMAs' (and the bulk copy's) async-proxy reads
             tc_fence_before_sync();
-            if (s + 1 < T) named_bar_arrive<PP_BAR_H + X, PP_NB>();
-            else named_bar_arrive<PP_BAR_FIN + X, PP_NB>();
+            if (s + 1 < T) named_bar_arrive_id<PP_NB>(PP_BAR_H + X);
+            else named_bar_arrive_id<PP_NB>(PP_BAR_FIN + X);
             PP_STAMP(X * 20 + 13);
         }
         if (L0 && xok && s + 2 < T) {
@@ -677,12 +681,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) rec_pp_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after_sync();
 
-    if (warp < PP_TILE_WARPS) pp_gate<LAYER, 0, TRACE>(smem, a, warp, lane);
-    else if (warp < PP_GATE_WARPS) pp_gate<LAYER, 1, TRACE>(smem, a, warp - PP_TILE_WARPS, lane);
-    else if (warp == PP_W_ISS) pp_issuer<LAYER, 0, ALLP, TRACE>(smem, a);
-    else if (warp == PP_W_ISS + 1) pp_issuer<LAYER, 1, ALLP, TRACE>(smem, a);
-    else if (warp == PP_W_REL) pp_relay<LAYER, 0, TRACE>(smem, a, lane);
-    else if (warp == PP_W_REL + 1) pp_relay<LAYER, 1, TRACE>(smem, a, lane);
+    // the two tiles run the same code with the tile index in a register (one copy in the instruction cache)
+    if (warp < PP_GATE_WARPS) pp_gate<LAYER, TRACE>(smem, a, warp / PP_TILE_WARPS, warp % PP_TILE_WARPS, lane);
+    else if (warp < PP_W_REL) pp_issuer<LAYER, ALLP, TRACE>(smem, a, warp - PP_W_ISS);
+    else if (warp < PP_W_LOG) pp_relay<LAYER, TRACE>(smem, a, warp - PP_W_REL, lane);
     else if (OUT_LOG) pp_logits<TRACE>(smem, a, lane);
 
     tc_fence_before_sync();

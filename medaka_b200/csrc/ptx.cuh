@@ -64,6 +64,17 @@ __device__ __forceinline__ void named_bar_arrive() {
     asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
 }
 
+// same with the barrier id in a register (the two tiles of rec_pp_kernel run ONE copy of the code: template-per-tile
+// copies doubled the hot instruction footprint of the kernel)
+template <int COUNT>
+__device__ __forceinline__ void named_bar_sync_id(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
+}
+template <int COUNT>
+__device__ __forceinline__ void named_bar_arrive_id(int id) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
+}
+
 // one lane of the (converged) warp; the compiler keeps operands of code under this predicate in uniform registers
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

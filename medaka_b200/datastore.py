@@ -12,11 +12,15 @@ Two interchangeable containers implement that layout:
     (this build image has neither h5py nor libhdf5).
 ``DataStore(filename, mode)`` picks by availability and file suffix.
 """
+import contextlib
+import functools
 import io
 import os
 import pickle
+import sys
 import tarfile
 import threading
+import types
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -33,6 +37,125 @@ def _to_numpy(x):
     if hasattr(x, "detach"):
         return x.detach().cpu().numpy()
     return x
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Pickles that cross the fence to the reference.  medaka stores OBJECTS in its archives and output files:
+# ``meta.pkl`` of a model archive and the ``meta/*`` datasets of a consensus HDF hold ``model_function`` = a
+# functools.partial of a medaka.models function, ``feature_encoder`` = a medaka.features.CountsFeatureEncoder and
+# ``label_scheme`` = a medaka.labels.HaploidLabelScheme (medaka/datastore.py:135-157,171-175; medaka/training.py:83-96;
+# read back at medaka/prediction.py:117-131 and, from the HDF, at medaka/stitch.py / variant.py via
+# ``index.metadata['label_scheme']``).  Reading: a restricted Unpickler maps exactly those globals to this package's
+# classes and refuses everything else (a model archive is downloaded data).  Writing: the same objects are pickled
+# under the reference's module paths, so that an unmodified `medaka sequence` / `medaka vcf` can load what we wrote.
+def _ref_model_from_dict(d, time_steps=None, device=0):
+    from medaka_b200 import models
+    return models.model_from_dict(d, time_steps=time_steps, device=device)
+
+
+def _ref_build_model_torch(feature_len, num_classes, gru_size=128, classify_activation='softmax', time_steps=None,
+                           device=0):
+    from medaka_b200 import models
+    return models.build_model_torch(feature_len, num_classes, gru_size=gru_size, time_steps=time_steps, device=device)
+
+
+def _ref_globals():
+    from medaka_b200 import features, labels
+    import collections
+    return {
+        ('functools', 'partial'): functools.partial,
+        ('collections', 'OrderedDict'): collections.OrderedDict,
+        ('collections', 'defaultdict'): collections.defaultdict,
+        ('builtins', 'list'): list, ('builtins', 'tuple'): tuple, ('builtins', 'dict'): dict, ('builtins', 'set'): set,
+        ('builtins', 'object'): object,
+        ('copyreg', '_reconstructor'): __import__('copyreg')._reconstructor,
+        ('medaka.models', 'model_from_dict'): _ref_model_from_dict,
+        ('medaka.models', 'build_model_torch'): _ref_build_model_torch,
+        ('medaka.features', 'CountsFeatureEncoder'): features.CountsFeatureEncoder,
+        ('medaka.labels', 'HaploidLabelScheme'): labels.HaploidLabelScheme,
+        # archives written by this package
+        ('medaka_b200.features', 'CountsFeatureEncoder'): features.CountsFeatureEncoder,
+        ('medaka_b200.labels', 'HaploidLabelScheme'): labels.HaploidLabelScheme,
+        ('medaka_b200.datastore', '_ref_model_from_dict'): _ref_model_from_dict,
+        ('medaka_b200.datastore', '_ref_build_model_torch'): _ref_build_model_torch,
+    }
+
+
+class _RefUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        try:
+            return _ref_globals()[module, name]
+        except KeyError:
+            raise pickle.UnpicklingError(
+                "refusing to unpickle {}.{}: medaka_b200 loads counts-matrix GRU models with a CountsFeatureEncoder and "
+                "a HaploidLabelScheme only".format(module, name))
+
+
+def ref_loads(data):
+    """Unpickle a meta item written by the reference (or by this package)."""
+    return _RefUnpickler(io.BytesIO(bytes(data))).load()
+
+
+@contextlib.contextmanager
+def _reference_module_names():
+    """While active, this package's stand-ins answer to the reference's module paths, so that pickle records
+    ``medaka.labels HaploidLabelScheme`` etc. (pickle checks that sys.modules[module].name is the object)."""
+    from medaka_b200 import features, labels
+    fakes = {
+        'medaka': types.ModuleType('medaka'),
+        'medaka.models': types.ModuleType('medaka.models'),
+        'medaka.features': types.ModuleType('medaka.features'),
+        'medaka.labels': types.ModuleType('medaka.labels'),
+    }
+    renamed = [(_ref_model_from_dict, 'medaka.models', 'model_from_dict'),
+               (_ref_build_model_torch, 'medaka.models', 'build_model_torch'),
+               (features.CountsFeatureEncoder, 'medaka.features', 'CountsFeatureEncoder'),
+               (labels.HaploidLabelScheme, 'medaka.labels', 'HaploidLabelScheme')]
+    saved_mods = {k: sys.modules.get(k) for k in fakes}
+    saved_names = [(o, o.__module__, o.__qualname__, o.__name__) for o, _, _ in renamed]
+    try:
+        for k, m in fakes.items():
+            sys.modules[k] = m
+        for obj, mod, name in renamed:
+            obj.__module__, obj.__qualname__, obj.__name__ = mod, name, name
+            setattr(fakes[mod], name, obj)
+        yield
+    finally:
+        for obj, mod, qn, nm in saved_names:
+            obj.__module__, obj.__qualname__, obj.__name__ = mod, qn, nm
+        for k, m in saved_mods.items():
+            if m is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = m
+
+
+_ref_dump_lock = threading.Lock()
+
+
+def ref_dumps(obj):
+    """Pickle a meta item the way the reference would have written it (protocol 2-compatible globals)."""
+    with _ref_dump_lock, _reference_module_names():
+        return pickle.dumps(obj, protocol=4)
+
+
+def as_reference_meta(meta):
+    """Normalise this package's plain-dict meta ({'type','kwargs'} dicts, a label-scheme name) into the objects the
+    reference stores: a partial of model_from_dict, an encoder object, a label-scheme object."""
+    from medaka_b200 import features, labels
+    out = dict(meta)
+    mf = out.get('model_function')
+    if isinstance(mf, dict):
+        out['model_function'] = functools.partial(_ref_model_from_dict, mf)
+    fe = out.get('feature_encoder')
+    if isinstance(fe, dict):
+        out['feature_encoder'] = features.CountsFeatureEncoder(**fe.get('kwargs', {}))
+    ls = out.get('label_scheme')
+    if isinstance(ls, str):
+        if ls != 'HaploidLabelScheme':
+            raise NotImplementedError("label scheme {} is not implemented".format(ls))
+        out['label_scheme'] = labels.HaploidLabelScheme()
+    return out
 
 
 class _NpzBackend(object):
@@ -69,32 +192,36 @@ class _NpzBackend(object):
 
     def write_blob(self, path, obj):
         with open(os.path.join(self.root, path.replace("/", os.sep) + ".pkl"), "wb") as fh:
-            pickle.dump(obj, fh)
+            fh.write(ref_dumps(obj))
 
     def read_blob(self, path):
         with open(os.path.join(self.root, path.replace("/", os.sep) + ".pkl"), "rb") as fh:
-            return pickle.load(fh)
+            return ref_loads(fh.read())
 
     def close(self):
         pass
 
 
-class _H5Backend(object):  # pragma: no cover - needs h5py
-    """HDF5 container with the reference's exact dataset paths and compression choices."""
+class _H5Backend(object):
+    """HDF5 container with the reference's exact dataset paths and compression choices (medaka/datastore.py:263-329).
 
-    def __init__(self, filename, mode):
-        self.fh = h5py.File(filename, mode)
+    ``h5`` is the h5py module (tests pass a stand-in that records the calls: this image has no libhdf5)."""
+
+    def __init__(self, filename, mode, h5=None):
+        self.h5 = h5 if h5 is not None else h5py
+        self.fh = self.h5.File(filename, mode)
 
     def write_fields(self, name, fields):
         for k, v in fields.items():
             loc = "samples/data/{}/{}".format(name, k)
             if isinstance(v, np.ndarray):
-                # the reference gzips ndarray fields only (datastore.py:323-329); label_probs arrives
-                # as a torch tensor there and is stored uncompressed - mirrored by the caller passing
-                # compress=False for it
+                # numpy arrays of unicode go in as bytes (datastore.py:283-286)
+                if v.dtype.kind == 'U':
+                    v = np.char.encode(v)
+                # _write_dataset (datastore.py:323-329): every ndarray field is gzip-1 compressed
                 self.fh.create_dataset(loc, data=v, compression="gzip", compression_opts=1)
             else:
-                self.fh[loc] = _to_numpy(v)
+                self.fh[loc] = v        # ref_name: a plain string dataset
 
     def read_fields(self, name):
         g = self.fh["samples/data/{}".format(name)]
@@ -108,13 +235,15 @@ class _H5Backend(object):  # pragma: no cover - needs h5py
         return set(self.fh["samples/data"].keys()) if "samples/data" in self.fh else set()
 
     def write_blob(self, path, obj):
+        # _write_pickled (datastore.py:331-336): np.string_(pickle.dumps(obj)), objects under the reference's module
+        # paths so that `medaka sequence` can unpickle index.metadata['label_scheme'] etc.
         if path in self.fh:
             del self.fh[path]
-        self.fh[path] = np.bytes_(pickle.dumps(obj))
+        self.fh[path] = np.bytes_(ref_dumps(obj))
         self.fh.flush()
 
     def read_blob(self, path):
-        return pickle.loads(self.fh[path][()])
+        return ref_loads(self.fh[path][()])
 
     def close(self):
         self.fh.close()
@@ -127,12 +256,13 @@ class DataStore(object):
     _sample_path_ = 'samples/data'
     _sample_registry_path_ = 'samples/registry'
 
-    def __init__(self, filename, mode='r'):
+    def __init__(self, filename, mode='r', h5=None):
         self.filename = filename
         self.mode = mode
         self.logger = common.get_named_logger('DataStre')
-        use_h5 = h5py is not None and not str(filename).endswith(".npzstore")
-        self._backend = _H5Backend(filename, mode) if use_h5 else _NpzBackend(filename, mode)
+        h5 = h5 if h5 is not None else h5py
+        use_h5 = h5 is not None and not str(filename).endswith(".npzstore")
+        self._backend = _H5Backend(filename, mode, h5) if use_h5 else _NpzBackend(filename, mode)
         self.write_executor = ThreadPoolExecutor(1)
         self.write_futures = []
         self._sample_registry = None
@@ -197,12 +327,13 @@ class DataStore(object):
 
 
 class ModelStoreTGZ(object):
-    """Model archive: ``model/weights.pt`` + pickled ``model/meta.pkl`` in a tar.gz.
+    """Model archive: ``model/weights.pt`` + pickled ``model/meta.pkl`` in a tar.gz (medaka/datastore.py:51-175).
 
-    Same container as the reference (medaka/datastore.py:51-175).  ``meta.pkl`` holds
-    ``model_function`` (a dict {'type','kwargs'} here rather than a pickled partial of a
-    medaka function, so the archive does not need the medaka package to load),
-    ``feature_encoder`` kwargs and ``label_scheme`` name.
+    Reads the reference's shipped ``*_model_pt.tar.gz`` archives: ``meta.pkl`` there holds ``model_function`` as a
+    functools.partial of medaka.models.model_from_dict / build_model_torch plus pickled medaka FeatureEncoder and
+    LabelScheme objects; they are loaded through ``ref_loads`` (restricted to exactly those classes) onto this
+    package's stand-ins.  ``write`` produces the same layout (``ref_dumps``), so the archive also loads in the reference.
+    A ``model_function`` given as a plain ``{'type', 'kwargs'}`` dict is accepted as well.
     """
 
     top_level_dir = 'model'
@@ -224,7 +355,7 @@ class ModelStoreTGZ(object):
         with tarfile.open(filepath, "w:gz") as tar:
             buf = io.BytesIO()
             torch.save({k: torch.as_tensor(np.asarray(v)) for k, v in state_dict.items()}, buf)
-            for name, data in (("weights.pt", buf.getvalue()), ("meta.pkl", pickle.dumps(meta))):
+            for name, data in (("weights.pt", buf.getvalue()), ("meta.pkl", ref_dumps(as_reference_meta(meta)))):
                 info = tarfile.TarInfo("{}/{}".format(cls.top_level_dir, name))
                 info.size = len(data)
                 tar.addfile(info, io.BytesIO(data))
@@ -237,7 +368,7 @@ class ModelStoreTGZ(object):
                 for needed in ("model/weights.pt", "model/meta.pkl"):
                     if needed not in members:
                         raise KeyError("{} is not a model archive: {} missing".format(self.filepath, needed))
-                self._meta = pickle.loads(tar.extractfile(members["model/meta.pkl"]).read())
+                self._meta = ref_loads(tar.extractfile(members["model/meta.pkl"]).read())
                 raw = tar.extractfile(members["model/weights.pt"]).read()
                 self._weights = torch.load(io.BytesIO(raw), map_location="cpu", weights_only=True)
         return self
@@ -250,14 +381,31 @@ class ModelStoreTGZ(object):
         return self.meta[key]
 
     def copy_meta(self, hdf):
+        """Copy metadata to the output store (datastore.py:165-175): objects, under the reference's module paths."""
         with DataStore(hdf, 'a') as ds:
-            for k, v in self.meta.items():
+            for k, v in as_reference_meta(self.meta).items():
                 ds.set_meta(v, k)
+
+    def model_kwargs(self):
+        """The architecture arguments inside ``model_function`` ({'type', 'kwargs'}), whatever its form."""
+        mf = self.meta["model_function"]
+        if isinstance(mf, dict):
+            return mf
+        if isinstance(mf, functools.partial):
+            if mf.func is _ref_model_from_dict:
+                return mf.args[0] if mf.args else mf.keywords['dict']
+            if mf.func is _ref_build_model_torch:
+                names = ('feature_len', 'num_classes', 'gru_size')
+                kw = dict(zip(names, mf.args))
+                kw.update({k: v for k, v in mf.keywords.items() if k in names})
+                return {'type': 'GRUModel', 'kwargs': {'num_features': kw['feature_len'], 'num_classes': kw['num_classes'],
+                                                       'gru_size': kw.get('gru_size', 128)}}
+        raise TypeError("unsupported model_function in {}: {!r}".format(self.filepath, mf))
 
     def load_model(self, device=0, time_steps=None):
         """Build the engine-backed model and load its weights (cf. datastore.py:135-157)."""
         from medaka_b200 import models
         self._unpack()
-        model = models.model_from_dict(self.meta["model_function"], time_steps=time_steps, device=device)
+        model = models.model_from_dict(self.model_kwargs(), time_steps=time_steps, device=device)
         model.load_state_dict(self._weights)
         return model.eval()

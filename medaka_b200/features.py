@@ -135,6 +135,20 @@ class CountsFeatureEncoder(object):
             raise ValueError('normalise={} is not one of {}'.format(self.normalise, self._norm_modes_))
         self.logger = common.get_named_logger('Feature')
 
+    # pickled like the reference's encoder (medaka/features.py:800-810): the attribute set of its __init__ (:819-846),
+    # no logger; nothing device- or source-specific crosses the fence
+    _state_fields = ('normalise', 'dtypes', 'feature_indices', 'tag_name', 'tag_value', 'tag_keep_missing',
+                     'read_group', 'min_mapq', 'sym_indels')
+
+    def __getstate__(self):
+        return {k: getattr(self, k) for k in self._state_fields}
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.__dict__.setdefault('pileup_source', None)
+        self.__dict__.setdefault('device', 0)
+        self.logger = common.get_named_logger('Feature')
+
     def to_dict(self):
         """Return dictionary of keyword arguments."""
         opts = inspect.signature(self.__class__.__init__).parameters

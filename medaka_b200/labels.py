@@ -121,6 +121,15 @@ class HaploidLabelScheme(object):
             self._ref_table[ord(c)] = i
         self._ref_table[ord('N')] = 5
 
+    # pickles as an attribute-less object, like the reference's label scheme (plain object pickling of a class whose
+    # instances carry no state); the lookup table and the device are rebuilt on load
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+        self.__dict__.update(state)
+
     @staticmethod
     def _pfmt(p, dp=3):
         """labels.py:404-416."""

@@ -223,6 +223,11 @@ def test_run_prediction_auto_batch_size_and_lookahead():
 
 
 def test_model_archive_roundtrip():
+    """An archive written here has the reference's layout: model/weights.pt + model/meta.pkl whose pickles name
+    medaka.models.model_from_dict / medaka.features.CountsFeatureEncoder / medaka.labels.HaploidLabelScheme
+    (medaka/datastore.py:51-175, medaka/training.py:83-96), and loads back through the restricted unpickler."""
+    import pickletools
+    import tarfile
     from oracle import synth
     sd = synth.synth_state_dict(1)
     with tempfile.TemporaryDirectory() as d:
@@ -231,11 +236,143 @@ def test_model_archive_roundtrip():
                 "feature_encoder": {"type": "CountsFeatureEncoder", "kwargs": {"normalise": "total"}},
                 "label_scheme": "HaploidLabelScheme"}
         datastore.ModelStoreTGZ.write(path, sd, meta)
+        with tarfile.open(path) as tar:
+            raw = tar.extractfile("model/meta.pkl").read()
+        strings = {arg for op, arg, _ in pickletools.genops(raw) if isinstance(arg, str)}
+        assert {"medaka.models", "model_from_dict", "medaka.features", "CountsFeatureEncoder", "medaka.labels",
+                "HaploidLabelScheme", "functools", "partial"} <= strings
+        assert not any(x.startswith("medaka_b200") for x in strings)
         with datastore.ModelStoreTGZ(path) as ms:
-            assert ms.get_meta("label_scheme") == "HaploidLabelScheme"
+            assert ms.get_meta("label_scheme").symbols == "*ACGT"
+            assert ms.get_meta("feature_encoder").to_dict()["kwargs"]["normalise"] == "total"
+            assert ms.model_kwargs() == {"type": "GRUModel", "kwargs": {"num_features": 10}}
             w = ms._unpack()._weights
             assert sorted(w) == sorted(sd)
             assert np.array_equal(w["linear.bias"].numpy(), sd["linear.bias"])
+            out = os.path.join(d, "probs.npzstore")
+            ms.copy_meta(out)
+            with datastore.DataStore(out, "r") as ds:
+                assert ds.get_meta("feature_encoder").normalise == "total"
+                assert type(ds.get_meta("label_scheme")).__name__ == "HaploidLabelScheme"
+
+
+def test_reference_pickled_meta_loads(golden_dir):
+    """meta items pickled by the REAL reference classes (tests/golden/make_meta_golden.py): the v2 form (partial of
+    model_from_dict) and the legacy form (partial of build_model_torch); anything else is refused."""
+    import pickle
+    g = np.load(os.path.join(golden_dir, "ref_meta.npz"))
+    m = datastore.ref_loads(g["v2"].tobytes())
+    enc = m["feature_encoder"]
+    assert (enc.normalise, tuple(enc.dtypes), enc.min_mapq, enc.sym_indels) == ("fwd_rev", ("r9", "r10"), 3, True)
+    assert enc.feature_vector_length == 20 and enc.pileup_source is None
+    assert sorted(enc.feature_indices) == sorted([("r9", True), ("r9", False), ("r10", True), ("r10", False)])
+    assert m["label_scheme"].symbols == "*ACGT" and m["label_scheme"].num_classes == 5
+    with tempfile.TemporaryDirectory() as d:
+        for key, expect in (("v2", {"num_features": 20, "num_classes": 5, "gru_size": 128}),
+                            ("legacy", {"num_features": 10, "num_classes": 5, "gru_size": 128})):
+            ms = datastore.ModelStoreTGZ(os.path.join(d, "x.tar.gz"))
+            ms._meta = datastore.ref_loads(g[key].tobytes())
+            ms._weights = {}
+            assert ms.model_kwargs() == {"type": "GRUModel", "kwargs": expect}
+    evil = pickle.dumps(os.system)
+    with pytest.raises(pickle.UnpicklingError):
+        datastore.ref_loads(evil)
+
+
+class FakeH5(object):
+    """Stands in for the h5py module (this image has no libhdf5): records every dataset with the arguments it was
+    created with, keeps files in memory by name."""
+
+    files = {}
+
+    class _DS(object):
+        def __init__(self, data, **kw):
+            self.data, self.kw = data, kw
+
+        def __getitem__(self, key):
+            assert key == ()
+            return self.data
+
+    class _Group(object):
+        def __init__(self, store, prefix):
+            self.store, self.prefix = store, prefix
+
+        def keys(self):
+            return sorted({k[len(self.prefix):].split("/")[0] for k in self.store if k.startswith(self.prefix)})
+
+        def __iter__(self):
+            return iter(self.keys())
+
+        def __getitem__(self, k):
+            return self.store[self.prefix + k]
+
+    class File(object):
+        def __init__(self, filename, mode):
+            if mode == "w" or filename not in FakeH5.files:
+                if mode == "r":
+                    raise FileNotFoundError(filename)
+                FakeH5.files[filename] = {}
+            self.store, self.closed = FakeH5.files[filename], False
+
+        def create_dataset(self, loc, data=None, **kw):
+            assert loc not in self.store
+            self.store[loc] = FakeH5._DS(np.array(data), **kw)
+
+        def __setitem__(self, loc, value):
+            assert loc not in self.store
+            self.store[loc] = FakeH5._DS(value)
+
+        def __getitem__(self, loc):
+            if loc in self.store:
+                return self.store[loc]
+            if any(k.startswith(loc + "/") for k in self.store):
+                return FakeH5._Group(self.store, loc + "/")
+            raise KeyError(loc)
+
+        def __contains__(self, loc):
+            return loc in self.store or any(k.startswith(loc + "/") for k in self.store)
+
+        def __delitem__(self, loc):
+            del self.store[loc]
+
+        def flush(self):
+            pass
+
+        def close(self):
+            self.closed = True
+
+
+def test_hdf_backend_layout():
+    """The HDF container writes what `medaka sequence` / `medaka vcf` read (medaka/datastore.py:263-336): datasets at
+    samples/data/<name>/<field>, every ndarray field gzip-1 compressed, ref_name as a plain string, the registry and
+    the meta items as np.bytes_ pickles under samples/registry and meta/<key>; a sample is written once."""
+    import pickle
+    FakeH5.files.clear()
+    n = 30
+    s = common.Sample("ctg", None, np.full(n, 2, dtype=np.uint8), None, _positions(n, 7),
+                      np.random.rand(n, 5).astype(np.float32), np.arange(n))
+    with datastore.DataStore("out.hdf", "a", h5=FakeH5) as ds:
+        ds.set_meta(datastore.as_reference_meta({"label_scheme": "HaploidLabelScheme"})["label_scheme"], "label_scheme")
+        ds.write_sample(s)
+        ds.write_sample(s)
+        assert ds.n_samples == 1
+    store = FakeH5.files["out.hdf"]
+    base = "samples/data/{}/".format(s.name)
+    assert sorted(k[len(base):] for k in store if k.startswith(base)) == ["depth", "label_probs", "labels", "positions",
+                                                                         "ref_name"]
+    for field in ("depth", "label_probs", "labels", "positions"):
+        assert store[base + field].kw == {"compression": "gzip", "compression_opts": 1}, field
+    assert store[base + "ref_name"].kw == {} and store[base + "ref_name"].data == "ctg"
+    assert isinstance(store["samples/registry"].data, np.bytes_)
+    assert pickle.loads(store["samples/registry"].data) == {s.name}
+    blob = store["meta/label_scheme"].data
+    assert isinstance(blob, np.bytes_) and b"medaka.labels" in bytes(blob) and b"medaka_b200" not in bytes(blob)
+    with datastore.DataStore("out.hdf", "r", h5=FakeH5) as ds:
+        assert ds.sample_registry == {s.name}
+        back = ds.load_sample(s.name)
+        assert back.ref_name == "ctg" and np.array_equal(back.label_probs, s.label_probs)
+        assert np.array_equal(back.labels, s.labels) and np.array_equal(back.positions, s.positions)
+        assert type(ds.get_meta("label_scheme")).__name__ == "HaploidLabelScheme"
 
 
 WORKER = r"""

@@ -168,7 +168,8 @@ def check_rec_trace(arg):
 
 PP_SLOTS = ["issuer: H seen", "issuer: r queued", "issuer: z queued", "issuer: n queued", "relay: r arrived",
             "relay: z arrived", "relay: n arrived", "gate: r ld done", "gate: r math done", "gate: z ld done",
-            "gate: z math done", "gate: n ld done", "gate: h written", "gate: arrived H", "issuer: logits queued"]
+            "gate: z math done", "gate: n ld done", "gate: h written", "gate: arrived H", "issuer: logits queued",
+            "issuer: r guard passed", "issuer: z guard passed", "issuer: n guard passed", "issuer: logits guard passed"]
 
 
 def check_pp(arg):
@@ -270,10 +271,10 @@ def check_pp_trace(arg):
         t = buf[layer].astype(np.int64)
         out = {}
         for X in (0, 1):
-            tt = t[:, X * 20:X * 20 + 15]
+            tt = t[:, X * 20:X * 20 + 19]
             rel = tt - tt[:, :1]
             out["tile%d" % X] = {"period": float(np.median(np.diff(tt[:, 0]))),
-                                 "offsets": {PP_SLOTS[k]: float(np.median(rel[:, k])) for k in range(15)}}
+                                 "offsets": {PP_SLOTS[k]: float(np.median(rel[:, k])) for k in range(19)}}
         out["B_minus_A_h_seen"] = float(np.median(t[:, 20] - t[:, 0]))
         res["layer%d" % layer] = out
     m.close()
