@@ -55,6 +55,8 @@ extern "C" {
 #define MDK_NORM_NONE 2
 
 typedef struct mdk_engine mdk_engine;
+typedef struct mdk_bam mdk_bam;              /* an open BAM file (+ its .bai index when present) */
+typedef struct mdk_bam_batch mdk_bam_batch;  /* the records of one region, in BAM's packed encodings */
 
 /* GRUModel constructor arguments (medaka/architectures/gru.py:13-21). */
 typedef struct mdk_model_desc {
@@ -203,6 +205,33 @@ int mdk_pileup_counts(int device, int64_t n_rec, const int32_t *pos, const uint1
                       int32_t start, int32_t end, int32_t num_dtypes, int32_t min_mapq,
                       int64_t max_cols, uint64_t *counts_out, int64_t *major_out, int64_t *minor_out,
                       int64_t *n_cols_out);
+
+/* ---- alignment access: what calculate_pileup gets from htslib (create_bam_fset src/medaka_bamiter.c:52-63,
+ * bam_itr_querys src/medaka_counts.c:233, the flag / mapQ part of read_bam src/medaka_bamiter.c:19-21).  Native BGZF
+ * inflate (zlib, a thread pool over the independent members), BAI-indexed region fetch (bins + linear index; without an
+ * index the file is streamed once in bounded memory), CG-tag long CIGARs resolved like htslib does.
+ *   mdk_bam_open     index_path NULL = "<path>.bai" (or "<stem>.bai") when it exists
+ *   mdk_bam_fetch    records of reference `tid` overlapping [start, end) whose flag has none of `exclude_flags` and
+ *                    whose mapping quality is >= min_mapq, in file (coordinate) order
+ *   mdk_bam_batch_arrays   pos[n], flag[n], mapq[n], l_seq[n]; cigar[] (len << 4 | op) with cigar_off[n+1]; seq[] 4-bit
+ *                    codes with seq_off[n+1] (bytes); aux[] the raw optional fields with aux_off[n+1] (tag / read-group /
+ *                    datatype filters are the caller's); names[] with name_off[n+1].  Any pointer may be NULL.  The
+ *                    arrays live until mdk_bam_batch_free.
+ * One handle may be used from several threads (reads are serialised on it). */
+int mdk_bam_open(const char *path, const char *index_path, mdk_bam **out);
+int mdk_bam_close(mdk_bam *b);
+int mdk_bam_n_refs(mdk_bam *b);
+const char *mdk_bam_ref_name(mdk_bam *b, int i);
+int32_t mdk_bam_ref_len(mdk_bam *b, int i);
+int mdk_bam_has_index(mdk_bam *b);
+int mdk_bam_fetch(mdk_bam *b, int tid, int32_t start, int32_t end, uint32_t exclude_flags, int min_mapq, int threads,
+                  mdk_bam_batch **out);
+int64_t mdk_bam_batch_size(mdk_bam_batch *x);
+int mdk_bam_batch_arrays(mdk_bam_batch *x, const int32_t **pos, const uint16_t **flag, const uint8_t **mapq,
+                         const int32_t **l_seq, const uint32_t **cigar, const int64_t **cigar_off,
+                         const uint8_t **seq, const int64_t **seq_off, const uint8_t **aux, const int64_t **aux_off,
+                         const char **names, const int64_t **name_off);
+int mdk_bam_batch_free(mdk_bam_batch *x);
 
 /* ---- decode seam: replaces the array part of HaploidLabelScheme.decode_consensus ------------
  * (medaka/labels.py:1053-1085 with _phred :387-401): labels = argmax (first max wins),

@@ -1,19 +1,18 @@
-"""A small BAM reader (BGZF inflate + record parsing) feeding the GPU pileup-counts featuriser.
+"""BAM access for the GPU pileup-counts featuriser.
 
 The reference reads alignments through htslib (``bam_itr_querys`` / ``bam_mplp_auto``,
 src/medaka_counts.c:233-251), which is not part of its tree and not available here; the
 engine does the per-base work on the GPU instead, so the host only has to (1) inflate the
-BGZF blocks and (2) slice out, per alignment record, the fields the featuriser consumes in
-BAM's own packed encodings: 32-bit CIGAR ops (``len << 4 | op``) and 4-bit sequence codes.
-File format per the SAM/BAM specification (sections 4.1 BGZF, 4.2 BAM).
-
-``BamFile`` inflates the whole file once (zlib releases the GIL, so blocks inflate in a
-thread pool) and keeps numpy arrays of the fixed-width fields; ``fetch(ref_name, start,
-end)`` then returns the records overlapping a region (what ``bam_itr_querys`` yields) as a
-``RecordBatch`` of flat arrays ready for ``mdk_pileup_counts``.
+BGZF blocks of the requested region and (2) slice out, per alignment record, the fields the
+featuriser consumes in BAM's own packed encodings: 32-bit CIGAR ops (``len << 4 | op``) and
+4-bit sequence codes.  Both are done natively (libmedaka_b200, csrc/bam_io.cu: zlib thread
+pool, .bai index, CG-tag long CIGARs); this module wraps the result in a ``RecordBatch`` of
+flat arrays ready for ``mdk_pileup_counts`` and applies the tag-based read filters.
+``bgzf_decompress`` (whole-file inflate in Python) is kept for tests and small tools.
 """
 import collections
 import concurrent.futures
+import os
 import struct
 import zlib
 
@@ -110,118 +109,129 @@ def _passes_tag_filters(tags, tag_name, tag_value, keep_missing, read_group):
 
 
 class BamFile(object):
-    """All alignment records of a BAM file, inflated and indexed in memory."""
+    """An open BAM file: region fetches go through the native reader in libmedaka_b200 (csrc/bam_io.cu: threaded BGZF
+    inflate, BAI-indexed access, bounded memory), the counterpart of the reference's ``bam_fset`` + ``bam_itr_querys``
+    (src/medaka_bamiter.c:52-63, src/medaka_counts.c:233).  Only the records of the requested region are ever inflated.
+    """
 
-    def __init__(self, path, threads=4):
-        with open(path, "rb") as fh:
-            data = bgzf_decompress(fh.read(), threads)
-        self.data = data
-        if data[:4] != b"BAM\x01":
-            raise ValueError("{} is not a BAM file".format(path))
-        l_text = struct.unpack_from("<i", data, 4)[0]
-        off = 8 + l_text
-        n_ref = struct.unpack_from("<i", data, off)[0]
-        off += 4
-        self.references, self.lengths = [], []
-        for _ in range(n_ref):
-            l_name = struct.unpack_from("<i", data, off)[0]
-            self.references.append(data[off + 4:off + 4 + l_name - 1].decode())
-            self.lengths.append(struct.unpack_from("<i", data, off + 4 + l_name)[0])
-            off += 8 + l_name
-        # record offsets (sequential walk over block_size fields)
-        offs = []
-        n = len(data)
-        while off + 4 <= n:
-            bs = struct.unpack_from("<i", data, off)[0]
-            offs.append(off)
-            off += 4 + bs
-        self.rec_off = np.array(offs, dtype=np.int64)
-        raw = np.frombuffer(data, dtype=np.uint8)
-        self._raw = raw
+    def __init__(self, path, threads=4, index=None):
+        from medaka_b200 import libmedaka as _lm
+        self._lm = _lm
+        lib, ffi = _lm.load(), _lm.ffi
+        self.path = path
+        self.threads = int(threads)
+        pb = ffi.new("mdk_bam **")
+        _lm.check(lib.mdk_bam_open(os.fsencode(path), os.fsencode(index) if index else ffi.NULL, pb))
+        self._h = pb[0]
+        n = lib.mdk_bam_n_refs(self._h)
+        self.references = [ffi.string(lib.mdk_bam_ref_name(self._h, i)).decode() for i in range(n)]
+        self.lengths = [int(lib.mdk_bam_ref_len(self._h, i)) for i in range(n)]
+        self.has_index = bool(lib.mdk_bam_has_index(self._h))
 
-        def field(delta, dtype):
-            width = np.dtype(dtype).itemsize
-            idx = self.rec_off[:, None] + delta + np.arange(width)[None, :]
-            return raw[idx].copy().view(dtype).reshape(-1)
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lm.lib.mdk_bam_close(self._h)
+            self._h = None
 
-        self.block_size = field(0, "<i4")
-        self.ref_id = field(4, "<i4")
-        self.pos = field(8, "<i4")
-        self.l_read_name = field(12, "u1").astype(np.int64)
-        self.mapq = field(13, "u1")
-        self.n_cigar = field(16, "<u2").astype(np.int64)
-        self.flag = field(18, "<u2")
-        self.l_seq = field(20, "<i4").astype(np.int64)
-        self.cigar_start = self.rec_off + 36 + self.l_read_name
-        self.seq_start = self.cigar_start + 4 * self.n_cigar
-        self.qual_start = self.seq_start + (self.l_seq + 1) // 2
-        self.tag_start = self.qual_start + self.l_seq
-        self.rec_end = self.rec_off + 4 + self.block_size
-        # reference end of every record from its CIGAR (vectorised)
-        total_ops = int(self.n_cigar.sum())
-        op_rec = np.repeat(np.arange(len(offs)), self.n_cigar)
-        first = np.cumsum(self.n_cigar) - self.n_cigar
-        op_idx = np.arange(total_ops) - np.repeat(first, self.n_cigar)
-        op_addr = self.cigar_start[op_rec] + 4 * op_idx
-        ops = raw[op_addr[:, None] + np.arange(4)[None, :]].copy().view("<u4").reshape(-1)
-        ref_len = np.zeros(len(offs), dtype=np.int64)
-        np.add.at(ref_len, op_rec, (ops >> 4).astype(np.int64) * _CONSUMES_REF[ops & 0xF])
-        self.end = self.pos.astype(np.int64) + ref_len
-        self._ops = ops
-        self._op_first = first
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *args):
+        self.close()
 
     def get_regions(self):
         """(name, length) of every reference sequence - what get_bam_regions needs (medaka/common.py:762-790)."""
         return list(zip(self.references, self.lengths))
 
-    def name(self, i):
-        s = int(self.rec_off[i]) + 36
-        return self.data[s:s + int(self.l_read_name[i]) - 1].decode()
-
-    def tags(self, i):
-        return _parse_tags(self.data[int(self.tag_start[i]):int(self.rec_end[i])])
-
     def fetch(self, ref_name, start, end, dtypes=None, tag_name=None, tag_value=None, keep_missing=False,
-              read_group=None, with_names=False):
-        """Records overlapping [start, end) on ref_name, with the tag-based read filters of
-        src/medaka_bamiter.c:24-44 applied on the host (flag / mapq filters run on the device)."""
+              read_group=None, with_names=False, min_mapq=0, exclude_flags=FILTER_FLAGS):
+        """Records overlapping [start, end) on ref_name that pass the read filter of src/medaka_bamiter.c:17-45, in the
+        reference's order: flag and mapping quality first (native, before anything is parsed), then the tag, read-group
+        and datatype tests on the survivors' aux fields."""
+        lm = self._lm
+        lib, ffi = lm.lib, lm.ffi
         tid = self.references.index(ref_name)
-        sel = np.flatnonzero((self.ref_id == tid) & (self.pos < end) & (self.end > start) &
-                             ((self.flag & 0x4) == 0))
+        if start is None:
+            start = 0
+        if end is None:
+            end = self.lengths[tid]
+        pbatch = ffi.new("mdk_bam_batch **")
+        lm.check(lib.mdk_bam_fetch(self._h, tid, int(start), int(end), int(exclude_flags), int(min_mapq), self.threads,
+                                   pbatch))
+        batch = pbatch[0]
+        try:
+            n = int(lib.mdk_bam_batch_size(batch))
+            ptrs = {k: ffi.new(t) for k, t in (
+                ("pos", "const int32_t **"), ("flag", "const uint16_t **"), ("mapq", "const uint8_t **"),
+                ("l_seq", "const int32_t **"), ("cigar", "const uint32_t **"), ("cigar_off", "const int64_t **"),
+                ("seq", "const uint8_t **"), ("seq_off", "const int64_t **"), ("aux", "const uint8_t **"),
+                ("aux_off", "const int64_t **"), ("names", "const char **"), ("name_off", "const int64_t **"))}
+            lm.check(lib.mdk_bam_batch_arrays(batch, *[ptrs[k] for k in (
+                "pos", "flag", "mapq", "l_seq", "cigar", "cigar_off", "seq", "seq_off", "aux", "aux_off", "names",
+                "name_off")]))
+
+            def arr(key, dtype, count):
+                if count == 0:
+                    return np.zeros(0, dtype=dtype)
+                return np.frombuffer(ffi.buffer(ptrs[key][0], count * np.dtype(dtype).itemsize), dtype=dtype).copy()
+
+            cigar_off = arr("cigar_off", np.int64, n + 1)
+            seq_off = arr("seq_off", np.int64, n + 1)
+            aux_off = arr("aux_off", np.int64, n + 1)
+            name_off = arr("name_off", np.int64, n + 1)
+            pos, flag, mapq = arr("pos", np.int32, n), arr("flag", np.uint16, n), arr("mapq", np.uint8, n)
+            l_seq = arr("l_seq", np.int32, n)
+            cigar = arr("cigar", np.uint32, int(cigar_off[-1]))
+            seq = arr("seq", np.uint8, int(seq_off[-1]))
+            aux = bytes(ffi.buffer(ptrs["aux"][0], int(aux_off[-1]))) if n and aux_off[-1] else b""
+            names_raw = bytes(ffi.buffer(ptrs["names"][0], int(name_off[-1]))) if n and name_off[-1] else b""
+        finally:
+            lib.mdk_bam_batch_free(batch)
+
+        def name(i):
+            return names_raw[int(name_off[i]):int(name_off[i + 1])].decode()
+
         need_tags = bool(tag_name) or read_group is not None or (dtypes is not None and len(dtypes) > 1)
-        dtype = np.zeros(len(sel), dtype=np.uint8)
+        dtype = np.zeros(n, dtype=np.uint8)
         tags_out = None
+        keep = np.ones(n, dtype=bool)
         if need_tags:
-            keep = np.ones(len(sel), dtype=bool)
             tags_out = []
-            for k, i in enumerate(sel):
-                tg = self.tags(i)
+            for i in range(n):
+                tg = _parse_tags(aux[int(aux_off[i]):int(aux_off[i + 1])])
                 tags_out.append(tg)
-                keep[k] = _passes_tag_filters(tg, tag_name, tag_value, keep_missing, read_group)
-                if keep[k] and dtypes is not None and len(dtypes) > 1:
+                keep[i] = _passes_tag_filters(tg, tag_name, tag_value, keep_missing, read_group)
+                if keep[i] and dtypes is not None and len(dtypes) > 1:
                     if tg.get("DT") not in dtypes:
-                        raise ValueError("Datatype not found for {}.".format(self.name(i)))
-                    dtype[k] = list(dtypes).index(tg["DT"])
-            sel, dtype = sel[keep], dtype[keep]
+                        raise ValueError("Datatype not found for {}.".format(name(i)))
+                    dtype[i] = list(dtypes).index(tg["DT"])
             tags_out = [t for t, k in zip(tags_out, keep) if k]
-        n_cig = self.n_cigar[sel]
-        cigar_off = np.zeros(len(sel) + 1, dtype=np.int64)
-        np.cumsum(n_cig, out=cigar_off[1:])
-        op_rec = np.repeat(np.arange(len(sel)), n_cig)
-        op_idx = np.arange(int(cigar_off[-1])) - np.repeat(cigar_off[:-1], n_cig)
-        cigar = self._ops[self._op_first[sel][op_rec] + op_idx] if len(sel) else np.zeros(0, dtype="<u4")
-        seq_bytes = (self.l_seq[sel] + 1) // 2
-        seq_off = np.zeros(len(sel) + 1, dtype=np.int64)
-        np.cumsum(seq_bytes, out=seq_off[1:])
-        b_rec = np.repeat(np.arange(len(sel)), seq_bytes)
-        b_idx = np.arange(int(seq_off[-1])) - np.repeat(seq_off[:-1], seq_bytes)
-        seq = self._raw[self.seq_start[sel][b_rec] + b_idx] if len(sel) else np.zeros(0, dtype=np.uint8)
-        names = [self.name(i) for i in sel] if with_names else None
-        return RecordBatch(pos=self.pos[sel].astype(np.int32), flag=self.flag[sel].astype(np.uint16),
-                           mapq=self.mapq[sel].astype(np.uint8), dtype=dtype,
-                           cigar=np.ascontiguousarray(cigar, dtype=np.uint32), cigar_off=cigar_off,
-                           seq=np.ascontiguousarray(seq, dtype=np.uint8), seq_off=seq_off,
-                           l_seq=self.l_seq[sel].astype(np.int32), names=names, tags=tags_out)
+        if not keep.all():
+            sel = np.flatnonzero(keep)
+            n_cig = (cigar_off[1:] - cigar_off[:-1])[sel]
+            new_coff = np.zeros(len(sel) + 1, dtype=np.int64)
+            np.cumsum(n_cig, out=new_coff[1:])
+            op_idx = np.arange(int(new_coff[-1])) - np.repeat(new_coff[:-1], n_cig) + np.repeat(cigar_off[:-1][sel], n_cig)
+            cigar = cigar[op_idx] if len(op_idx) else np.zeros(0, dtype=np.uint32)
+            n_sb = (seq_off[1:] - seq_off[:-1])[sel]
+            new_soff = np.zeros(len(sel) + 1, dtype=np.int64)
+            np.cumsum(n_sb, out=new_soff[1:])
+            b_idx = np.arange(int(new_soff[-1])) - np.repeat(new_soff[:-1], n_sb) + np.repeat(seq_off[:-1][sel], n_sb)
+            seq = seq[b_idx] if len(b_idx) else np.zeros(0, dtype=np.uint8)
+            names = [name(i) for i in sel] if with_names else None
+            pos, flag, mapq, l_seq, dtype = pos[sel], flag[sel], mapq[sel], l_seq[sel], dtype[sel]
+            cigar_off, seq_off = new_coff, new_soff
+        else:
+            names = [name(i) for i in range(n)] if with_names else None
+        return RecordBatch(pos=pos, flag=flag, mapq=mapq, dtype=dtype, cigar=np.ascontiguousarray(cigar, dtype=np.uint32),
+                           cigar_off=cigar_off, seq=np.ascontiguousarray(seq, dtype=np.uint8), seq_off=seq_off,
+                           l_seq=l_seq, names=names, tags=tags_out)
 
 
 def records_from_dicts(records, dtypes=None):

@@ -11,13 +11,22 @@
 //
 //   warps 0-7    gate warps of tile A   (warp w: TMEM lane quarter w % 4, windows (w / 4) * 8 .. + 7: 8 windows / thread)
 //   warps 8-15   gate warps of tile B
-//   warp 16, 17  MMA issuer of tile A / B (one elected thread each)
-//   warp 18, 19  relay of tile A / B: the only waiter on that tile's commit mbarriers; releases the gate warps through
+//   warp 17, 18  MMA issuers of tile A / B for the r and n blocks (one elected thread each)
+//   warp 19, 20  MMA issuers of tile A / B for the z block and (layer 1) the logits.  Two issuers per tile because issue is
+//                what limits the MMA phase here: an MMA costs ~7 issue slots of descriptor arithmetic (ptxas routes the
+//                operands through vector registers and R2UR), and unlike in the one-tile kernel the issuer shares its
+//                scheduler with gate warps of the OTHER tile that are busy - measured 21 cycles per MMA from one issuer
+//                against 9.75 on the tensor pipe (profiles/r02_pp_bringup.md).  Blocks are never split between warps, so
+//                "first MMA of a block overwrites the accumulator" stays well defined.
+//   warp 21, 22  relay of tile A / B: the only waiter on that tile's commit mbarriers; releases the gate warps through
 //                named hardware barriers (a blocked mbarrier.try_wait of 8 warps costs 100-250 cycles more than one
 //                bar.sync, measured in round 1); in its idle time it stages the next pre-activation block (layer 1: one
-//                24 KiB bulk copy into shared memory, two steps ahead) or copies the published h tile to HBM (layer 0: the
-//                tile already is the operand-tile image the projection GEMM wants) and prefetches L2
-//   warp 20      (layer 1) reads the 5 x 16 partial logits out of tensor memory and writes them
+//                24 KiB bulk copy into shared memory, two steps ahead) and prefetches L2
+//   warp 16      (layer 1) reads the 5 x 16 partial logits out of tensor memory and writes them
+//   warp 16, 21  (layer 0) copy warp of tile A / B: moves the published h tile - which already is the operand-tile image
+//                the projection GEMM wants - to HBM with 16-byte loads and stores.  (Round 2, first cut: 32 bulk copies
+//                of 256 B per tile-step from the relay; the copy engine became the limiter of the whole kernel at
+//                ~70 cycles per small copy, 4 800 cycles per pair of tile-steps: profiles/r02_pp_bringup.md)
 //
 // Tensor memory (512 columns, all of it):  W_hh fp16 hi|lo as the A operand [0, 384);
 //   layer 0:  W_ih (K = 16) hi|lo [384, 432);  accumulators r, z, n, W_in.x [432, 496)
@@ -50,11 +59,19 @@ namespace mdk {
 
 constexpr int PP_TILE_WARPS = 8;
 constexpr int PP_GATE_WARPS = 2 * PP_TILE_WARPS;
-constexpr int PP_W_ISS = 16, PP_W_REL = 18, PP_W_LOG = 20;
-constexpr int PP_WARPS = 21;
-constexpr int PP_THREADS = 32 * PP_WARPS;                 // 672 -> at most 96 registers per thread
+// service warps.  Warp 16 must be the one that reads the logits (tcgen05.ld reaches TMEM lanes 32 * (warp % 4) ..., the
+// classes sit in lanes 0..4); the two issuers - the only service warps with real instruction streams - get a scheduler
+// each that they share with nobody but gate warps (scheduler = warp % 4)
+constexpr int PP_W_AUX0 = 16;     // layer 1: logits warp; tiles out: copy warp of tile A
+constexpr int PP_W_ISS = 17;      // 17, 18: issuers (r and n blocks) of tile A / B; 19, 20: issuers (z block, logits) of A / B
+constexpr int PP_W_REL = 21;      // 21, 22: relay of tile A / B
+constexpr int PP_W_AUX1 = 23;     // tiles out: copy warp of tile B
+constexpr int PP_WARPS = 24;
+constexpr int PP_THREADS = 32 * PP_WARPS;                 // 768 -> at most 80 registers per thread
 constexpr int PP_BAR_H = 1, PP_BAR_R = 3, PP_BAR_Z = 5, PP_BAR_N = 7, PP_BAR_FIN = 9;   // + X
-constexpr int PP_NB = 32 * (PP_TILE_WARPS + 1);           // threads on every named barrier
+constexpr int PP_NB = 32 * (PP_TILE_WARPS + 1);           // 8 gate warps + 1 service warp
+constexpr int PP_NB2 = 32 * (PP_TILE_WARPS + 2);          // 8 gate warps + 2 service warps
+constexpr int PP_NB3 = 32 * (PP_TILE_WARPS + 3);          // 8 gate warps + 3 service warps
 constexpr int PP_GI_BUFS = 3;
 constexpr int PP_GI_BLOCK = (GI_TS_FLOATS / 2) * 4;       // one (tile-step, direction) of gi: 24 576 bytes
 constexpr int PP_WL_PLANE = 16 * 64 * 16;                 // W_lin lo plane as an M = 64 shared-memory A operand: 16 KiB
@@ -118,7 +135,7 @@ __device__ __forceinline__ unsigned long long *pp_trace_row(const PPArgs &a, int
 
 // ------------------------------------------------------------------------------------------------ issuer of tile X
 template <int LAYER, bool ALLP, bool TRACE>
-__device__ __noinline__ void pp_issuer(uint8_t *smem, const PPArgs &a, const int X) {
+__device__ __noinline__ void pp_issuer(uint8_t *smem, const PPArgs &a, const int X, const int role) {
     using L = PPCfg<LAYER>;
     constexpr bool IN_X = L::IN_X, OUT_LOG = L::OUT_LOG;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::bar_off);
@@ -129,14 +146,16 @@ __device__ __noinline__ void pp_issuer(uint8_t *smem, const PPArgs &a, const int
     // base, issue predicated by elect.sync (otherwise every tcgen05.mma is wrapped in an R2UR waterfall loop).
     const uint32_t idesc = make_idesc_f16(128, RT_N);
     const uint32_t idesc64 = make_idesc_f16(64, RT_N);
-    const uint64_t hdesc0 = make_smem_desc(smem_u32(smem + L::h_off + X * 4 * RT_HPLANE), RT_KG, 128);
-    const uint64_t xdesc0 = make_smem_desc(smem_u32(smem + L::x_off + X * 2 * RT_XBUF), RT_KG, 128);
-    const uint64_t wldesc0 = make_smem_desc(smem_u32(smem + L::wl_off), 64 * 16, 128);
+    // descriptors as (low word, high word): only the address field of the low word moves (ptx.cuh umma_f16_ts2)
+    const uint32_t d_hi = smem_desc_hi(128);
+    const uint32_t h_lo0 = smem_desc_lo(smem_u32(smem + L::h_off), RT_KG) + (uint32_t)X * ((4 * RT_HPLANE) >> 4);
+    const uint32_t x_lo0 = smem_desc_lo(smem_u32(smem + L::x_off), RT_KG) + (uint32_t)X * ((2 * RT_XBUF) >> 4);
+    const uint32_t wl_lo0 = smem_desc_lo(smem_u32(smem + L::wl_off), 64 * 16);
     const uint32_t mask = ALLP ? 7u : a.prod_mask;
     const int64_t T = a.T;
 
     // W_hh[gate] . h (tile buffer hd), the selected fp16 products, into accumulator columns d; returns the accumulate flag
-    auto issue_h = [&](uint32_t d, int gate, uint64_t hd, uint32_t accf) -> uint32_t {
+    auto issue_h = [&](uint32_t d, int gate, uint32_t hd, uint32_t accf) -> uint32_t {
 #pragma unroll
         for (int prod = 0; prod < 3; ++prod) {
             if (!ALLP && !(mask & (1u << prod))) continue;
@@ -144,28 +163,28 @@ __device__ __noinline__ void pp_issuer(uint8_t *smem, const PPArgs &a, const int
             const int pb = (prod == 1) ? 1 : 0;   // h part: hi, lo, hi
 #pragma unroll
             for (int ks = 0; ks < H / 16; ++ks) {
-                umma_f16_ts(d, (uint32_t)(((pa * 3 + gate) * 8 + ks) * 8),
-                            hd + (uint64_t)((pb * RT_HPLANE + ks * 2 * RT_KG) >> 4), idesc, accf);
+                umma_f16_ts2(d, (uint32_t)(((pa * 3 + gate) * 8 + ks) * 8),
+                             hd + (uint32_t)((pb * RT_HPLANE + ks * 2 * RT_KG) >> 4), d_hi, idesc, accf);
                 accf = 1u;
             }
         }
         return accf;
     };
     // + W_ih[gate] . x_t (layer 0)
-    auto issue_x = [&](uint32_t d, int gate, uint64_t xd, uint32_t accf) -> uint32_t {
+    auto issue_x = [&](uint32_t d, int gate, uint32_t xd, uint32_t accf) -> uint32_t {
 #pragma unroll
         for (int prod = 0; prod < 3; ++prod) {
             if (!ALLP && !(mask & (1u << prod))) continue;
             const int pa = (prod == 2) ? 1 : 0;
             const int pb = (prod == 1) ? 1 : 0;
-            umma_f16_ts(d, L::wx_col + (uint32_t)((pa * 3 + gate) * 8), xd + (uint64_t)((pb * RT_XPLANE) >> 4), idesc, accf);
+            umma_f16_ts2(d, L::wx_col + (uint32_t)((pa * 3 + gate) * 8), xd + (uint32_t)((pb * RT_XPLANE) >> 4), d_hi, idesc, accf);
             accf = 1u;
         }
         return accf;
     };
     // partial logits of the h in tile buffer hd: W_lin hi plane from tensor memory (M = 128, rows >= 5 zero), lo plane
     // from shared memory (M = 64: rows 0..4 land in the same TMEM lanes)
-    auto issue_logits = [&](uint64_t hd) {
+    auto issue_logits = [&](uint32_t hd) {
         uint32_t accf = 0u;
 #pragma unroll
         for (int prod = 0; prod < 3; ++prod) {
@@ -173,71 +192,76 @@ __device__ __noinline__ void pp_issuer(uint8_t *smem, const PPArgs &a, const int
             const int pb = (prod == 1) ? 1 : 0;
 #pragma unroll
             for (int ks = 0; ks < H / 16; ++ks) {
-                const uint64_t bd = hd + (uint64_t)((pb * RT_HPLANE + ks * 2 * RT_KG) >> 4);
-                if (prod != 2) umma_f16_ts(L::log_col, L::wl_col + (uint32_t)(ks * 8), bd, idesc, accf);
-                else umma_f16(L::log_col, wldesc0 + (uint64_t)((ks * 2 * (64 * 16)) >> 4), bd, idesc64, accf);
+                const uint32_t bd = hd + (uint32_t)((pb * RT_HPLANE + ks * 2 * RT_KG) >> 4);
+                if (prod != 2) umma_f16_ts2(L::log_col, L::wl_col + (uint32_t)(ks * 8), bd, d_hi, idesc, accf);
+                else umma_f16_ss2(L::log_col, wl_lo0 + (uint32_t)((ks * 2 * (64 * 16)) >> 4), d_hi, bd, d_hi, idesc64, accf);
                 accf = 1u;
             }
         }
         umma_commit(log_full);
     };
 
+    // role 0: the r block (with the n gate's W_in.x, layer 0) and the n block; role 1: the z block and the logits
+    constexpr int NB_H = OUT_LOG ? PP_NB2 : PP_NB3;      // H_X: 8 gate warps + 2 issuers (+ the copy warp when tiles go out)
 #pragma unroll 1
     for (int64_t s = 0; s < T; ++s) {
         const uint32_t par = (uint32_t)(s & 1);
         unsigned long long *tr = pp_trace_row<TRACE>(a, s, true);
-        named_bar_sync_id<PP_NB>(PP_BAR_H + X);
+        named_bar_sync_id<NB_H>(PP_BAR_H + X);
         tc_fence_after_sync();
         if (elect_one()) {
-            PP_STAMP(X * 20 + 0);
-            const uint64_t hd = hdesc0 + (uint64_t)((par * 2 * RT_HPLANE) >> 4);
-            const uint64_t xd = xdesc0 + (uint64_t)((par * RT_XBUF) >> 4);
+            const uint32_t hd = h_lo0 + par * ((2 * RT_HPLANE) >> 4);
+            const uint32_t xd = x_lo0 + par * (RT_XBUF >> 4);
             // the use just before this one was the other tile's: B's of step s-1 for A, A's of step s for B
             const bool guard = (X == 1) || s > 0;          // the very first use of the accumulators needs no hand-over
             const uint32_t gpar = (uint32_t)((X == 0 ? s - 1 : s) & 1);
-            if (guard) mbar_wait(&free_acc[0], gpar);
-            PP_STAMP(X * 20 + 15);
-            tc_fence_after_sync();
-            if (IN_X) issue_x(L::acc_col + 48, 2, xd, 0u);   // W_in . x of the n gate keeps its own columns
-            {
-                const uint32_t f = issue_h(L::acc_col + 0, 0, hd, 0u);
-                if (IN_X) issue_x(L::acc_col + 0, 0, xd, f);
-            }
-            umma_commit(&acc[0]);
-            PP_STAMP(X * 20 + 1);
-            if (guard) mbar_wait(&free_acc[1], gpar);
-            PP_STAMP(X * 20 + 16);
-            tc_fence_after_sync();
-            {
-                const uint32_t f = issue_h(L::acc_col + 16, 1, hd, 0u);
-                if (IN_X) issue_x(L::acc_col + 16, 1, xd, f);
-            }
-            umma_commit(&acc[1]);
-            PP_STAMP(X * 20 + 2);
-            if (guard) mbar_wait(&free_acc[2], gpar);
-            PP_STAMP(X * 20 + 17);
-            tc_fence_after_sync();
-            issue_h(L::acc_col + 32, 2, hd, 0u);
-            umma_commit(&acc[2]);
-            PP_STAMP(X * 20 + 3);
-            if (OUT_LOG && s > 0) {
-                // the tile buffer holds h of the previous step: its logits ride in the shadow of the gate phase
-                // this tile's logits use k = s - 1 follows B's use k-1 (tile A) / A's use k (tile B)
-                if (X == 1 || s > 1) mbar_wait(log_free, (uint32_t)((X == 0 ? s - 2 : s - 1) & 1));
-                PP_STAMP(X * 20 + 18);
+            if (role == 0) {
+                PP_STAMP(X * 20 + 0);
+                if (guard) mbar_wait(&free_acc[0], gpar);
+                PP_STAMP(X * 20 + 15);
                 tc_fence_after_sync();
-                issue_logits(hd);
-                PP_STAMP(X * 20 + 14);
+                if (IN_X) issue_x(L::acc_col + 48, 2, xd, 0u);   // W_in . x of the n gate keeps its own columns
+                {
+                    const uint32_t f = issue_h(L::acc_col + 0, 0, hd, 0u);
+                    if (IN_X) issue_x(L::acc_col + 0, 0, xd, f);
+                }
+                umma_commit(&acc[0]);
+                PP_STAMP(X * 20 + 1);
+                if (guard) mbar_wait(&free_acc[2], gpar);
+                PP_STAMP(X * 20 + 17);
+                tc_fence_after_sync();
+                issue_h(L::acc_col + 32, 2, hd, 0u);
+                umma_commit(&acc[2]);
+                PP_STAMP(X * 20 + 3);
+            } else {
+                if (guard) mbar_wait(&free_acc[1], gpar);
+                PP_STAMP(X * 20 + 16);
+                tc_fence_after_sync();
+                {
+                    const uint32_t f = issue_h(L::acc_col + 16, 1, hd, 0u);
+                    if (IN_X) issue_x(L::acc_col + 16, 1, xd, f);
+                }
+                umma_commit(&acc[1]);
+                PP_STAMP(X * 20 + 2);
+                if (OUT_LOG && s > 0) {
+                    // the tile buffer holds h of the previous step: its logits ride in the shadow of the gate phase
+                    // this tile's logits use k = s - 1 follows B's use k-1 (tile A) / A's use k (tile B)
+                    if (X == 1 || s > 1) mbar_wait(log_free, (uint32_t)((X == 0 ? s - 2 : s - 1) & 1));
+                    PP_STAMP(X * 20 + 18);
+                    tc_fence_after_sync();
+                    issue_logits(hd);
+                    PP_STAMP(X * 20 + 14);
+                }
             }
         }
         __syncwarp();
     }
-    if (OUT_LOG) {
+    if (OUT_LOG && role == 1) {
         // h of the last step: every gate warp of the tile has published it (FIN_X), one more round of logits MMAs
         named_bar_sync_id<PP_NB>(PP_BAR_FIN + X);
         tc_fence_after_sync();
         if (elect_one()) {
-            const uint64_t hd = hdesc0 + (uint64_t)(((uint32_t)(T & 1) * 2 * RT_HPLANE) >> 4);
+            const uint32_t hd = h_lo0 + (uint32_t)(T & 1) * ((2 * RT_HPLANE) >> 4);
             if (X == 1 || T > 1) mbar_wait(log_free, (uint32_t)((X == 0 ? T - 2 : T - 1) & 1));   // use k = T - 1
             tc_fence_after_sync();
             issue_logits(hd);
@@ -288,20 +312,6 @@ __device__ __noinline__ void pp_relay(uint8_t *smem, const PPArgs &a, const int 
             bulk_prefetch_l2(reinterpret_cast<const void *>(p0), (uint32_t)(((p + nbytes - p0) + 15) & ~(uintptr_t)15));
         }
     };
-    // layer 0: h of time index `sidx` (in processing order) sits in tile buffer `buf` -> its 16 rows of the GEMM's operand tiles
-    auto copy_out = [&](int64_t sidx, int buf) {
-        const int64_t orow = (tile * T + (dir ? (T - 1 - sidx) : sidx)) * WT;
-        uint8_t *dst = reinterpret_cast<uint8_t *>(a.h_out) + (orow >> 7) * (int64_t)XT_TILE_BYTES +
-                       (int64_t)(dir * (H / 8)) * (XT_ROWS * 16) + (orow & (XT_ROWS - 1)) * 16;
-        const uint8_t *src = smem + L::h_off + (X * 2 + buf) * 2 * RT_HPLANE;
-#pragma unroll
-        for (int plane = 0; plane < 2; ++plane)
-#pragma unroll 4
-            for (int kg = 0; kg < H / 8; ++kg)
-                bulk_s2g(dst + plane * XT_PLANE_BYTES + kg * (XT_ROWS * 16), src + plane * RT_HPLANE + kg * RT_KG, WT * 16);
-        bulk_commit_group();
-    };
-
     if (!IN_X && lead && tile_ok) {
         stage_gi(0);
         if (T > 1) stage_gi(1);
@@ -325,15 +335,12 @@ __device__ __noinline__ void pp_relay(uint8_t *smem, const PPArgs &a, const int 
         tc_fence_before_sync();
         named_bar_arrive_id<PP_NB>(PP_BAR_Z + X);
         PP_STAMP(X * 20 + 5);
-        if (lead) {
-            mbar_wait(&acc[2], par);
-            // tiles out: the copy issued a step ago read the buffer the gate warps overwrite after this barrier
-            if (!OUT_LOG) bulk_wait_read_all();
-        }
+        if (lead) mbar_wait(&acc[2], par);
         __syncwarp();
         tc_fence_after_sync();
         tc_fence_before_sync();
-        named_bar_arrive_id<PP_NB>(PP_BAR_N + X);
+        if (OUT_LOG) named_bar_arrive_id<PP_NB>(PP_BAR_N + X);
+        else named_bar_arrive_id<PP_NB2>(PP_BAR_N + X);
         PP_STAMP(X * 20 + 6);
         // ---- idle until the next commit: staging / copy-out / prefetch (one thread) ----
         if (lead && tile_ok) {
@@ -343,26 +350,59 @@ __device__ __noinline__ void pp_relay(uint8_t *smem, const PPArgs &a, const int 
                 if (s + 2 < T) stage_gi(s + 2);
                 if (s + 2 + GI_PREFETCH_STEPS < T) prefetch_gi(s + 2 + GI_PREFETCH_STEPS);
             }
-            if (!OUT_LOG && s > 0) {
-                // all MMAs of step s are done, so buffer `par` (h of step s-1, published through H_X(s)) is only read by
-                // this copy until the gate warps overwrite it in the tail of step s+1, i.e. after N_X(s+1) above
-                fence_proxy_async_smem();
-                copy_out(s - 1, (int)par);
-            }
             if (IN_X) prefetch_x(s);
         }
         __syncwarp();
     }
-    if (!OUT_LOG) {
-        // h of the last step: published through FIN_X
-        named_bar_sync_id<PP_NB>(PP_BAR_FIN + X);
-        if (lead && tile_ok) {
-            fence_proxy_async_smem();
-            copy_out(T - 1, (int)(T & 1));
-            bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------ copy warp of tile X
+// Tiles out (layer 0): the h tile the gate warps publish is the K-major operand image the projection GEMM reads
+// ([plane][k-group 16][16 windows][8 halfs]); per (plane, k-group) its 256 bytes are contiguous in the GEMM's operand
+// tile in HBM.  One warp moves the 8 KiB with 16-byte accesses: two 256-byte chunks per warp-wide instruction.
+// It takes part in H_X (it may read the buffer the gate warps have just published) and in N_X of the same step (it
+// arrives once its loads are in registers: the buffer it read is only overwritten after N_X of the NEXT step, which
+// needs this warp's next arrival).
+template <int LAYER>
+__device__ __noinline__ void pp_copy(uint8_t *smem, const PPArgs &a, const int X, int lane) {
+    using L = PPCfg<LAYER>;
+    const int dir = blockIdx.y;
+    const int64_t T = a.T;
+    const int64_t tile = (int64_t)blockIdx.x * 2 + X;
+    const bool tile_ok = tile < a.ntiles;
+    const int half = lane >> 4, l16 = lane & 15;
+    auto copy = [&](int64_t sidx, int buf, bool arrive) {
+        const int64_t orow = (tile * T + (dir ? (T - 1 - sidx) : sidx)) * WT;
+        uint8_t *dst = reinterpret_cast<uint8_t *>(a.h_out) + (orow >> 7) * (int64_t)XT_TILE_BYTES +
+                       (int64_t)(dir * (H / 8)) * (XT_ROWS * 16) + (orow & (XT_ROWS - 1)) * 16 + l16 * 16;
+        const uint8_t *src = smem + L::h_off + (X * 2 + buf) * 2 * RT_HPLANE + l16 * 16;
+        // two batches of eight 16-byte accesses per lane (32 registers in flight); chunk c: plane = c / 16, k-group = c % 16
+#pragma unroll
+        for (int b8 = 0; b8 < 2; ++b8) {
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = (b8 * 8 + i) * 2 + half;
+                v[i] = *reinterpret_cast<const uint4 *>(src + (c >> 4) * RT_HPLANE + (c & 15) * RT_KG);
+            }
+            if (b8 == 1 && arrive) named_bar_arrive_id<PP_NB2>(PP_BAR_N + X);     // every load has been issued ...
+            if (tile_ok) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {                                      // ... and is complete before its store
+                    const int c = (b8 * 8 + i) * 2 + half;
+                    *reinterpret_cast<uint4 *>(dst + (c >> 4) * XT_PLANE_BYTES + (c & 15) * (XT_ROWS * 16)) = v[i];
+                }
+            }
         }
-        __syncwarp();
+    };
+#pragma unroll 1
+    for (int64_t s = 0; s < T; ++s) {
+        named_bar_sync_id<PP_NB3>(PP_BAR_H + X);
+        if (s > 0) copy(s - 1, (int)(s & 1), true);
+        else named_bar_arrive_id<PP_NB2>(PP_BAR_N + X);
     }
+    named_bar_sync_id<PP_NB>(PP_BAR_FIN + X);        // h of the last step
+    copy(T - 1, (int)(T & 1), false);
 }
 
 // ------------------------------------------------------------------------------------------------ logits warp (layer 1)
@@ -380,7 +420,7 @@ __device__ __noinline__ void pp_logits(uint8_t *smem, const PPArgs &a, int lane)
         mbar_wait_warp(log_full, (uint32_t)(v & 1));
         tc_fence_after_sync();
         uint32_t r[16];
-        tmem_ld_x16(L::log_col, r);           // this warp (20 % 4 == 0) reads TMEM lanes 0..31; lanes 0..4 = classes
+        tmem_ld_x16(L::log_col, r);           // this warp (16 % 4 == 0) reads TMEM lanes 0..31; lanes 0..4 = classes
         tmem_ld_wait();
         tc_fence_before_sync();
         __syncwarp();
@@ -458,10 +498,13 @@ __device__ __noinline__ void pp_gate(uint8_t *smem, const PPArgs &a, const int X
 #pragma unroll
     for (int p = 0; p < NP; ++p) hprev2[p] = f2_make(0.f, 0.f);
 
+    // H_X: 8 gate warps + 2 issuers; N_X: 8 gate warps + relay; both + the tile's copy warp when tiles go out
+    constexpr int NB_H = L::OUT_LOG ? PP_NB2 : PP_NB3;
+    constexpr int NB_HN = L::OUT_LOG ? PP_NB : PP_NB2;
     // h_{-1} = 0 (zeroed tile) and x_0 are in shared memory: publish
     fence_proxy_async_smem();
     tc_fence_before_sync();
-    named_bar_arrive_id<PP_NB>(PP_BAR_H + X);
+    named_bar_arrive_id<NB_H>(PP_BAR_H + X);
 
 #pragma unroll 1
     for (int64_t s = 0; s < T; ++s) {
@@ -546,7 +589,7 @@ __device__ __noinline__ void pp_gate(uint8_t *smem, const PPArgs &a, const int X
         // ---------------- n, h ----------------
         {
             uint32_t an[8];
-            named_bar_sync_id<PP_NB>(PP_BAR_N + X);
+            named_bar_sync_id<NB_HN>(PP_BAR_N + X);
             tc_fence_after_sync();
             tmem_ld_x8(t_lane + 32, an);
             tmem_ld_wait();
@@ -590,7 +633,7 @@ __device__ __noinline__ void pp_gate(uint8_t *smem, const PPArgs &a, const int X
             PP_STAMP(X * 20 + 12);
             fence_proxy_async_smem();     // h / x tile writes -> visible to the MMAs' (and the bulk copy's) async-proxy reads
             tc_fence_before_sync();
-            if (s + 1 < T) named_bar_arrive_id<PP_NB>(PP_BAR_H + X);
+            if (s + 1 < T) named_bar_arrive_id<NB_H>(PP_BAR_H + X);
             else named_bar_arrive_id<PP_NB>(PP_BAR_FIN + X);
             PP_STAMP(X * 20 + 13);
         }
@@ -610,7 +653,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) rec_pp_kernel(const __grid_cons
     constexpr bool IN_X = L::IN_X, OUT_LOG = L::OUT_LOG;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + L::bar_off);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + L::tmem_off);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // (broadcast from lane 0: tells the compiler the warp index is warp-uniform, so that everything derived from it -
+    // the tile index, shared-memory descriptors - can live in uniform registers)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int dir = blockIdx.y;
 
     // ---- prologue: zero the tiles (h_{-1} = 0; empty tiles compute on zeros), barriers, TMEM, weights ----
@@ -627,7 +673,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) rec_pp_kernel(const __grid_cons
         mbar_init(&bars[20], 1);
         fence_mbar_init();
     }
-    if (warp == PP_W_ISS) {
+    if (warp == PP_W_AUX0) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -683,13 +729,17 @@ __global__ void __launch_bounds__(PP_THREADS, 1) rec_pp_kernel(const __grid_cons
 
     // the two tiles run the same code with the tile index in a register (one copy in the instruction cache)
     if (warp < PP_GATE_WARPS) pp_gate<LAYER, TRACE>(smem, a, warp / PP_TILE_WARPS, warp % PP_TILE_WARPS, lane);
-    else if (warp < PP_W_REL) pp_issuer<LAYER, ALLP, TRACE>(smem, a, warp - PP_W_ISS);
-    else if (warp < PP_W_LOG) pp_relay<LAYER, TRACE>(smem, a, warp - PP_W_REL, lane);
-    else if (OUT_LOG) pp_logits<TRACE>(smem, a, lane);
+    else if (warp >= PP_W_ISS && warp < PP_W_ISS + 4) pp_issuer<LAYER, ALLP, TRACE>(smem, a, (warp - PP_W_ISS) & 1, (warp - PP_W_ISS) >> 1);
+    else if (warp == PP_W_REL || warp == PP_W_REL + 1) pp_relay<LAYER, TRACE>(smem, a, warp - PP_W_REL, lane);
+    else if (OUT_LOG) {
+        if (warp == PP_W_AUX0) pp_logits<TRACE>(smem, a, lane);
+    } else {
+        pp_copy<LAYER>(smem, a, warp == PP_W_AUX0 ? 0 : 1, lane);
+    }
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == PP_W_ISS) {
+    if (warp == PP_W_AUX0) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, 512);
     }

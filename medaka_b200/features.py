@@ -66,8 +66,11 @@ def pileup_counts(region, bam, dtype_prefixes=None, region_split=100000, workers
         bam = mbam.BamFile(bam)
     multi = not (dtype_prefixes is None or isinstance(dtype_prefixes, str) or len(dtype_prefixes) == 1)
     num_dtypes = len(dtype_prefixes) if multi else 1
+    # the read filter in the reference's order (src/medaka_bamiter.c:17-45): flags and mapping quality first, natively,
+    # so that the tag / read-group / datatype tests only ever see reads the reference would have looked at too
     batch = bam.fetch(region.ref_name, region.start, region.end, dtypes=dtype_prefixes if multi else None,
-                      tag_name=tag_name, tag_value=tag_value, keep_missing=keep_missing, read_group=read_group)
+                      tag_name=tag_name, tag_value=tag_value, keep_missing=keep_missing, read_group=read_group,
+                      min_mapq=min_mapq)
     counts, positions = pileup_counts_from_batch(batch, region.start, region.end, num_dtypes, min_mapq, device)
     return _split_on_gaps(counts, positions)
 
