@@ -298,6 +298,10 @@ int mdk_selftest_umma(int device, const float *A, const float *B, float *D, int 
  * the last traced forward: uint64 [2 layers][16 time steps (512..527)][32 slots] of %clock64 on CTA (0,0); the slot
  * meanings are listed in tools/diag.py.  Not part of the hot path. */
 int mdk_debug_rec_trace(int device, int enable, uint64_t *out);
+/* diagnostics of the TRACED ping-pong recurrent kernels: a bit set that switches parts of a time step off (1: h-tile
+ * stores, 2: proxy fence, 4: gate arithmetic, 8: x staging, 16: gi staging, 32: tile copy-out) so that the cycle trace
+ * shows what each costs; results are wrong while any bit is set.  0 restores normal operation. */
+int mdk_debug_pp_flags(int flags);
 /* partial logits of the last forward on the fused-head path: float32 [2 directions][tiles][T][5 classes][16 windows]
  * (what the layer-1 recurrence writes instead of h1); per-direction parity checks of the fused linear head */
 int mdk_debug_read_plog(mdk_engine *e, float *out_host, int64_t n_floats);

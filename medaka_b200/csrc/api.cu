@@ -716,6 +716,11 @@ int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_
     return MDK_OK;
 }
 
+int mdk_debug_pp_flags(int flags) {
+    pp_set_debug((uint32_t)flags);
+    return MDK_OK;
+}
+
 int mdk_debug_read_plog(mdk_engine *e, float *out_host, int64_t n_floats) {
     MDK_REQUIRE(e && out_host, MDK_ERR_ARG, "NULL argument");
     mdk_lane &ln = e->lane[e->last_lane];
@@ -809,7 +814,7 @@ int mdk_pileup_counts(int device, int64_t n_rec, const int32_t *pos, const uint1
                  o_cnt = take((size_t)max_cols * F * 8), o_maj = take((size_t)max_cols * 8),
                  o_min = take((size_t)max_cols * 8);
     uint8_t *buf = nullptr;
-    MDK_CUDA(cudaMalloc(&buf, off + 16));
+    MDK_CUDA(plp_scratch(off + 16, &buf, 1));     // cached per host thread: no cudaMalloc / cudaFree per region
     cudaStream_t s = 0;
     cudaError_t err = cudaMemcpy(buf + o_pos, pos, (size_t)n_rec * 4, cudaMemcpyHostToDevice);
     if (err == cudaSuccess) err = cudaMemcpy(buf + o_flag, flag, (size_t)n_rec * 2, cudaMemcpyHostToDevice);
@@ -836,7 +841,6 @@ int mdk_pileup_counts(int device, int64_t n_rec, const int32_t *pos, const uint1
         if (err == cudaSuccess) err = cudaMemcpy(major_out, buf + o_maj, (size_t)n * 8, cudaMemcpyDeviceToHost);
         if (err == cudaSuccess) err = cudaMemcpy(minor_out, buf + o_min, (size_t)n * 8, cudaMemcpyDeviceToHost);
     }
-    cudaFree(buf);
     if (err != cudaSuccess) return cuda_fail(err, "pileup_counts", __FILE__, __LINE__);
     return rc;
 }

@@ -215,6 +215,7 @@ cudaError_t launch_rec_tc(const float *gi, const RecXArgs *fuse, const __half *w
 cudaError_t launch_rec_pp(int layer, const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
                           void *h_out, int64_t B, int64_t T, cudaStream_t s, const __half *lin_w_tc, float *plog,
                           uint32_t prod_mask);
+void pp_set_debug(uint32_t flags);   // diagnostics of the traced ping-pong kernels (gru_pp.cu PPArgs::debug)
 // head on the partial logits of the fused path: sum of the two directions + bias -> softmax / argmax
 cudaError_t launch_head_plog(const float *plog, const float *lin_b, int64_t B, int64_t T, float *probs, float *logits,
                              uint8_t *labels, cudaStream_t s);
@@ -224,6 +225,7 @@ cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const flo
                            int sm_count, cudaStream_t s, uint32_t prod_mask = 7u);
 int selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant);
 // pileup.cu
+cudaError_t plp_scratch(size_t bytes, uint8_t **out, int slot);   // per-host-thread cached device buffers (slot 0 / 1)
 int pileup_counts_dev(int64_t n_rec, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
                       const uint8_t *dtype, const uint32_t *cigar, const int64_t *cigar_off, int64_t n_ops,
                       const uint8_t *seq, const int64_t *seq_off, int32_t start, int32_t end, int num_dtypes,

@@ -118,7 +118,11 @@ struct PPArgs {
     const __half *lin_w_tc;   // layer 1: packed W_lin (misc.cu pack_linear_kernel)
     float *plog;              // layer 1: partial logits [dir][tile][t][class 5][16 windows]
     uint32_t prod_mask;       // bit 0: W_hi.h_hi, bit 1: W_hi.h_lo, bit 2: W_lo.h_hi (7 = fp32-faithful)
+    uint32_t debug;           // TRACE instantiations only: switch parts of the step off to see what they cost
+                              // (results are then wrong).  1: no h-tile stores, 2: no proxy fence, 4: no gate arithmetic,
+                              // 8: no x staging, 16: no gi staging / prefetch, 32: no tile copy-out
 };
+#define PP_DBG(bit) (TRACE && (a.debug & (bit)))
 
 constexpr int PP_TRACE_STEP0 = 512, PP_TRACE_STEPS = 16, PP_TRACE_SLOTS = 40;   // == the rec_tc trace geometry
 #define PP_STAMP(slot)                                                    \
@@ -312,7 +316,8 @@ __device__ __noinline__ void pp_relay(uint8_t *smem, const PPArgs &a, const int 
             bulk_prefetch_l2(reinterpret_cast<const void *>(p0), (uint32_t)(((p + nbytes - p0) + 15) & ~(uintptr_t)15));
         }
     };
-    if (!IN_X && lead && tile_ok) {
+    const bool no_gi = PP_DBG(16);
+    if (!IN_X && lead && tile_ok && !no_gi) {
         stage_gi(0);
         if (T > 1) stage_gi(1);
     }
@@ -322,7 +327,7 @@ __device__ __noinline__ void pp_relay(uint8_t *smem, const PPArgs &a, const int 
         unsigned long long *tr = pp_trace_row<TRACE>(a, s, lead);
         if (lead) {
             mbar_wait(&acc[0], par);
-            if (!IN_X && tile_ok) mbar_wait(&gi_full[s % PP_GI_BUFS], (uint32_t)((s / PP_GI_BUFS) & 1));
+            if (!IN_X && tile_ok && !no_gi) mbar_wait(&gi_full[s % PP_GI_BUFS], (uint32_t)((s / PP_GI_BUFS) & 1));
         }
         __syncwarp();
         tc_fence_after_sync();
@@ -343,7 +348,7 @@ __device__ __noinline__ void pp_relay(uint8_t *smem, const PPArgs &a, const int 
         else named_bar_arrive_id<PP_NB2>(PP_BAR_N + X);
         PP_STAMP(X * 20 + 6);
         // ---- idle until the next commit: staging / copy-out / prefetch (one thread) ----
-        if (lead && tile_ok) {
+        if (lead && tile_ok && !no_gi) {
             if (!IN_X) {
                 // buffer (s+2) % 3 == (s-1) % 3 was last read in step s-1, which every gate warp had left when it
                 // arrived on H_X(s), and the MMAs of step s (just committed) were issued after that barrier
@@ -363,13 +368,13 @@ __device__ __noinline__ void pp_relay(uint8_t *smem, const PPArgs &a, const int 
 // It takes part in H_X (it may read the buffer the gate warps have just published) and in N_X of the same step (it
 // arrives once its loads are in registers: the buffer it read is only overwritten after N_X of the NEXT step, which
 // needs this warp's next arrival).
-template <int LAYER>
+template <int LAYER, bool TRACE>
 __device__ __noinline__ void pp_copy(uint8_t *smem, const PPArgs &a, const int X, int lane) {
     using L = PPCfg<LAYER>;
     const int dir = blockIdx.y;
     const int64_t T = a.T;
     const int64_t tile = (int64_t)blockIdx.x * 2 + X;
-    const bool tile_ok = tile < a.ntiles;
+    const bool tile_ok = tile < a.ntiles && !PP_DBG(32);
     const int half = lane >> 4, l16 = lane & 15;
     auto copy = [&](int64_t sidx, int buf, bool arrive) {
         const int64_t orow = (tile * T + (dir ? (T - 1 - sidx) : sidx)) * WT;
@@ -536,6 +541,7 @@ __device__ __noinline__ void pp_gate(uint8_t *smem, const PPArgs &a, const int X
             PP_STAMP(X * 20 + 7);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
+                if (PP_DBG(4)) { r2[p] = one2; gp2[p] = one2; continue; }
                 // (weights and biases carry the -log2 e / 2 log2 e factors, common.cuh gate_scale: the accumulator is
                 // the exponent.)  r = 1 / (1 + 2^acc), reciprocal on the FMA pipe (rec_common.cuh)
                 const F2 accr = f2_make(__uint_as_float(ar[2 * p]), __uint_as_float(ar[2 * p + 1]));
@@ -572,6 +578,7 @@ __device__ __noinline__ void pp_gate(uint8_t *smem, const PPArgs &a, const int X
             PP_STAMP(X * 20 + 9);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
+                if (PP_DBG(4)) { nzb2[p] = negone2; a2[p] = one2; b2[p] = one2; continue; }
                 // z = 1 / (1 + eb) is never formed.  With en = e^{2x} (the tanh argument, next phase):
                 //   h = (1 - z) n + z h_prev = ((eb + h_prev) en + (h_prev - eb)) / ((1 + eb) en + (1 + eb))
                 // so everything but en is prepared here, off the n -> h critical path
@@ -600,6 +607,7 @@ __device__ __noinline__ void pp_gate(uint8_t *smem, const PPArgs &a, const int X
             uint8_t *hw = hrow + (int)((s + 1) & 1) * (2 * RT_HPLANE);      // the buffer the MMAs of this step do not read
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
+                if (PP_DBG(4)) continue;
                 const F2 accn = f2_make(__uint_as_float(an[2 * p]), __uint_as_float(an[2 * p + 1]));
                 float t0, t1;
                 f2_get(f2_fma(r2[p], accn, gp2[p]), t0, t1);
@@ -617,12 +625,13 @@ __device__ __noinline__ void pp_gate(uint8_t *smem, const PPArgs &a, const int X
                 float l0v, l1v;
                 f2_get(f2_fma(f2_make(u0, u1), negone2, h2), l0v, l1v);
                 const __half2 hi2 = __floats2half2_rn(u0, u1), lo2 = __floats2half2_rn(l0v, l1v);
+                if (PP_DBG(1)) continue;
                 *reinterpret_cast<__half *>(hw + (2 * p) * 16) = __low2half(hi2);
                 *reinterpret_cast<__half *>(hw + RT_HPLANE + (2 * p) * 16) = __low2half(lo2);
                 *reinterpret_cast<__half *>(hw + (2 * p + 1) * 16) = __high2half(hi2);
                 *reinterpret_cast<__half *>(hw + RT_HPLANE + (2 * p + 1) * 16) = __high2half(lo2);
             }
-            if (L0 && xown && s + 1 < T) {
+            if (L0 && xown && s + 1 < T && !PP_DBG(8)) {
                 // stage x_{s+1} (loaded a step ago) into the other x buffer
                 __half hi, lo;
                 split_f16(xreg, hi, lo);
@@ -631,13 +640,14 @@ __device__ __noinline__ void pp_gate(uint8_t *smem, const PPArgs &a, const int X
                 *reinterpret_cast<__half *>(xd + RT_XPLANE) = lo;
             }
             PP_STAMP(X * 20 + 12);
-            fence_proxy_async_smem();     // h / x tile writes -> visible to the MMAs' (and the bulk copy's) async-proxy reads
+            if (!PP_DBG(2))
+            fence_proxy_async_smem();     // h / x tile writes -> visible to the MMAs' async-proxy reads
             tc_fence_before_sync();
             if (s + 1 < T) named_bar_arrive_id<NB_H>(PP_BAR_H + X);
             else named_bar_arrive_id<PP_NB>(PP_BAR_FIN + X);
             PP_STAMP(X * 20 + 13);
         }
-        if (L0 && xok && s + 2 < T) {
+        if (L0 && xok && s + 2 < T && !PP_DBG(8)) {
             xreg = *xnext;                // the feature value staged during the NEXT step
             xnext += xadv;
         }
@@ -734,7 +744,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) rec_pp_kernel(const __grid_cons
     else if (OUT_LOG) {
         if (warp == PP_W_AUX0) pp_logits<TRACE>(smem, a, lane);
     } else {
-        pp_copy<LAYER>(smem, a, warp == PP_W_AUX0 ? 0 : 1, lane);
+        pp_copy<LAYER, TRACE>(smem, a, warp == PP_W_AUX0 ? 0 : 1, lane);
     }
 
     tc_fence_before_sync();
@@ -746,6 +756,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) rec_pp_kernel(const __grid_cons
 }
 
 unsigned long long *rec_trace_buffer();   // gru_tc.cu: [2 layers][steps][slots], null = tracing off
+static uint32_t g_pp_debug = 0;
+void pp_set_debug(uint32_t flags) { g_pp_debug = flags; }
 
 cudaError_t launch_rec_pp(int layer, const float *gi, const RecXArgs *fuse, const __half *w_hh_tm, const float *b_hn,
                           void *h_out, int64_t B, int64_t T, cudaStream_t s, const __half *lin_w_tc, float *plog,
@@ -763,6 +775,7 @@ cudaError_t launch_rec_pp(int layer, const float *gi, const RecXArgs *fuse, cons
     a.lin_w_tc = lin_w_tc;
     a.plog = plog;
     a.prod_mask = prod_mask & 7u;
+    a.debug = g_pp_debug;
     // layer: 0 = layer 0 (fused projection when `fuse` is given, else gi in), 1 = layer 1
     const int variant = layer == 1 ? 1 : (fuse ? 0 : 2);
     if (variant == 0 && (fuse->F > 16 || !h_out)) return cudaErrorInvalidValue;

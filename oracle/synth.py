@@ -139,10 +139,12 @@ def synth_features_fast(B, T, F=10, seed=1234):
     return x
 
 
-def synth_reads(n_reads, ref_len, seed=0, mean_len=3000, p_ins=0.04, p_del=0.04, p_skip=0.0, num_dtypes=1):
+def synth_reads(n_reads, ref_len, seed=0, mean_len=3000, p_ins=0.04, p_del=0.04, p_skip=0.0, num_dtypes=1,
+                ins_after_skip=False):
     """Random alignment records (dicts as oracle/pileup_oracle.py takes them): CIGARs with M/=/X runs, insertions
-    (incl. consecutive I ops and I right after D), deletions, optional N skips, soft clips, both strands, a few
-    filtered flags / low mapQ reads and IUPAC ambiguity codes."""
+    (incl. consecutive I ops and I right after D), deletions, optional N skips (``ins_after_skip``: insertions may
+    follow a skip directly - they widen the column group but are not counted, medaka_counts.c:259-263,282), soft clips,
+    both strands, a few filtered flags / low mapQ reads and IUPAC ambiguity codes."""
     rs = np.random.RandomState(seed)
     recs = []
     for i in range(n_reads):
@@ -154,7 +156,7 @@ def synth_reads(n_reads, ref_len, seed=0, mean_len=3000, p_ins=0.04, p_del=0.04,
         last = None
         while ref_used < target:
             u = rs.uniform()
-            if u < p_ins and last in ("M", "D", "I"):
+            if u < p_ins and last in (("M", "D", "I", "N") if ins_after_skip else ("M", "D", "I")):
                 l = int(rs.randint(1, 6)); ops.append((l, "I")); qlen += l; last = "I"
             elif u < p_ins + p_del and last == "M":
                 l = int(min(rs.randint(1, 8), target - ref_used)); ops.append((l, "D")); ref_used += l; last = "D"

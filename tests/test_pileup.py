@@ -98,10 +98,16 @@ def test_gpu_pileup_real_bam_slice(golden_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,num_dtypes,p_skip", [(0, 1, 0.0), (1, 1, 0.02), (2, 2, 0.0)])
-def test_gpu_pileup_random_reads(seed, num_dtypes, p_skip):
+@pytest.mark.parametrize("seed,num_dtypes,p_skip,ins_after_skip",
+                         [(0, 1, 0.0, False), (1, 1, 0.02, False), (2, 2, 0.0, False), (3, 1, 0.08, True), (4, 2, 0.05, True)])
+def test_gpu_pileup_random_reads(seed, num_dtypes, p_skip, ins_after_skip):
+    """(the last two cases put insertions right behind reference skips: they widen the column group of the skip's last
+    position but are not counted, src/medaka_counts.c:259-263 vs :282)"""
     from medaka_b200 import features
-    recs = synth.synth_reads(300, 4000, seed=seed, mean_len=800, p_skip=p_skip, num_dtypes=num_dtypes)
+    recs = synth.synth_reads(300, 4000, seed=seed, mean_len=800, p_skip=p_skip, num_dtypes=num_dtypes,
+                             ins_after_skip=ins_after_skip)
+    if ins_after_skip:
+        assert any(__import__("re").search(r"\d+N\d+I", r["cigar"]) for r in recs)
     dtypes = ["dt%d" % k for k in range(num_dtypes)] if num_dtypes > 1 else None
     batch = bam.records_from_dicts(recs, dtypes)
     for s, e, mq in [(0, 4000, 1), (1000, 2500, 1), (500, 600, 20)]:
@@ -127,6 +133,28 @@ def test_gpu_pileup_gaps_empty_and_overflow():
     c, p = features.pileup_counts_from_batch(bam.records_from_dicts([ins_read]), 0, 4)
     ec, ep = pileup_oracle.pileup_counts([ins_read], 0, 4)
     assert len(p) == 44 and np.array_equal(c, ec) and np.array_equal(p, ep)
+
+
+@pytest.mark.gpu
+def test_gpu_pileup_long_operations_and_many_reads():
+    """Balance cases of the rewritten kernels: reads with > 32 CIGAR ops per warp step and multi-kilobase single
+    operations (a 5 kb match, a 3 kb deletion, a 2 kb reference skip followed by an insertion), a region longer than
+    one scan block, and depth in the hundreds."""
+    from medaka_b200 import features
+    rs = np.random.RandomState(5)
+    seq = lambda n: "".join(rs.choice(list("ACGT"), n))  # noqa: E731
+    recs = [dict(query_name="longM", pos=10, cigar="5000M", seq=seq(5000), flag=0, mapq=60, tags={}),
+            dict(query_name="longD", pos=500, cigar="100M3000D100M", seq=seq(200), flag=16, mapq=60, tags={}),
+            dict(query_name="skipI", pos=700, cigar="50M2000N4I60M", seq=seq(114), flag=0, mapq=60, tags={})]
+    recs += synth.synth_reads(1500, 9000, seed=9, mean_len=2500, p_skip=0.01, ins_after_skip=True)
+    recs.sort(key=lambda r: r["pos"])
+    batch = bam.records_from_dicts(recs)
+    for s, e in [(0, 9000), (2040, 4100), (4095, 4097)]:
+        c, p = features.pileup_counts_from_batch(batch, s, e)
+        ec, ep = pileup_oracle.pileup_counts(recs, s, e)
+        assert np.array_equal(p, ep), (s, e)
+        assert np.array_equal(c, ec), (s, e)
+    assert int(c.sum()) > 0
 
 
 @pytest.mark.gpu

@@ -253,8 +253,11 @@ def check_pp_trace(arg):
     """Cycle stamps of the ping-pong kernel's hand-off points on CTA (0,0), steps 512..527: 'B,T'."""
     from medaka_b200 import libmedaka as lm, models
     from oracle import synth
-    B, T = (int(x) for x in arg.split(","))
+    parts = [int(x) for x in arg.split(",")]
+    B, T = parts[0], parts[1]
     lib, ffi = lm.load(), lm.ffi
+    if len(parts) > 2:
+        lm.check(lib.mdk_debug_pp_flags(parts[2]))
     m = models.GRUModel()
     m.load_state_dict(synth.synth_state_dict(0))
     m.set_rec_mode("pp")
