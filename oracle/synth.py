@@ -58,6 +58,23 @@ def synth_state_dict(seed=0, num_features=10, gru_size=128, n_layers=2,
     return sd
 
 
+def synth_state_dict_neartie(seed=0, eps=1e-3, bias_shift=-6.318e-4, **kw):
+    """Adversarial head for the label-parity tests: classes 1 and 2 get (almost) the same row of the Linear layer and
+    (almost) the same, raised, bias - they are the top two everywhere.  ``bias_shift`` centres the logit difference of
+    the two on zero (calibrated once for seed 5 with synth_features(6, 400, 10, seed=105): the difference then has
+    standard deviation 4e-5), so the top-2 probability margins spread from 0 to ~1e-4: hundreds of positions sit inside
+    fp32 re-association noise of flipping, the rest just outside it."""
+    sd = synth_state_dict(seed, **kw)
+    rs = np.random.RandomState(seed + 7919)
+    w = sd["linear.weight"].copy()
+    w[2] = w[1] * (1.0 + eps * rs.standard_normal(w.shape[1])).astype(np.float32)
+    b = sd["linear.bias"].copy()
+    b[1] += 3.0
+    b[2] = b[1] + np.float32(bias_shift)
+    sd["linear.weight"], sd["linear.bias"] = w.astype(np.float32), b.astype(np.float32)
+    return sd
+
+
 def synth_counts(n_cols, seed=20240923, num_dtypes=1, mean_depth=30, max_depth=120,
                  minor_frac=0.15, start_major=0, start_on_minor=False):
     """Synthetic raw pileup counts the way BASELINE.md section 4 describes them.

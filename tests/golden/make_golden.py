@@ -116,8 +116,12 @@ def main():
             ("long", 1, 2, 1500, 10, 8.0, 1.0),
             ("hot", 2, 5, 300, 10, 24.0, 2.5),      # larger recurrent gain / sharper logits
             ("f20", 3, 2, 200, 20, 8.0, 1.0),       # two dtypes (config 5)
-            ("b1", 4, 1, 777, 10, 8.0, 1.0)]:       # remainder path: B=1, odd T
-        sd = synth.synth_state_dict(seed, num_features=F, head_gain=head_gain, rec_gain=rec_gain)
+            ("b1", 4, 1, 777, 10, 8.0, 1.0),        # remainder path: B=1, odd T
+            ("neartie", 5, 6, 400, 10, 8.0, 1.0)]:  # adversarial head: two classes within ~1e-5 of each other everywhere
+        if name == "neartie":
+            sd = synth.synth_state_dict_neartie(seed, num_features=F, head_gain=head_gain, rec_gain=rec_gain)
+        else:
+            sd = synth.synth_state_dict(seed, num_features=F, head_gain=head_gain, rec_gain=rec_gain)
         model = ref_gru.GRUModel(num_features=F)
         model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
         model.eval()

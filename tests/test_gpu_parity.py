@@ -75,11 +75,12 @@ def test_umma_tile_selftest(lm, N, K):
 
 # ------------------------------------------------------------------ forward pass
 @pytest.mark.parametrize("precision", ["fp32", "tc"])
-@pytest.mark.parametrize("case", ["small", "long", "hot", "f20", "b1"])
+@pytest.mark.parametrize("case", ["small", "long", "hot", "f20", "b1", "neartie"])
 def test_forward_matches_reference_golden(golden_dir, case, precision):
     g = np.load(os.path.join(golden_dir, "gru_forward.npz"))
     seed, B, T, F, head_gain, rec_gain = g[case + "_args"]
-    sd = synth.synth_state_dict(int(seed), num_features=int(F), head_gain=head_gain, rec_gain=rec_gain)
+    maker = synth.synth_state_dict_neartie if case == "neartie" else synth.synth_state_dict
+    sd = maker(int(seed), num_features=int(F), head_gain=head_gain, rec_gain=rec_gain)
     feats = synth.synth_features(int(B), int(T), int(F), seed=100 + int(seed))
     m = _make_model(sd, int(F), precision)
     out = m.forward_arrays(feats, want_logits=True, want_labels=True)
