@@ -202,7 +202,8 @@ def run_reference(args, rank, world):
         "unit": "positions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(), "timing": "host wall clock, CPU only", "threads": cores},
+        "config": {"workload": workload_name(args.config), "baseline_config": args.config,
+                   "timing": "host wall clock, CPU only", "threads": cores},
         "cpu_baseline": {"value": rate, "unit": "positions/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": rate, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -211,20 +212,40 @@ def run_reference(args, rank, world):
     emit(line)
 
 
-def workload_name():
-    return ("r1041_e82_400bps_sup_v5 consensus, synthetic 10 Mb draft: %d windows x %d cols x %d feats "
-            "(chunk_len 10000, overlap 1000), six 200-window batches coalesced into one device batch"
-            % (WINDOWS, COLS, FEATS))
+CONFIGS = {
+    # BASELINE.json configs[1..4]: windows per GPU, columns per window, features, what a step is
+    2: dict(windows=1111, cols=10000, feats=10,
+            name="r1041_e82_400bps_sup_v5 consensus, synthetic 10 Mb draft: 1111 windows x 10000 cols x 10 feats "
+                 "(chunk_len 10000, overlap 1000)"),
+    3: dict(windows=2778, cols=10000, feats=10,
+            name="r1041_e82_400bps_sup_v5 consensus, synthetic 200 Mb draft region-sharded over 8 GPUs: this rank's share, "
+                 "2778 of 22223 windows x 10000 cols x 10 feats"),
+    4: dict(windows=5556, cols=10000, feats=10,
+            name="r1041_e82_400bps_sup_variant_v5, synthetic 50 Mb: 5556 windows x 10000 cols x 10 feats; the e2e leg adds "
+                 "the variant decode of every step's output on the GPU (mdk_decode_variants)"),
+    5: dict(windows=1111, cols=10000, feats=20,
+            name="r941_min_hac_g507-style legacy encoder, synthetic 10 Mb: 1111 windows x 10000 cols x 20 feats (two "
+                 "datatypes, normalise='fwd_rev'); a step starts from raw uint64 counts (normalise kernel + forward)"),
+}
+
+
+def workload_name(cfg=2):
+    return CONFIGS[cfg]["name"]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--windows", type=int, default=WINDOWS, help="windows per step per GPU")
-    ap.add_argument("--cols", type=int, default=COLS)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (2..5)")
+    ap.add_argument("--windows", type=int, default=0, help="windows per step per GPU (0 = the config's)")
+    ap.add_argument("--cols", type=int, default=0)
+    ap.add_argument("--batch-windows", type=int, default=200,
+                    help="windows per predict_on_batch call in the e2e leg (the reference's --batch_size; the engine "
+                         "coalesces them into device-filling groups)")
+    ap.add_argument("--rec-mode", default="auto", choices=["auto", "one", "pp"])
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--cpu-windows", type=int, default=200, help="windows in the bounded CPU-baseline sample")
     ap.add_argument("--cpu-cols", type=int, default=0,
@@ -236,6 +257,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = CONFIGS[args.config]
+    global FEATS
+    FEATS = cfg["feats"]
 
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -258,7 +282,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
 
     # ---- weights: rank 0 owns them, one NCCL broadcast of the packed fp32 blob (1.62 MB) ----
-    sd = synth.synth_state_dict(0, num_features=FEATS)
+    F = cfg["feats"]
+    sd = synth.synth_state_dict(0, num_features=F)
     keys = sorted(sd)
     if world > 1:
         blob = np.concatenate([sd[k].ravel() for k in keys])
@@ -270,33 +295,66 @@ def main():
             n = sd[k].size
             sd[k] = flat[off:off + n].reshape(sd[k].shape).copy()
             off += n
-    model = models.GRUModel(num_features=FEATS, device=dev)
+    model = models.GRUModel(num_features=F, device=dev)
     model.load_state_dict(sd)
     model.set_precision(args.precision)
+    model.set_rec_mode(args.rec_mode)
     eng = model.engine
 
-    B, T, F = args.windows, args.cols, FEATS
+    B = args.windows or cfg["windows"]
+    T = args.cols or cfg["cols"]
     P = B * T
-    log("generating %d x %d x %d synthetic features into pinned host memory" % (B, T, F))
+    group = model.preferred_batch_size()                 # windows per device forward (one wave; lanes alternate)
+    chunks = [(a, min(B, a + group)) for a in range(0, B, group)]
+    log("config %d: %d x %d x %d synthetic features into pinned host memory" % (args.config, B, T, F))
     feats = fill_features(model.pinned("bench_feats", (B, T, F), np.float32), 1000 + rank)
-    log("reserving workspace")
-    lm.check(lib.mdk_engine_reserve(eng, B, T))
+    log("reserving the compute lanes (%d-window groups)" % min(group, B))
+    model.reserve(min(group, B), T)
 
-    # ---- device-resident leg ("value") ----
     def dalloc(nbytes):
         pp = ffi.new("void **")
         lm.check(lib.mdk_dev_alloc(dev, nbytes, pp))
         return pp[0]
 
+    # ---- device-resident leg ("value"): inputs in HBM when the timed region starts ----
     d_feats = dalloc(feats.nbytes)
-    d_probs = dalloc(P * 5 * 4)
-    d_labels = dalloc(P)
     lm.check(lib.mdk_memcpy_h2d(dev, d_feats, ffi.from_buffer(feats), feats.nbytes))
+    # two output sets: consecutive steps run on alternating lanes and may overlap
+    d_probs_set = [dalloc(P * 5 * 4), dalloc(P * 5 * 4)]
+    d_labels_set = [dalloc(P), dalloc(P)]
+    d_probs, d_labels = d_probs_set[0], d_labels_set[0]
+    d_counts = d_major = d_minor = d_depth = None
+    if args.config == 5:
+        # raw counts resident in HBM: the step is normalise (a3) + forward; counts chosen so that the features are the
+        # synthetic ones is not possible bit-for-bit, so the normalise output simply replaces d_feats
+        counts, pos = synth.synth_counts(min(P, 4000000), seed=77, num_dtypes=2)
+        reps = (P + len(counts) - 1) // len(counts)
+        counts = np.tile(counts, (reps, 1))[:P]
+        major = np.tile(pos["major"], reps)[:P].astype(np.int64)
+        minor = np.tile(pos["minor"], reps)[:P].astype(np.int64)
+        minor[0] = 0
+        d_counts, d_major, d_minor, d_depth = dalloc(counts.nbytes), dalloc(P * 8), dalloc(P * 8), dalloc(P * 8)
+        lm.check(lib.mdk_memcpy_h2d(dev, d_counts, ffi.from_buffer(counts), counts.nbytes))
+        lm.check(lib.mdk_memcpy_h2d(dev, d_major, ffi.from_buffer(major), P * 8))
+        lm.check(lib.mdk_memcpy_h2d(dev, d_minor, ffi.from_buffer(minor), P * 8))
+        del counts
+
+    step_no = [0]
 
     def step_dev():
-        lm.check(lib.mdk_engine_forward_dev(eng, ffi.cast("const float *", d_feats), B, T,
-                                            ffi.cast("float *", d_probs), ffi.NULL,
-                                            ffi.cast("uint8_t *", d_labels)))
+        d_probs, d_labels = d_probs_set[step_no[0] & 1], d_labels_set[step_no[0] & 1]
+        step_no[0] += 1
+        if args.config == 5:
+            lm.check(lib.mdk_device_synchronize(dev))    # the normalise kernel runs on the default stream
+            lm.check(lib.mdk_normalise_counts_dev(dev, ffi.cast("const uint64_t *", d_counts),
+                                                  ffi.cast("const int64_t *", d_major), ffi.cast("const int64_t *", d_minor),
+                                                  P, 2, lib.MDK_NORM_FWD_REV, 0, ffi.cast("float *", d_feats),
+                                                  ffi.cast("int64_t *", d_depth)))
+            lm.check(lib.mdk_device_synchronize(dev))
+        for a, b in chunks:
+            lm.check(lib.mdk_engine_forward_dev(
+                eng, ffi.cast("const float *", d_feats) + a * T * F, b - a, T, ffi.cast("float *", d_probs) + a * T * 5,
+                ffi.NULL, ffi.cast("uint8_t *", d_labels) + a * T))
 
     def barrier():
         if dist is not None:
@@ -315,13 +373,14 @@ def main():
     lm.check(lib.mdk_engine_timer_start(eng))
     for _ in range(args.steps):
         step_dev()
-    lm.check(lib.mdk_engine_timer_stop(eng, ms))     # records + synchronises the end event
+    lm.check(lib.mdk_engine_timer_stop(eng, ms))     # end event after every lane and the copy streams
     barrier()
     clocks = sampler.stop()
     dev_ms = float(ms[0])
-    launches = model.launch_count() - launches0
+    launches = model.launch_count() - launches0 + (args.steps if args.config == 5 else 0)
     tm = ffi.new("mdk_timings *")
-    lm.check(lib.mdk_engine_mean_timings(eng, min(args.steps, 32), tm))
+    n_fwd = min(args.steps * len(chunks), 32)
+    lm.check(lib.mdk_engine_mean_timings(eng, n_fwd, tm))
     stage = {k: float(getattr(tm, k)) for k in ("inproj0_ms", "rec0_ms", "inproj1_ms", "rec1_ms", "head_ms")}
 
     # sanity: the timed path produced real outputs (labels consistent with probabilities)
@@ -329,31 +388,78 @@ def main():
     lm.check(lib.mdk_memcpy_d2h(dev, ffi.from_buffer(chk), d_probs, chk.nbytes))
     assert np.isfinite(chk).all() and abs(float(chk.sum(-1).mean()) - 1.0) < 1e-4
 
-    # ---- host-buffer leg ("e2e"): pinned H2D + forward + D2H of probs and labels EVERY step, through the
-    # reference-facing C-ABI call with host buffers (mdk_engine_submit / mdk_engine_wait, the asynchronous form of
-    # mdk_engine_forward that medaka_b200.prediction.run_prediction uses: two calls in flight, so the copies of
-    # neighbouring steps hide under the compute of the current one) ----
-    h_feats = feats
-    h_probs = [model.pinned("bench_probs%d" % i, (B, T, 5), np.float32) for i in range(2)]
-    h_labels = [model.pinned("bench_labels%d" % i, (B, T), np.uint8) for i in range(2)]
+    # one forward on an otherwise idle GPU: clean per-kernel durations (in the timed region the groups of two lanes
+    # overlap, so a kernel's event-to-event time there includes the other lane's kernels)
+    b0 = chunks[0][1]
+    barrier()
+    lm.check(lib.mdk_engine_forward_dev(eng, ffi.cast("const float *", d_feats), b0, T, ffi.cast("float *", d_probs),
+                                        ffi.NULL, ffi.cast("uint8_t *", d_labels)))
+    lm.check(lib.mdk_engine_mean_timings(eng, 1, tm))
+    solo = {k: float(getattr(tm, k)) for k in ("inproj0_ms", "rec0_ms", "inproj1_ms", "rec1_ms", "head_ms")}
 
-    def run_host(n):
-        tickets = []
+    # ---- host-buffer leg ("e2e"): the reference-facing call with HOST buffers, the way run_prediction drives it -
+    # batches of --batch-windows windows (the reference's --batch_size) submitted with a look-ahead
+    # (mdk_engine_submit / mdk_engine_wait); every step copies its features in and its probabilities + labels out ----
+    bw = max(1, min(args.batch_windows, B))
+    batches = [(a, min(B, a + bw)) for a in range(0, B, bw)]
+    depth = model.lookahead(bw, T)
+    h_probs = model.pinned("bench_probs", (2, B, T, 5), np.float32)      # two steps' worth: results stay valid while
+    h_labels = model.pinned("bench_labels", (2, B, T), np.uint8)         # the next step is already queued
+    variant_ms = []
+    vd = None
+    if args.config == 4:
+        # synthetic draft for the variant decode: every window is decoded against a random draft with ~12 % insertion
+        # columns (the decode is per joined sample; here one call per batch of windows)
+        rs = np.random.RandomState(5)
+        vminor = (rs.uniform(size=T) < 0.12).astype(np.int64)
+        vminor[0] = 0
+        vref = np.where(vminor == 0, rs.randint(1, 5, T), 0).astype(np.uint8)
+        from medaka_b200 import labels as mlabels
+        vd = (mlabels, vminor, vref)
+
+    def run_host(n, timed=False):
+        pending = []
         for k in range(n):
-            tickets.append(model.submit_arrays(h_feats, h_probs[k % 2], h_labels[k % 2]))
-            if k >= 1:
-                model.wait(tickets[k - 1])
-        model.wait(tickets[-1])
+            for a, b in batches:
+                while len(pending) >= depth:
+                    model.wait(pending.pop(0)[0])
+                tk = model.submit_arrays(feats[a:b], h_probs[k % 2, a:b], h_labels[k % 2, a:b])
+                pending.append((tk, k, a, b))
+            if vd is not None:
+                # config 4: decode the previous step's output while this step runs on the device
+                for tk, kk, a, b in [p for p in pending if p[1] < k]:
+                    model.wait(tk)
+                pending = [p for p in pending if p[1] >= k]
+                if k >= 1:
+                    decode_step(k - 1, timed)
+        while pending:
+            model.wait(pending.pop(0)[0])
+        if vd is not None:
+            decode_step(n - 1, timed)
 
-    log("host-buffer leg")
+    def decode_step(k, timed):
+        mlabels, vminor, vref = vd
+        t0 = time.perf_counter()
+        n_var = 0
+        for w in range(0, B, 64):                       # 64 windows per call: 640 k columns, like a joined region
+            wb = min(B, w + 64)
+            probs = h_probs[k % 2, w:wb].reshape(-1, 5)
+            mn = np.tile(vminor, wb - w)
+            rf = np.tile(vref, wb - w)
+            n_var += len(mlabels.decode_variant_arrays(probs, mn, rf, dev, want_quals=False)["run_start"])
+        if timed:
+            variant_ms.append((time.perf_counter() - t0) * 1e3)
+        return n_var
+
+    log("host-buffer leg (%d-window batches, %d in flight)" % (bw, depth))
     run_host(max(1, min(args.warmup, 2)))
     barrier()
     lm.check(lib.mdk_engine_timer_start(eng))
-    run_host(args.steps)
+    run_host(args.steps, timed=True)
     lm.check(lib.mdk_engine_timer_stop(eng, ms))
     barrier()
     e2e_ms = float(ms[0])
-    assert np.isfinite(h_probs[(args.steps - 1) % 2][:2]).all()
+    assert np.isfinite(h_probs[(args.steps - 1) % 2, :2]).all()
 
     if dist is not None:
         t = torch.tensor([dev_ms, e2e_ms], device="cuda")
@@ -364,36 +470,41 @@ def main():
     value = total_positions / (dev_ms * 1e-3)
     e2e = total_positions / (e2e_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel ----
+    # ---- roofline of the dominant kernel (tensor bound).  Per-kernel numbers come from the solo forward (one group
+    # of `b0` windows, nothing else on the GPU); `phase` is the steady-state figure of the timed region, where the
+    # layer-1 recurrence of one group overlaps the layer-0 recurrence of the next on the other half of the SMs ----
     peaks = measured_peaks()
+    p0 = b0 * T
+    rec_ms = 0.5 * (solo["rec0_ms"] + solo["rec1_ms"])
     kernels = {
-        "rec_tc_kernel (GRU recurrence, layer 0 and layer 1 launches)":
-            (0.5 * (stage["rec0_ms"] + stage["rec1_ms"]), P * FLOP_REC_PER_LAYER,
-             stage["rec0_ms"] + stage["rec1_ms"]),
-        "gemm_tc_kernel (layer-1 input projection)": (stage["inproj1_ms"], P * FLOP_INPROJ1, stage["inproj1_ms"]),
+        "recurrent kernel (rec_pp_kernel / rec_tc_kernel: GRU recurrence, layer-0 and layer-1 launches)":
+            (rec_ms, p0 * FLOP_REC_PER_LAYER, solo["rec0_ms"] + solo["rec1_ms"]),
+        "gemm_tc_kernel (layer-1 input projection)": (solo["inproj1_ms"], p0 * FLOP_INPROJ1, solo["inproj1_ms"]),
     }
     dom = max(kernels, key=lambda k: kernels[k][2])
     k_ms, k_flop, k_share_ms = kernels[dom]
     achieved = k_flop / (k_ms * 1e-3) / 1e12
-    # DRAM traffic per launch of that kernel: from the committed ncu --set full capture of this same workload
-    # (profiles/ncu_traffic.json, written by tools/ncu_summary.py); null for any other shape
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if (B, T) == (WINDOWS, COLS) and args.precision == "tc" and os.path.exists(tpath):
+    if args.config == 2 and args.precision == "tc" and os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
-        traffic = tj.get("rec_tc_kernel" if dom.startswith("rec_tc") else "gemm_tc_kernel")
+        traffic = tj.get("rec_pp_kernel" if dom.startswith("recurrent") else "gemm_tc_kernel")
+    flop_gru = 2 * FLOP_REC_PER_LAYER + FLOP_INPROJ1 + 2 * (2 * 384 * F)
     roofline = {
-        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops_sustained"],
-        "unit": "TFLOP/s", "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
-        "peak_source": "MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step)"
+        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops_burst"],
+        "unit": "TFLOP/s", "frac": achieved / peaks["tflops_burst"], "traffic": traffic,
+        "peak_source": "MEASURED_PEAKS.json bf16 burst (kernel timed alone: one forward of %d windows on an idle GPU)" % b0
         if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)",
         "note": "algorithmic FLOPs; operands are fp16 hi/lo pairs so the kernel issues 3 MMAs per product "
                 "(fp32-faithful parity), i.e. executed tensor FLOPs are 3x this figure",
-        "kernel_share_of_step": k_share_ms / max(sum(stage.values()), 1e-9),
-        "whole_pipeline_achieved": value * FLOP_GRU_TOTAL / 1e12,
-        "whole_pipeline_frac": value * FLOP_GRU_TOTAL / 1e12 / peaks["tflops_sustained"] / world,
-        "stage_ms": stage,
+        "kernel_share_of_step": k_share_ms / max(sum(solo.values()), 1e-9),
+        "solo_stage_ms": solo, "solo_windows": b0,
+        "timed_region_stage_ms": stage,
+        "whole_pipeline_achieved": value / world * flop_gru / 1e12,
+        "whole_pipeline_frac": value / world * flop_gru / 1e12 / peaks["tflops_sustained"],
+        "whole_pipeline_note": "all GRU-gate FLOPs (both recurrences + the layer-1 projection, all three on the tensor "
+                               "cores) / step time of the timed region, against the sustained bf16 peak",
     }
 
     if rank != 0:
@@ -405,9 +516,9 @@ def main():
     if not args.no_cpu_baseline:
         cores = host_cores()
         log("cpu baseline on %d threads" % cores)
-        rate, sec, ccols = cpu_reference_rate(cores, args.cpu_windows, args.cpu_cols, F, steps=1, warmup=0)
+        rate, sec, ccols = cpu_reference_rate(cores, args.cpu_windows, args.cpu_cols, F, steps=1, warmup=1)
         cpu_baseline = {"value": rate, "unit": "positions/s", "cores": cores, "kind": "port",
-                        "sample": "%d windows x %d cols, 1 pass (%.1f s), torch %s fp32 nn.GRU oracle" % (
+                        "sample": "%d windows x %d cols, 1 warm-up + 1 timed pass (%.1f s), torch %s fp32 nn.GRU oracle" % (
                             args.cpu_windows, ccols, sec, torch.__version__)}
     log("done")
 
@@ -418,18 +529,23 @@ def main():
         "dtype": "f32 gate math; fp16 hi/lo split tensor-core operands, fp32 accumulate"
         if args.precision == "tc" else "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name() if (B, T) == (WINDOWS, COLS) else
+        "config": {"workload": workload_name(args.config) if not (args.windows or args.cols) else
                    "synthetic %d windows x %d cols x %d feats" % (B, T, F),
-                   "windows_per_gpu": B, "cols": T, "precision": args.precision,
-                   "l2_policy": "inputs larger than L2 (444 MB of features, >3 GB of activations per step)",
+                   "baseline_config": args.config, "windows_per_gpu": B, "cols": T, "features": F,
+                   "precision": args.precision, "rec_mode": args.rec_mode,
+                   "group_windows": min(group, B), "batch_windows": bw, "batches_in_flight": depth,
+                   "l2_policy": "inputs larger than L2 (%d MB of features, > 3 GB of activations per step)" % (feats.nbytes >> 20),
                    "sm_count": info["sm_count"]},
         "e2e": {"value": e2e, "unit": "positions/s", "h2d_bytes_per_step": int(feats.nbytes),
-                "d2h_bytes_per_step": int(P * 5 * 4 + P), "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": int(P * 5 * 4 + P), "ms_per_step": e2e_ms / args.steps,
+                "batch_windows": bw},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
+    if variant_ms:
+        line["e2e"]["variant_decode_ms_per_step"] = float(np.mean(variant_ms))
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

@@ -302,6 +302,10 @@ int mdk_debug_rec_trace(int device, int enable, uint64_t *out);
  * stores, 2: proxy fence, 4: gate arithmetic, 8: x staging, 16: gi staging, 32: tile copy-out) so that the cycle trace
  * shows what each costs; results are wrong while any bit is set.  0 restores normal operation. */
 int mdk_debug_pp_flags(int flags);
+/* completion times (ms after mdk_engine_timer_start's event) of the eight stage events of the last n_last forwards,
+ * oldest first: out is float[n_last][8] = start, features in, inproj0, rec0, inproj1, rec1, head, end.  Shows how the
+ * lanes' kernels actually interleaved. */
+int mdk_debug_timeline(mdk_engine *e, int n_last, float *out);
 /* partial logits of the last forward on the fused-head path: float32 [2 directions][tiles][T][5 classes][16 windows]
  * (what the layer-1 recurrence writes instead of h1); per-direction parity checks of the fused linear head */
 int mdk_debug_read_plog(mdk_engine *e, float *out_host, int64_t n_floats);

@@ -1,6 +1,7 @@
 // C ABI of libmedaka_b200 (include/medaka_b200.h): engine life-cycle, weight loading, the forward
 // pipeline, and the featuriser / decode entry points.  Host orchestration only - kernels live in
 // misc.cu, gru_fp32.cu and gru_tc.cu.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -86,35 +87,36 @@ static int prepare_weights(mdk_engine *e) {
     return MDK_OK;
 }
 
-static int ensure_workspace(mdk_engine *e, mdk_lane &ln, int64_t B, int64_t T) {
+static int ensure_workspace(mdk_engine *e, mdk_ws &ws, int64_t B, int64_t T) {
     // rows of the tile-interleaved intermediates (>= B*T: the last window tile is padded to 16 windows)
     const int64_t rows = tiled_rows(B, T);
     const int64_t need = ((rows + XT_ROWS - 1) / XT_ROWS) * XT_ROWS;
-    if (need <= ln.cap_pos) return MDK_OK;
-    MDK_CUDA(cudaStreamSynchronize(ln.stream));
-    dev_free(ln.gi);
-    if (ln.h0) { cudaFree(ln.h0); ln.h0 = nullptr; }
-    dev_free(ln.h1);
-    ln.cap_h1 = 0;
-    dev_free(ln.plog);
-    ln.cap_pos = 0;
+    if (need <= ws.cap_pos) return MDK_OK;
+    MDK_CUDA(cudaStreamSynchronize(ws.stream));
+    dev_free(ws.gi);
+    if (ws.h0) { cudaFree(ws.h0); ws.h0 = nullptr; }
+    dev_free(ws.h1);
+    ws.cap_h1 = 0;
+    dev_free(ws.plog);
+    ws.cap_pos = 0;
     int rc;
-    if ((rc = dev_alloc(&ln.gi, (size_t)need * GI_COLS))) return rc;
-    MDK_CUDA(cudaMalloc(&ln.h0, (size_t)need * H2 * sizeof(float)));
-    if ((rc = dev_alloc(&ln.plog, (size_t)NDIR * (need / WT) * PLOG_TS_FLOATS))) return rc;
-    ln.cap_pos = need;
+    if ((rc = dev_alloc(&ws.gi, (size_t)need * GI_COLS))) return rc;
+    MDK_CUDA(cudaMalloc(&ws.h0, (size_t)need * H2 * sizeof(float)));
+    if ((rc = dev_alloc(&ws.plog, (size_t)NDIR * (need / WT) * PLOG_TS_FLOATS))) return rc;
+    if (!ws.gemm_ctr) MDK_CUDA(cudaMalloc(&ws.gemm_ctr, 8 * sizeof(int)));
+    ws.cap_pos = need;
     return MDK_OK;
 }
 
 // h1 (the layer-1 output, 1 KiB / position) only exists on the unfused-head paths: allocated on first use
-static int ensure_h1(mdk_lane &ln) {
-    if (ln.cap_h1 >= ln.cap_pos && ln.h1) return MDK_OK;
-    MDK_CUDA(cudaStreamSynchronize(ln.stream));
-    dev_free(ln.h1);
-    ln.cap_h1 = 0;
+static int ensure_h1(mdk_ws &ws) {
+    if (ws.cap_h1 >= ws.cap_pos && ws.h1) return MDK_OK;
+    MDK_CUDA(cudaStreamSynchronize(ws.stream));
+    dev_free(ws.h1);
+    ws.cap_h1 = 0;
     int rc;
-    if ((rc = dev_alloc(&ln.h1, (size_t)ln.cap_pos * H2))) return rc;
-    ln.cap_h1 = ln.cap_pos;
+    if ((rc = dev_alloc(&ws.h1, (size_t)ws.cap_pos * H2))) return rc;
+    ws.cap_h1 = ws.cap_pos;
     return MDK_OK;
 }
 
@@ -122,7 +124,7 @@ static int ensure_io(mdk_engine *e, mdk_lane &ln, int64_t B, int64_t T) {
     const int64_t P = B * T;
     const int64_t feats = P * e->desc.num_features;
     if (P <= ln.cap_io && feats <= ln.cap_feats) return MDK_OK;
-    MDK_CUDA(cudaStreamSynchronize(ln.stream));
+    MDK_CUDA(cudaStreamSynchronize(ln.ws->stream));
     MDK_CUDA(cudaStreamSynchronize(e->copy_in));
     MDK_CUDA(cudaStreamSynchronize(e->copy_out));
     ln.cap_io = 0; ln.cap_feats = 0;
@@ -146,14 +148,14 @@ static bool use_pingpong(const mdk_engine *e, int64_t B) {
     return tiles * NDIR > (int64_t)e->sm_count / 2;
 }
 
-// The forward pipeline on the lane's stream.  ev[1..6] bracket the stages for mdk_timings.
-static int run_forward(mdk_engine *e, mdk_lane &ln, const float *feats_dev, int64_t B, int64_t T, float *probs_dev,
+// The forward pipeline on the workspace's stream.  ev[1..6] bracket the stages for mdk_timings.
+static int run_forward(mdk_engine *e, mdk_ws &ws, const float *feats_dev, int64_t B, int64_t T, float *probs_dev,
                        float *logits_dev, uint8_t *labels_dev) {
     int rc;
     if ((rc = prepare_weights(e))) return rc;
-    if ((rc = ensure_workspace(e, ln, B, T))) return rc;
+    if ((rc = ensure_workspace(e, ws, B, T))) return rc;
     const int64_t P = B * T;
-    cudaStream_t s = ln.stream;
+    cudaStream_t s = ws.stream;
     const bool tc = e->precision == MDK_PREC_TC;
     int launches = 0;
     const bool fuse_x = tc && e->fuse_x && e->layer[0].w_x_tm != nullptr;
@@ -162,49 +164,49 @@ static int run_forward(mdk_engine *e, mdk_lane &ln, const float *feats_dev, int6
     // instead of the 1 KiB/position h1 round trip): always on the ping-pong path, on the one-tile path when the batch
     // is one tile per CTA
     const bool fuse_head = tc && !e->keep_act && (pp || rec_tc_can_fuse_logits(B, e->sm_count));
-    if (!fuse_head && (rc = ensure_h1(ln))) return rc;
+    if (!fuse_head && (rc = ensure_h1(ws))) return rc;
     MDK_CUDA(cudaEventRecord(e->ev[1], s));
     if (!fuse_x) {
-        MDK_CUDA(launch_inproj0(feats_dev, e->layer[0].w_in_packed, e->layer[0].bias_gi, ln.gi, P,
+        MDK_CUDA(launch_inproj0(feats_dev, e->layer[0].w_in_packed, e->layer[0].bias_gi, ws.gi, P,
                                 e->desc.num_features, T, tc ? 1 : 0, s));
         launches++;
     }
     MDK_CUDA(cudaEventRecord(e->ev[2], s));
     if (tc) {
         const RecXArgs fx{feats_dev, e->layer[0].w_x_tm, e->layer[0].bias_gi_tc, e->desc.num_features};
-        if (pp) MDK_CUDA(launch_rec_pp(0, ln.gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn_tc, ln.h0, B, T, s,
+        if (pp) MDK_CUDA(launch_rec_pp(0, ws.gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn_tc, ws.h0, B, T, s,
                                        nullptr, nullptr, e->prod_mask));
-        else MDK_CUDA(launch_rec_tc(ln.gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn_tc, ln.h0, 1, B, T,
+        else MDK_CUDA(launch_rec_tc(ws.gi, fuse_x ? &fx : nullptr, e->layer[0].w_hh_tm, e->layer[0].b_hn_tc, ws.h0, 1, B, T,
                                     e->sm_count, s, nullptr, nullptr, e->prod_mask));
     } else {
-        MDK_CUDA(launch_rec_fp32(ln.gi, e->layer[0].w_hh_t, e->layer[0].b_hn, (float *)ln.h0, B, T, s));
+        MDK_CUDA(launch_rec_fp32(ws.gi, e->layer[0].w_hh_t, e->layer[0].b_hn, (float *)ws.h0, B, T, s));
     }
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[3], s));
-    if (tc) MDK_CUDA(launch_gemm_tc(ln.h0, e->layer[1].w_in_tc, e->layer[1].bias_gi_tc, ln.gi, tiled_rows(B, T), e->sm_count, s,
-                                    e->prod_mask));
-    else MDK_CUDA(launch_gemm_fp32((const float *)ln.h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, ln.gi, P, s));
+    if (tc) MDK_CUDA(launch_gemm_tc(ws.h0, e->layer[1].w_in_tc, e->layer[1].bias_gi_tc, ws.gi, tiled_rows(B, T), e->sm_count, s,
+                                    e->prod_mask, ws.gemm_ctr));
+    else MDK_CUDA(launch_gemm_fp32((const float *)ws.h0, e->layer[1].w_in_packed, e->layer[1].bias_gi, ws.gi, P, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[4], s));
     if (tc) {
-        if (pp && fuse_head) MDK_CUDA(launch_rec_pp(1, ln.gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, nullptr, B, T, s,
-                                                    e->lin_w_tc, ln.plog, e->prod_mask));
-        else MDK_CUDA(launch_rec_tc(ln.gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, ln.h1, 0, B, T, e->sm_count, s,
-                                    fuse_head ? e->lin_w_tc : nullptr, fuse_head ? ln.plog : nullptr, e->prod_mask));
+        if (pp && fuse_head) MDK_CUDA(launch_rec_pp(1, ws.gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, nullptr, B, T, s,
+                                                    e->lin_w_tc, ws.plog, e->prod_mask));
+        else MDK_CUDA(launch_rec_tc(ws.gi, nullptr, e->layer[1].w_hh_tm, e->layer[1].b_hn_tc, ws.h1, 0, B, T, e->sm_count, s,
+                                    fuse_head ? e->lin_w_tc : nullptr, fuse_head ? ws.plog : nullptr, e->prod_mask));
     } else {
-        MDK_CUDA(launch_rec_fp32(ln.gi, e->layer[1].w_hh_t, e->layer[1].b_hn, ln.h1, B, T, s));
+        MDK_CUDA(launch_rec_fp32(ws.gi, e->layer[1].w_hh_t, e->layer[1].b_hn, ws.h1, B, T, s));
     }
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[5], s));
-    if (fuse_head) MDK_CUDA(launch_head_plog(ln.plog, e->lin_b, B, T, probs_dev, logits_dev, labels_dev, s));
-    else MDK_CUDA(launch_head(ln.h1, e->lin_w, e->lin_b, B, T, tc ? 1 : 0, probs_dev, logits_dev, labels_dev, s));
+    if (fuse_head) MDK_CUDA(launch_head_plog(ws.plog, e->lin_b, B, T, probs_dev, logits_dev, labels_dev, s));
+    else MDK_CUDA(launch_head(ws.h1, e->lin_w, e->lin_b, B, T, tc ? 1 : 0, probs_dev, logits_dev, labels_dev, s));
     launches++;
     MDK_CUDA(cudaEventRecord(e->ev[6], s));
     e->launches += launches;
     e->last.launches = launches;
-    ln.last_fused_head = fuse_head;
-    ln.last_B = B; ln.last_T = T; ln.last_precision = e->precision;
-    e->last_lane = (int)(&ln - e->lane);
+    ws.last_fused_head = fuse_head;
+    ws.last_B = B; ws.last_T = T; ws.last_precision = e->precision;
+    e->last_ws = (int)(&ws - e->ws);
     return MDK_OK;
 }
 
@@ -236,13 +238,13 @@ static int launch_group(mdk_engine *e) {
     ln.open = false;
     if (ln.items.empty()) return MDK_OK;
     int rc;
-    cudaStream_t s = ln.stream;
+    cudaStream_t s = ln.ws->stream;
     e->ev = e->evr[e->fwd_count % mdk_engine::EV_RING];
     e->fwd_count++;
     MDK_CUDA(cudaEventRecord(e->ev[0], s));
     MDK_CUDA(cudaEventRecord(ln.ev_in, e->copy_in));      // every feature copy of the group was queued on copy_in
     MDK_CUDA(cudaStreamWaitEvent(s, ln.ev_in, 0));
-    if ((rc = run_forward(e, ln, ln.d_feats, ln.gB, ln.gT, ln.d_probs, ln.want_logits ? ln.d_logits : nullptr,
+    if ((rc = run_forward(e, *ln.ws, ln.d_feats, ln.gB, ln.gT, ln.d_probs, ln.want_logits ? ln.d_logits : nullptr,
                           ln.want_labels ? ln.d_labels : nullptr)))
         return rc;
     MDK_CUDA(cudaEventRecord(ln.ev_done, s));
@@ -374,14 +376,19 @@ int mdk_engine_create(int device, const mdk_model_desc *desc, mdk_engine **out) 
         v = getenv("MDK_PRODUCTS");
         if (v && v[0] >= '1' && v[0] <= '7') e->prod_mask = ((uint32_t)(v[0] - '0') & 7u) | 1u;
     }
-    for (auto &ln : e->lane) {
-        cudaError_t err = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking);
+    for (auto &ws : e->ws) {
+        cudaError_t err = cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking);
         if (err != cudaSuccess) { mdk_engine_destroy(e); return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
+    }
+    for (int i = 0; i < mdk_engine::N_LANES; ++i) {
+        mdk_lane &ln = e->lane[i];
+        ln.ws = i < mdk_engine::BIG_LANES ? &e->ws[i % mdk_engine::BIG_WS]
+                                          : &e->ws[mdk_engine::BIG_WS + (i - mdk_engine::BIG_LANES)];
         cudaEventCreateWithFlags(&ln.ev_in, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ln.ev_out, cudaEventDisableTiming);
     }
-    e->stream = e->lane[0].stream;
+    e->stream = e->ws[0].stream;
     for (auto &set : e->evr) for (auto &ev : set) cudaEventCreate(&ev);
     cudaStreamCreateWithFlags(&e->copy_in, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&e->copy_out, cudaStreamNonBlocking);
@@ -394,7 +401,7 @@ int mdk_engine_create(int device, const mdk_model_desc *desc, mdk_engine **out) 
 int mdk_engine_destroy(mdk_engine *e) {
     if (!e) return MDK_OK;
     cudaSetDevice(e->device);
-    for (auto &ln : e->lane) if (ln.stream) cudaStreamSynchronize(ln.stream);
+    for (auto &ws : e->ws) if (ws.stream) cudaStreamSynchronize(ws.stream);
     if (e->copy_out) cudaStreamSynchronize(e->copy_out);
     for (int l = 0; l < 2; ++l) {
         LayerWeights &lw = e->layer[l];
@@ -404,14 +411,17 @@ int mdk_engine_destroy(mdk_engine *e) {
         dev_free(lw.w_hh_tm); dev_free(lw.w_x_tm); dev_free(lw.w_in_tc);
     }
     dev_free(e->lin_w); dev_free(e->lin_b); dev_free(e->lin_w_tc);
+    for (auto &ws : e->ws) {
+        dev_free(ws.gi); dev_free(ws.h1); dev_free(ws.plog);
+        if (ws.gemm_ctr) { cudaFree(ws.gemm_ctr); ws.gemm_ctr = nullptr; }
+        if (ws.h0) cudaFree(ws.h0);
+        if (ws.stream) cudaStreamDestroy(ws.stream);
+    }
     for (auto &ln : e->lane) {
-        dev_free(ln.gi); dev_free(ln.h1); dev_free(ln.plog);
-        if (ln.h0) cudaFree(ln.h0);
         dev_free(ln.d_feats); dev_free(ln.d_probs); dev_free(ln.d_logits); dev_free(ln.d_labels);
         if (ln.ev_in) cudaEventDestroy(ln.ev_in);
         if (ln.ev_done) cudaEventDestroy(ln.ev_done);
         if (ln.ev_out) cudaEventDestroy(ln.ev_out);
-        if (ln.stream) cudaStreamDestroy(ln.stream);
     }
     if (e->copy_in) cudaStreamDestroy(e->copy_in);
     if (e->copy_out) cudaStreamDestroy(e->copy_out);
@@ -427,7 +437,7 @@ int mdk_engine_destroy(mdk_engine *e) {
 static int quiesce(mdk_engine *e) {
     int rc = launch_group(e);
     if (rc) return rc;
-    for (auto &ln : e->lane) MDK_CUDA(cudaStreamSynchronize(ln.stream));
+    for (auto &ws : e->ws) MDK_CUDA(cudaStreamSynchronize(ws.stream));
     return MDK_OK;
 }
 
@@ -496,8 +506,8 @@ int mdk_engine_set_group_windows(mdk_engine *e, int64_t windows) {
     return MDK_OK;
 }
 
-// Reserve = size the two big lanes (workspace + staging) for groups of up to B windows of T columns.  This is also what
-// switches coalescing on: a group collects submitted batches only as far as its lane's staging buffers reach.
+// Reserve = size the big workspaces and the big lanes' staging for groups of up to B windows of T columns.  This is also
+// what switches coalescing on: a group collects submitted batches only as far as its lane's staging buffers reach.
 int mdk_engine_reserve(mdk_engine *e, int64_t B, int64_t T) {
     MDK_REQUIRE(e && B >= 1 && T >= 1, MDK_ERR_ARG, "reserve: bad arguments");
     MDK_CUDA(cudaSetDevice(e->device));
@@ -508,7 +518,7 @@ int mdk_engine_reserve(mdk_engine *e, int64_t B, int64_t T) {
     for (int i = l0; i < l1; ++i) {
         mdk_lane &ln = e->lane[i];
         if (ln.busy) { MDK_CUDA(cudaEventSynchronize(ln.ev_out)); ln.busy = false; }
-        if ((rc = ensure_workspace(e, ln, B, T))) return rc;
+        if ((rc = ensure_workspace(e, *ln.ws, B, T))) return rc;
         if ((rc = ensure_io(e, ln, B, T))) return rc;
     }
     return MDK_OK;
@@ -520,17 +530,28 @@ int mdk_engine_forward_dev(mdk_engine *e, const float *feats_dev, int64_t B, int
     if ((rc = check_shapes(e, feats_dev, B, T, probs_dev))) return rc;
     MDK_CUDA(cudaSetDevice(e->device));
     if ((rc = launch_group(e))) return rc;
-    int li;
-    if ((rc = acquire_lane(e, B * T, &li))) return rc;
-    mdk_lane &ln = e->lane[li];
+    // device buffers need no staging: take the next workspace of the size class (stream order keeps it safe)
+    int wi;
+    if (B * T > mdk_engine::SMALL_POS) {
+        wi = e->next_big_ws;
+        e->next_big_ws = (e->next_big_ws + 1) % mdk_engine::BIG_WS;
+    } else {
+        wi = mdk_engine::BIG_WS + e->next_small;
+        e->next_small = (e->next_small + 1) % mdk_engine::SMALL_LANES;
+    }
+    mdk_ws &ws = e->ws[wi];
     e->ev = e->evr[e->fwd_count % mdk_engine::EV_RING];
     e->fwd_count++;
-    MDK_CUDA(cudaEventRecord(e->ev[0], ln.stream));
-    if ((rc = run_forward(e, ln, feats_dev, B, T, probs_dev, logits_dev, labels_dev))) return rc;
-    MDK_CUDA(cudaEventRecord(e->ev[7], ln.stream));
+    MDK_CUDA(cudaEventRecord(e->ev[0], ws.stream));
+    if ((rc = run_forward(e, ws, feats_dev, B, T, probs_dev, logits_dev, labels_dev))) return rc;
+    MDK_CUDA(cudaEventRecord(e->ev[7], ws.stream));
     return MDK_OK;
 }
 
+// Submitted batches are packed into groups window by window: a batch that does not fit what is left of the open group
+// is split (windows are independent, medaka/prediction.py:40-52 treats every row of a batch separately), so every
+// group of a long run is exactly one wave however the caller sized its batches.  The ticket follows the batch's last
+// piece; groups complete in submission order per lane and the pieces of one batch sit in consecutive groups.
 int mdk_engine_submit(mdk_engine *e, const float *feats_host, int64_t B, int64_t T, float *probs_host,
                       float *logits_host, uint8_t *labels_host, int64_t *ticket) {
     int rc;
@@ -538,41 +559,51 @@ int mdk_engine_submit(mdk_engine *e, const float *feats_host, int64_t B, int64_t
     MDK_REQUIRE(ticket, MDK_ERR_ARG, "submit: ticket is NULL");
     MDK_CUDA(cudaSetDevice(e->device));
     const int64_t gmax = e->group_windows > 0 ? e->group_windows : mdk_engine_preferred_windows(e);
-    // does the batch fit the group being collected?  (same window length, the lane's staging reaches, at most one wave)
-    if (e->open_lane >= 0) {
+    const int64_t F = e->desc.num_features;
+    if (e->open_lane >= 0 && e->lane[e->open_lane].gT != T && (rc = launch_group(e))) return rc;
+    int64_t done = 0;
+    while (done < B) {
+        if (e->open_lane < 0) {
+            int li;
+            if ((rc = acquire_lane(e, (B - done) * T, &li))) return rc;
+            mdk_lane &ln = e->lane[li];
+            // the staging grows to this batch (at most one wave of it); a reserved lane is already larger and keeps
+            // collecting further batches up to its size
+            if ((rc = ensure_io(e, ln, std::min<int64_t>(B - done, gmax), T))) return rc;
+            ln.items.clear();
+            ln.gB = 0; ln.gT = T;
+            ln.want_logits = false; ln.want_labels = false;
+            ln.open = true;
+            ln.group++;
+            e->open_lane = li;
+        }
         mdk_lane &ln = e->lane[e->open_lane];
-        const bool fits = T == ln.gT && ln.gB + B <= gmax && (ln.gB + B) * T <= ln.cap_io &&
-                          (ln.gB + B) * T * e->desc.num_features <= ln.cap_feats &&
-                          tiled_rows(ln.gB + B, T) <= ln.cap_pos;
-        if (!fits && (rc = launch_group(e))) return rc;
+        // windows the open group can still take: one wave, and what the lane's staging reaches
+        int64_t room = std::min(gmax, std::min(ln.cap_io / T, ln.cap_feats / (T * F))) - ln.gB;
+        if (ln.gB == 0 && room < 1) room = 1;        // (ensure_io above sized the staging for at least one window)
+        if (room < 1) {
+            if ((rc = launch_group(e))) return rc;
+            continue;
+        }
+        const int64_t n = std::min(room, B - done);
+        // copy-in stream: features H2D (asynchronous when feats_host is page-locked), behind the group's earlier pieces
+        MDK_CUDA(cudaMemcpyAsync(ln.d_feats + (size_t)ln.gB * T * F, feats_host + (size_t)done * T * F,
+                                 (size_t)n * T * F * sizeof(float), cudaMemcpyHostToDevice, e->copy_in));
+        ln.items.push_back(mdk_lane::Item{feats_host + (size_t)done * T * F, probs_host + (size_t)done * T * NCLS,
+                                          logits_host ? logits_host + (size_t)done * T * NCLS : nullptr,
+                                          labels_host ? labels_host + (size_t)done * T : nullptr, n});
+        ln.gB += n;
+        ln.want_logits = ln.want_logits || logits_host != nullptr;
+        ln.want_labels = ln.want_labels || labels_host != nullptr;
+        done += n;
+        if (done == B) {
+            const int64_t tk = e->submit_count++;
+            e->ticket_lane[tk % mdk_engine::TICKET_RING] = (int16_t)e->open_lane;
+            e->ticket_group[tk % mdk_engine::TICKET_RING] = ln.group;
+            *ticket = tk;
+        }
+        if (n == room && (rc = launch_group(e))) return rc;      // full: launch right away
     }
-    if (e->open_lane < 0) {
-        int li;
-        if ((rc = acquire_lane(e, B * T, &li))) return rc;
-        mdk_lane &ln = e->lane[li];
-        if ((rc = ensure_io(e, ln, B, T))) return rc;
-        if ((rc = ensure_workspace(e, ln, B, T))) return rc;
-        ln.items.clear();
-        ln.gB = 0; ln.gT = T;
-        ln.want_logits = false; ln.want_labels = false;
-        ln.open = true;
-        ln.group++;
-        e->open_lane = li;
-    }
-    mdk_lane &ln = e->lane[e->open_lane];
-    // copy-in stream: features H2D (asynchronous when feats_host is page-locked), behind the group's earlier batches
-    MDK_CUDA(cudaMemcpyAsync(ln.d_feats + (size_t)ln.gB * T * e->desc.num_features, feats_host,
-                             (size_t)B * T * e->desc.num_features * sizeof(float), cudaMemcpyHostToDevice, e->copy_in));
-    ln.items.push_back(mdk_lane::Item{feats_host, probs_host, logits_host, labels_host, B});
-    ln.gB += B;
-    ln.want_logits = ln.want_logits || logits_host != nullptr;
-    ln.want_labels = ln.want_labels || labels_host != nullptr;
-    const int64_t tk = e->submit_count++;
-    e->ticket_lane[tk % mdk_engine::TICKET_RING] = (int16_t)e->open_lane;
-    e->ticket_group[tk % mdk_engine::TICKET_RING] = ln.group;
-    *ticket = tk;
-    // a group that cannot take another batch of this size is launched right away
-    if (ln.gB + B > gmax || (ln.gB + B) * T > ln.cap_io || tiled_rows(ln.gB + B, T) > ln.cap_pos) return launch_group(e);
     return MDK_OK;
 }
 
@@ -616,7 +647,7 @@ int mdk_engine_sync(mdk_engine *e) {
     int rc = launch_group(e);
     if (rc) return rc;
     MDK_CUDA(cudaStreamSynchronize(e->copy_in));
-    for (auto &ln : e->lane) MDK_CUDA(cudaStreamSynchronize(ln.stream));
+    for (auto &ws : e->ws) MDK_CUDA(cudaStreamSynchronize(ws.stream));
     MDK_CUDA(cudaStreamSynchronize(e->copy_out));
     for (auto &ln : e->lane) ln.busy = false;
     return MDK_OK;
@@ -640,7 +671,7 @@ int mdk_engine_mean_timings(mdk_engine *e, int n_last, mdk_timings *out) {
     MDK_REQUIRE(n_last >= 1 && n_last <= mdk_engine::EV_RING, MDK_ERR_ARG, "mean_timings: n_last out of range");
     MDK_REQUIRE(e->fwd_count >= n_last, MDK_ERR_STATE, "mean_timings: fewer forwards recorded than requested");
     MDK_CUDA(cudaSetDevice(e->device));
-    for (auto &ln : e->lane) MDK_CUDA(cudaStreamSynchronize(ln.stream));
+    for (auto &ws : e->ws) MDK_CUDA(cudaStreamSynchronize(ws.stream));
     mdk_timings acc{};
     for (int i = 0; i < n_last; ++i) {
         mdk_timings t{};
@@ -657,6 +688,20 @@ int mdk_engine_mean_timings(mdk_engine *e, int n_last, mdk_timings *out) {
     return MDK_OK;
 }
 
+// Diagnostics: completion times (ms after the timer's start event) of the eight stage events of the last n forwards,
+// oldest first - the schedule the lanes actually ran (tools/diag.py --check timeline).
+int mdk_debug_timeline(mdk_engine *e, int n_last, float *out) {
+    MDK_REQUIRE(e && out, MDK_ERR_ARG, "NULL argument");
+    MDK_REQUIRE(n_last >= 1 && n_last <= mdk_engine::EV_RING && e->fwd_count >= n_last, MDK_ERR_ARG, "timeline: bad n_last");
+    MDK_CUDA(cudaSetDevice(e->device));
+    for (auto &ws : e->ws) MDK_CUDA(cudaStreamSynchronize(ws.stream));
+    for (int i = 0; i < n_last; ++i) {
+        cudaEvent_t *ev = e->evr[(e->fwd_count - n_last + i) % mdk_engine::EV_RING];
+        for (int k = 0; k < 8; ++k) MDK_CUDA(cudaEventElapsedTime(out + i * 8 + k, e->ev_timer[0], ev[k]));
+    }
+    return MDK_OK;
+}
+
 // The timed region spans every lane: the start event goes on lane 0 after all lanes have drained, the stop event on
 // lane 0 after it has been made to wait for every other lane and for the copy-out stream.
 int mdk_engine_timer_start(mdk_engine *e) {
@@ -666,7 +711,7 @@ int mdk_engine_timer_start(mdk_engine *e) {
     if (rc) return rc;
     MDK_CUDA(cudaEventRecord(e->ev_timer[0], e->stream));
     // work queued on the other lanes / copy streams after this point must not start before the start event
-    for (int i = 1; i < mdk_engine::N_LANES; ++i) MDK_CUDA(cudaStreamWaitEvent(e->lane[i].stream, e->ev_timer[0], 0));
+    for (int i = 1; i < mdk_engine::N_WS; ++i) MDK_CUDA(cudaStreamWaitEvent(e->ws[i].stream, e->ev_timer[0], 0));
     MDK_CUDA(cudaStreamWaitEvent(e->copy_in, e->ev_timer[0], 0));
     return MDK_OK;
 }
@@ -675,8 +720,8 @@ int mdk_engine_timer_stop(mdk_engine *e, float *elapsed_ms) {
     MDK_CUDA(cudaSetDevice(e->device));
     int rc = launch_group(e);
     if (rc) return rc;
-    for (int i = 1; i < mdk_engine::N_LANES; ++i) {
-        MDK_CUDA(cudaEventRecord(e->ev_join, e->lane[i].stream));
+    for (int i = 1; i < mdk_engine::N_WS; ++i) {
+        MDK_CUDA(cudaEventRecord(e->ev_join, e->ws[i].stream));
         MDK_CUDA(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
     }
     MDK_CUDA(cudaEventRecord(e->ev_join, e->copy_out));     // the end event must follow every copy-out still in flight
@@ -690,7 +735,7 @@ int mdk_engine_timer_stop(mdk_engine *e, float *elapsed_ms) {
 int mdk_engine_read_activation(mdk_engine *e, int which, float *out_host, int64_t n_floats) {
     MDK_REQUIRE(e && out_host, MDK_ERR_ARG, "NULL argument");
     MDK_REQUIRE(which == 0 || which == 1, MDK_ERR_ARG, "read_activation: which must be 0 or 1");
-    mdk_lane &ln = e->lane[e->last_lane];
+    mdk_ws &ln = e->ws[e->last_ws];
     const int64_t P = ln.last_B * ln.last_T;
     MDK_REQUIRE(P > 0 && n_floats == P * H2, MDK_ERR_ARG, "read_activation: size must be B*T*256 of the last forward");
     MDK_REQUIRE(!(which == 1 && ln.last_fused_head), MDK_ERR_STATE,
@@ -723,7 +768,7 @@ int mdk_debug_pp_flags(int flags) {
 
 int mdk_debug_read_plog(mdk_engine *e, float *out_host, int64_t n_floats) {
     MDK_REQUIRE(e && out_host, MDK_ERR_ARG, "NULL argument");
-    mdk_lane &ln = e->lane[e->last_lane];
+    mdk_ws &ln = e->ws[e->last_ws];
     MDK_REQUIRE(ln.last_fused_head, MDK_ERR_STATE, "read_plog: the last forward did not run the fused head");
     const int64_t tiles = (ln.last_B + WT - 1) / WT;
     MDK_REQUIRE(n_floats == NDIR * tiles * ln.last_T * PLOG_TS_FLOATS, MDK_ERR_ARG, "read_plog: size must be 2*tiles*T*80");

@@ -95,19 +95,30 @@ struct LayerWeights {
 
 }  // namespace mdk
 
-// One compute lane of the engine: a stream, the workspace of one forward and the device-side staging of one GROUP of
-// submitted batches.  Groups on different lanes run concurrently: the ping-pong recurrent kernels (gru_pp.cu) need only
-// half of the SMs for a 1184-window group, so the layer-1 pass of group k shares the GPU with the layer-0 pass of group
-// k+1; small forwards (the B = 1 remainder regions of medaka/prediction.py:196-209) spread over the small lanes.
-struct mdk_lane {
+// The engine runs GROUPS of windows.  A workspace (mdk_ws) is a compute stream plus the intermediates of one forward; a
+// lane (mdk_lane) is the device-side staging of one group of submitted batches (features in, probabilities / labels
+// out) and is bound to one workspace.  There are more big lanes than big workspaces: while two groups compute, a third
+// is receiving its features and a fourth is draining its results, so the copies never hold a workspace (48 GB for a
+// 1184 x 10 000 group) idle.  Groups on the two big workspaces run concurrently: the ping-pong recurrent kernels
+// (gru_pp.cu) need half of the SMs for a 1184-window group.  Small forwards (the B = 1 remainder regions of
+// medaka/prediction.py:196-209) spread over the small lanes, each with a workspace of its own.
+struct mdk_ws {
     cudaStream_t stream = nullptr;
-    // workspace (tile-interleaved intermediates, see below)
     int64_t cap_pos = 0;       // capacity in positions (rounded up to XT_ROWS)
     float *gi = nullptr;       // [cap_pos][768]
     void *h0 = nullptr;        // fp32 [cap_pos][256]  or  fp16 hi/lo tiles (same byte size)
     float *h1 = nullptr;       // [cap_pos][256], allocated on first use (unfused head only)
     int64_t cap_h1 = 0;
     float *plog = nullptr;     // fused head: per-direction partial logits [dir][tile-step][class 5][16 windows]
+    int *gemm_ctr = nullptr;   // the GEMM's six tile counters (zeroed in front of each launch)
+    // geometry of the last forward run here (mdk_engine_read_activation)
+    int64_t last_B = 0, last_T = 0;
+    int last_precision = -1;
+    bool last_fused_head = false;
+};
+
+struct mdk_lane {
+    mdk_ws *ws = nullptr;      // where the lane's groups compute (fixed at engine creation)
     // device staging of the group's host buffers
     int64_t cap_io = 0;        // positions
     int64_t cap_feats = 0;     // floats
@@ -126,10 +137,6 @@ struct mdk_lane {
     bool want_logits = false, want_labels = false;
     bool open = false, busy = false;
     int64_t group = -1;        // serial number of the lane's current (open / in-flight / last finished) group
-    // geometry of the last forward run on this lane (mdk_engine_read_activation)
-    int64_t last_B = 0, last_T = 0;
-    int last_precision = -1;
-    bool last_fused_head = false;
 };
 
 struct mdk_engine {
@@ -140,14 +147,16 @@ struct mdk_engine {
     bool fuse_x = true;           // layer-0 input projection fused into the recurrence (F <= 16); MDK_NO_FUSE_X=1 disables
     int rec_mode = MDK_REC_AUTO;  // which recurrent kernel the tensor-core path runs (MDK_REC_*)
     uint32_t prod_mask = 7u;      // fp16 products per contraction (mdk_engine_set_products)
-    static constexpr int BIG_LANES = 2, SMALL_LANES = 14, N_LANES = BIG_LANES + SMALL_LANES;
+    static constexpr int BIG_WS = 2, BIG_LANES = 4, SMALL_LANES = 14;
+    static constexpr int N_LANES = BIG_LANES + SMALL_LANES, N_WS = BIG_WS + SMALL_LANES;
     static constexpr int64_t SMALL_POS = 1 << 18;   // forwards up to this many positions run on the small lanes
-    mdk_lane lane[N_LANES];
-    int next_big = 0, next_small = 0;
+    mdk_ws ws[N_WS];              // [0, BIG_WS): big groups; then one per small lane
+    mdk_lane lane[N_LANES];       // big lane j computes on ws[j % BIG_WS], small lane i on ws[BIG_WS + i]
+    int next_big = 0, next_small = 0, next_big_ws = 0;
     int open_lane = -1;           // lane whose group is still collecting batches (at most one), -1 = none
-    int last_lane = 0;            // lane of the most recent forward
+    int last_ws = 0;              // workspace of the most recent forward
     int64_t group_windows = 0;    // most windows coalesced into one group (0 = one wave, mdk_engine_preferred_windows)
-    cudaStream_t stream = nullptr;       // == lane[0].stream: weight preparation, timers
+    cudaStream_t stream = nullptr;       // == ws[0].stream: weight preparation, timers
     static constexpr int EV_RING = 32;   // per-forward event sets kept for mdk_engine_mean_timings
     cudaEvent_t evr[EV_RING][8] = {};
     cudaEvent_t *ev = evr[0];            // event set of the forward being queued
@@ -222,7 +231,7 @@ cudaError_t launch_head_plog(const float *plog, const float *lin_b, int64_t B, i
 cudaError_t launch_pack_linear(const float *lin_w, __half *lin_w_tc, cudaStream_t s);
 constexpr int PLOG_TS_FLOATS = NCLS * WT;     // 80 floats per (tile-step, direction)
 cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const float *bias, float *gi, int64_t P,
-                           int sm_count, cudaStream_t s, uint32_t prod_mask = 7u);
+                           int sm_count, cudaStream_t s, uint32_t prod_mask, int *tile_ctr);
 int selftest_umma(int device, const float *A, const float *B, float *D, int N, int K, int variant);
 // pileup.cu
 cudaError_t plp_scratch(size_t bytes, uint8_t **out, int slot);   // per-host-thread cached device buffers (slot 0 / 1)

@@ -918,13 +918,21 @@ constexpr uint32_t GT_W_COLS = 2 * (H2 / 2);                    // weight block 
 // per 64 cycles = the entire 128 B/clk, leaving nothing for the bulk-copy writes) and doubles the pipeline depth.
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w_in_tm,
-               const float *__restrict__ bias, float *__restrict__ gi, int64_t P, int64_t ntiles, uint32_t prod_mask) {
+               const float *__restrict__ bias, float *__restrict__ gi, int64_t P, int64_t ntiles, uint32_t prod_mask,
+               int *__restrict__ tile_ctr) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + GT_BAR_OFF);
     uint64_t *empty = full + GT_STAGES;
     uint64_t *acc_full = empty + GT_STAGES;
     uint64_t *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    // Tiles are CLAIMED, not strided: the producer takes the next tile of its weight block from tile_ctr[blk] and hands
+    // the index down the pipeline (stage_tile with the stage's full barrier, acc_tile with the accumulator's).  A CTA
+    // that reaches its SM late - the other lane's recurrent kernel holds up to half of them - then simply takes fewer
+    // tiles, and the kernel ends when the work does instead of when the last-placed CTA has finished a fixed share.
+    volatile int *stage_tile = reinterpret_cast<volatile int *>(tmem_slot + 1);   // [GT_STAGES]; -1 = no more tiles
+    volatile int *acc_tile = stage_tile + GT_STAGES;                              // [2]
+    volatile int *first_tile = acc_tile + 2;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -935,13 +943,12 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
     // instead of 12.5 GB (11.4 algorithmic); the kernel is at the power cap, so the saved HBM energy is clock for the whole
     // step: 10.7 -> 9.65 ms for this kernel and +7 % end to end (profiles/r01h_gemm_cta_order.md).
     const int blk = blockIdx.x;                 // weight block: dir*3 + gate
-    const int64_t tile0 = blockIdx.y;
-    const int64_t tstride = gridDim.y;
 
     if (tid == 0) {
         for (int i = 0; i < GT_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
         fence_mbar_init();
+        first_tile[0] = atomicAdd(tile_ctr + blk, 1);      // a CTA placed after the work ran out leaves at once
     }
     if (warp == 1) {
         tmem_alloc(tmem_slot, GT_TMEM_COLS);
@@ -951,8 +958,9 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const bool have_work = first_tile[0] < ntiles;
 
-    if (warp >= 2) {
+    if (have_work && warp >= 2) {
         // weights (row-major fp16 [blk][part][row j][k 256]) -> TMEM: lane j, plane p chunk ks at column (p*16+ks)*8
         const int q = warp & 3;
         const int jrow = q * 32 + lane;
@@ -972,15 +980,25 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
     __syncthreads();
     tc_fence_after_sync();
 
-    if (warp == 0) {
+    if (!have_work) {
+        // nothing claimed: fall through to the TMEM release
+    } else if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
-            for (int64_t tile = tile0; tile < ntiles; tile += tstride) {
+            for (int64_t tile = first_tile[0];; tile = atomicAdd(tile_ctr + blk, 1)) {
+                if (tile >= ntiles) {
+                    const uint32_t stage = it % GT_STAGES;
+                    mbar_wait(&empty[stage], ((it / GT_STAGES) & 1) ^ 1);
+                    stage_tile[stage] = -1;
+                    mbar_arrive(&full[stage]);
+                    break;
+                }
                 const uint8_t *src = x_tiles + tile * (int64_t)XT_TILE_BYTES;
                 for (int s = 0; s < XT_K / GT_KSLICE; ++s, ++it) {
                     const uint32_t stage = it % GT_STAGES;
                     mbar_wait(&empty[stage], ((it / GT_STAGES) & 1) ^ 1);
                     uint8_t *dst = smem + stage * GT_STAGE_BYTES;
+                    stage_tile[stage] = (int)tile;
                     mbar_arrive_expect_tx(&full[stage], GT_STAGE_BYTES);
                     bulk_g2s(dst, src + (size_t)s * GT_SLICE_BYTES, GT_SLICE_BYTES, &full[stage]);
                     bulk_g2s(dst + GT_SLICE_BYTES, src + XT_PLANE_BYTES + (size_t)s * GT_SLICE_BYTES,
@@ -998,7 +1016,7 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
             __trap();
         }
         uint32_t it = 0, tcount = 0;
-        for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++tcount) {
+        for (bool more = true; more; ++tcount) {
             const uint32_t as = tcount & 1;
             mbar_wait(&acc_empty[as], ((tcount >> 1) & 1) ^ 1);
             tc_fence_after_sync();
@@ -1006,6 +1024,16 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
                 const uint32_t stage = it % GT_STAGES;
                 mbar_wait(&full[stage], (it / GT_STAGES) & 1);
                 tc_fence_after_sync();
+                if (s == 0) {
+                    const int tile = stage_tile[stage];
+                    if (lane == 0) {
+                        acc_tile[as] = tile;
+                        fence_proxy_async_smem();      // the index is read behind a barrier the tensor core arrives on
+                        if (tile < 0) mbar_arrive(&acc_full[as]);
+                    }
+                    __syncwarp();
+                    if (tile < 0) { more = false; break; }
+                }
                 if (elect_one()) {
                     const uint32_t d = GT_W_COLS + as * XT_ROWS;
                     const uint64_t b_s = b_desc0 + (uint64_t)((stage * GT_STAGE_BYTES) >> 4);
@@ -1031,10 +1059,11 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int j = q * 32 + lane;
         const float bj = bias[blk * H + j];
-        uint32_t tcount = 0;
-        for (int64_t tile = tile0; tile < ntiles; tile += tstride, ++tcount) {
+        for (uint32_t tcount = 0;; ++tcount) {
             const uint32_t as = tcount & 1;
             mbar_wait(&acc_full[as], (tcount >> 1) & 1);
+            const int64_t tile = acc_tile[as];
+            if (tile < 0) break;
             tc_fence_after_sync();
             const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + GT_W_COLS + as * XT_ROWS;
             // quad layout (common.cuh): column c of this tile = tile-step tile*8 + c/16, window c%16; the four windows
@@ -1069,18 +1098,22 @@ gemm_tc_kernel(const uint8_t *__restrict__ x_tiles, const __half *__restrict__ w
 }
 
 cudaError_t launch_gemm_tc(const void *x_tiles, const __half *w_in_tm, const float *bias, float *gi, int64_t P,
-                           int sm_count, cudaStream_t s, uint32_t prod_mask) {
+                           int sm_count, cudaStream_t s, uint32_t prod_mask, int *tile_ctr) {
     if (P == 0) return cudaSuccess;
     const int64_t ntiles = (P + XT_ROWS - 1) / XT_ROWS;
     // (the attribute is per device: set it on every launch, a process may drive several GPUs)
     cudaError_t ea = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM);
     if (ea != cudaSuccess) return ea;
     int64_t ct = sm_count / 6;
+    static const int rows_env = getenv("MDK_GEMM_ROWS") ? atoi(getenv("MDK_GEMM_ROWS")) : 0;   // experiments only
+    if (rows_env > 0 && rows_env < ct) ct = rows_env;
     if (ct < 1) ct = 1;
     if (ct > ntiles) ct = ntiles;
     dim3 grid(6, (unsigned)ct);
+    ea = cudaMemsetAsync(tile_ctr, 0, 6 * sizeof(int), s);     // the six per-weight-block tile counters
+    if (ea != cudaSuccess) return ea;
     gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, s>>>(reinterpret_cast<const uint8_t *>(x_tiles), w_in_tm, bias, gi,
-                                                     P, ntiles, (prod_mask & 7u) | 1u);
+                                                     P, ntiles, (prod_mask & 7u) | 1u, tile_ctr);
     return cudaGetLastError();
 }
 

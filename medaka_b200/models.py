@@ -243,9 +243,10 @@ class GRUModel(object):
         """Asynchronous predict_on_batch: returns a handle whose ``result()`` is the CPU tensor [B,T,5].
 
         Up to ``slots`` calls may be in flight (each owns one set of page-locked staging arrays).  The engine
-        coalesces consecutive batches of the same window length into one device forward (mdk_engine_submit), so
-        ``run_prediction`` keeps about two device waves of batches queued: the reference's default 200-window batches
-        then run as ~1000-window groups on alternating compute lanes, with the PCIe copies under the compute.
+        packs consecutive batches of the same window length into one-wave groups window by window (mdk_engine_submit;
+        a batch may straddle two groups), so ``run_prediction`` keeps about three groups of batches queued: the
+        reference's default 200-window batches then run as 1184-window groups, two computing at a time, with the
+        PCIe copies of the neighbouring groups under the compute.
         """
         import torch
         x = _as_f32(self.get_model_input_features(batch))
@@ -269,11 +270,12 @@ class GRUModel(object):
         return _Handle()
 
     def lookahead(self, batch_size, window_len=None):
-        """How many ``predict_async`` calls of ``batch_size`` windows to keep in flight (two coalesced groups)."""
+        """How many ``predict_async`` calls of ``batch_size`` windows to keep in flight (three coalesced groups: two
+        computing, one copying in or out)."""
         pref = self.preferred_batch_size()
         if window_len is not None and batch_size * window_len <= (1 << 18):
             return 14                                   # small forwards rotate over the engine's small lanes
-        return int(max(2, min(64, 2 * ((pref + batch_size - 1) // max(batch_size, 1)) + 1)))
+        return int(max(2, min(64, 3 * ((pref + batch_size - 1) // max(batch_size, 1)) + 1)))
 
     def reserve(self, windows, window_len):
         """Size the engine's compute lanes for coalesced groups of up to ``windows`` windows (mdk_engine_reserve)."""

@@ -78,3 +78,36 @@ def test_submit_wait_matches_synchronous_forward():
     for s, p, l in zip(sync, probs, labels):
         assert np.array_equal(s.probs, p) and np.array_equal(s.labels, l)
     m.close()
+
+
+@pytest.mark.parametrize("group_windows,rec_mode", [(48, "one"), (48, "pp"), (7, "one")])
+def test_batches_split_across_groups(group_windows, rec_mode):
+    """Batches are packed into groups window by window: with groups smaller than a batch every batch straddles several
+    groups (and several lanes); results must equal the one-forward-per-batch results bit for bit and tickets must
+    cover the last piece."""
+    from medaka_b200 import models
+    sd = synth.synth_state_dict(5)
+    m = models.GRUModel(num_features=10)
+    m.load_state_dict(sd)
+    m.set_rec_mode(rec_mode)
+    sizes = [70, 33, 1, 120, 16, 50]
+    T = 2000                                   # big-lane class: B*T > 2^18 for the larger batches
+    batches = [synth.synth_features_fast(n, T, 10, seed=20 + i) for i, n in enumerate(sizes)]
+    sync = [m.forward_arrays(b, want_logits=True) for b in batches]
+    m.reserve(max(group_windows, 16), T)
+    m.set_group_windows(group_windows)
+    outs, tickets = [], []
+    for i, b in enumerate(batches):
+        x = m.pinned("sin%d" % i, b.shape, np.float32)
+        np.copyto(x, b)
+        p = m.pinned("sp%d" % i, b.shape[:2] + (5,), np.float32)
+        l = m.pinned("sl%d" % i, b.shape[:2], np.uint8)
+        g = m.pinned("sg%d" % i, b.shape[:2] + (5,), np.float32)
+        p[...] = -1.0
+        tickets.append(m.submit_arrays(x, p, l, g))
+        outs.append((p, l, g))
+    for t in reversed(tickets):                # waiting out of order is allowed
+        m.wait(t)
+    for s, (p, l, g) in zip(sync, outs):
+        assert np.array_equal(s.probs, p) and np.array_equal(s.labels, l) and np.array_equal(s.logits, g)
+    m.close()

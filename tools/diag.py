@@ -169,7 +169,8 @@ def check_rec_trace(arg):
 PP_SLOTS = ["issuer: H seen", "issuer: r queued", "issuer: z queued", "issuer: n queued", "relay: r arrived",
             "relay: z arrived", "relay: n arrived", "gate: r ld done", "gate: r math done", "gate: z ld done",
             "gate: z math done", "gate: n ld done", "gate: h written", "gate: arrived H", "issuer: logits queued",
-            "issuer: r guard passed", "issuer: z guard passed", "issuer: n guard passed", "issuer: logits guard passed"]
+            "issuer: r guard passed", "issuer: z guard passed", "issuer: n guard passed", "issuer: logits guard passed",
+            "issuer: r commit seen by issuer (L0 only)"]
 
 
 def check_pp(arg):
@@ -274,17 +275,57 @@ def check_pp_trace(arg):
         t = buf[layer].astype(np.int64)
         out = {}
         for X in (0, 1):
-            tt = t[:, X * 20:X * 20 + 19]
+            tt = t[:, X * 20:X * 20 + 20]
             rel = tt - tt[:, :1]
             out["tile%d" % X] = {"period": float(np.median(np.diff(tt[:, 0]))),
-                                 "offsets": {PP_SLOTS[k]: float(np.median(rel[:, k])) for k in range(19)}}
+                                 "offsets": {PP_SLOTS[k]: float(np.median(rel[:, k])) for k in range(20)}}
         out["B_minus_A_h_seen"] = float(np.median(t[:, 20] - t[:, 0]))
         res["layer%d" % layer] = out
     m.close()
     return res
 
 
-CHECKS = {"pp": check_pp, "rec_timing": check_rec_timing, "pp_trace": check_pp_trace, "selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism,
+def check_timeline(arg):
+    """'mode,B,T,n' -> stage completion times (ms) of n device-resident forwards queued back to back on alternating
+    lanes: the schedule the two lanes really ran."""
+    from medaka_b200 import libmedaka as lm, models
+    from oracle import synth
+    parts = arg.split(",")
+    mode, B, T, n = parts[0], int(parts[1]), int(parts[2]), int(parts[3])
+    lib, ffi = lm.load(), lm.ffi
+    m = models.GRUModel()
+    m.load_state_dict(synth.synth_state_dict(0))
+    m.set_rec_mode(mode)
+    m.reserve(B, T)
+    eng, dev = m.engine, 0
+    feats = synth.synth_features_fast(B, T, 10, seed=3)
+
+    def dalloc(nbytes):
+        pp = ffi.new("void **")
+        lm.check(lib.mdk_dev_alloc(dev, nbytes, pp))
+        return pp[0]
+    d_feats = dalloc(feats.nbytes)
+    lm.check(lib.mdk_memcpy_h2d(dev, d_feats, ffi.from_buffer(feats), feats.nbytes))
+    d_probs = [dalloc(B * T * 20), dalloc(B * T * 20)]
+
+    def fwd(i):
+        lm.check(lib.mdk_engine_forward_dev(eng, ffi.cast("const float *", d_feats), B, T,
+                                            ffi.cast("float *", d_probs[i & 1]), ffi.NULL, ffi.NULL))
+    for i in range(4):
+        fwd(i)
+    lm.check(lib.mdk_engine_sync(eng))
+    ms = ffi.new("float *")
+    lm.check(lib.mdk_engine_timer_start(eng))
+    for i in range(n):
+        fwd(i)
+    lm.check(lib.mdk_engine_timer_stop(eng, ms))
+    out = np.zeros((n, 8), dtype=np.float32)
+    lm.check(lib.mdk_debug_timeline(eng, n, ffi.cast("float *", ffi.from_buffer(out))))
+    rows = [[round(float(v), 2) for v in r[[0, 3, 4, 5, 6]]] for r in out]     # start, rec0, gemm, rec1, head done
+    return {"total_ms": float(ms[0]), "ms_per_forward": float(ms[0]) / n, "start_rec0_gemm_rec1_head": rows}
+
+
+CHECKS = {"timeline": check_timeline, "pp": check_pp, "rec_timing": check_rec_timing, "pp_trace": check_pp_trace, "selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism,
           "rec_trace": check_rec_trace}
 
 PLAN = [
