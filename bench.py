@@ -64,8 +64,30 @@ class ClockSampler(object):
         self.device = device
         self.lines = []
         self.proc = None
+        self.nvml = None
+        self.samples = []          # (sm MHz, reason bits, power W) from the NVML poller
+        self.stop_flag = False
 
     def start(self):
+        # NVML poller (a sample every ~10 ms: the timed region of a default run lasts a few hundred ms); nvidia-smi -lms
+        # is the fallback when the binding is missing
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.device
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.device])
+                except (ValueError, IndexError):
+                    idx = self.device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
@@ -76,11 +98,48 @@ class ClockSampler(object):
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    watts = None
+                self.samples.append((float(mhz), int(bits), watts))
+            except Exception:
+                break
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            nv = self.nvml
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            try:
+                smax = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            except Exception:
+                smax = None
+            names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+            sm = [x[0] for x in self.samples]
+            reasons = sorted(k for k, bit in names.items() if any(x[1] & bit for x in self.samples))
+            watts = [x[2] for x in self.samples if x[2] is not None]
+            out = {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                   "reasons": reasons, "source": "nvml"}
+            if sm:
+                out["sm_mhz_min"] = min(sm)
+            if watts:
+                out["power_w"] = statistics.median(watts)
+            return out
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -104,7 +163,7 @@ class ClockSampler(object):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def host_cores():
