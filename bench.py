@@ -333,6 +333,7 @@ def main():
     ffi = lm.ffi
     dev = local_rank if world > 1 else 0
     info = lm.require_gpu(dev)
+    sm_count = int(info["sm_count"])
 
     dist = None
     if world > 1:
@@ -456,6 +457,31 @@ def main():
     lm.check(lib.mdk_engine_mean_timings(eng, 1, tm))
     solo = {k: float(getattr(tm, k)) for k in ("inproj0_ms", "rec0_ms", "inproj1_ms", "rec1_ms", "head_ms")}
 
+    # the recurrent kernel with one CTA on every SM, alone on the GPU: a full wave of windows (2368 for the two-tile
+    # kernel) over as many columns as the reserved workspace holds - the per-step cost of the persistent kernel does
+    # not depend on the window length
+    full_wave = None
+    if args.precision == "tc" and args.config != 5:
+        tiles_b0 = (b0 + 15) // 16
+        pp_sel = args.rec_mode == "pp" or (args.rec_mode == "auto" and tiles_b0 * 2 > sm_count // 2)
+        fw_windows = 16 * sm_count if pp_sel else 8 * sm_count
+        fw_cols = (b0 * T) // fw_windows
+        if fw_cols >= 256:
+            model.set_rec_mode("pp" if pp_sel else "one")
+            for _ in range(2):
+                lm.check(lib.mdk_engine_forward_dev(eng, ffi.cast("const float *", d_feats), fw_windows, fw_cols,
+                                                    ffi.cast("float *", d_probs), ffi.NULL, ffi.cast("uint8_t *", d_labels)))
+                barrier()
+            lm.check(lib.mdk_engine_mean_timings(eng, 1, tm))
+            model.set_rec_mode(args.rec_mode)
+            fw_ms = 0.5 * (float(tm.rec0_ms) + float(tm.rec1_ms))
+            fw_tf = fw_windows * fw_cols * FLOP_REC_PER_LAYER / (fw_ms * 1e-3) / 1e12
+            pk = measured_peaks()
+            full_wave = {"windows": fw_windows, "cols": fw_cols, "ctas": sm_count, "rec0_ms": float(tm.rec0_ms),
+                         "rec1_ms": float(tm.rec1_ms), "inproj1_ms": float(tm.inproj1_ms), "achieved": fw_tf,
+                         "peak": pk["tflops_burst"], "frac": fw_tf / pk["tflops_burst"],
+                         "peak_source": "MEASURED_PEAKS.json bf16 burst (kernel timed alone)"}
+
     # ---- host-buffer leg ("e2e"): the reference-facing call with HOST buffers, the way run_prediction drives it -
     # batches of --batch-windows windows (the reference's --batch_size) submitted with a look-ahead
     # (mdk_engine_submit / mdk_engine_wait); every step copies its features in and its probabilities + labels out ----
@@ -529,37 +555,48 @@ def main():
     value = total_positions / (dev_ms * 1e-3)
     e2e = total_positions / (e2e_ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (tensor bound).  Per-kernel numbers come from the solo forward (one group
-    # of `b0` windows, nothing else on the GPU); `phase` is the steady-state figure of the timed region, where the
-    # layer-1 recurrence of one group overlaps the layer-0 recurrence of the next on the other half of the SMs ----
+    # ---- roofline of the dominant kernel (tensor bound) ----
+    # The recurrent kernel of a config-2 group runs on a PART of the GPU (ping-pong kernel: one CTA per window tile =
+    # 70 of 148 SMs for 1111 windows; the other lane's kernels use the rest), so its roofline is the tensor peak of the
+    # SMs it holds: peak = sustained bf16 peak x CTAs / SMs.  achieved = algorithmic FLOPs per launch / mean launch
+    # duration in the TIMED REGION (event to event on the launching stream; includes any wait for SMs, so it is a lower
+    # bound).  full_wave_solo is the same kernel launched alone with one CTA on every SM.
     peaks = measured_peaks()
     p0 = b0 * T
-    rec_ms = 0.5 * (solo["rec0_ms"] + solo["rec1_ms"])
+    tiles0 = (b0 + 15) // 16
+    use_pp = args.precision == "tc" and (args.rec_mode == "pp" or (args.rec_mode == "auto" and tiles0 * 2 > sm_count // 2))
+    rec_ctas = tiles0 if use_pp else min(2 * tiles0, sm_count)
+    sm_share = min(1.0, rec_ctas / float(sm_count))
+    rec_ms_region = 0.5 * (stage["rec0_ms"] + stage["rec1_ms"])
     kernels = {
-        "recurrent kernel (rec_pp_kernel / rec_tc_kernel: GRU recurrence, layer-0 and layer-1 launches)":
-            (rec_ms, p0 * FLOP_REC_PER_LAYER, solo["rec0_ms"] + solo["rec1_ms"]),
-        "gemm_tc_kernel (layer-1 input projection)": (solo["inproj1_ms"], p0 * FLOP_INPROJ1, solo["inproj1_ms"]),
+        "recurrent kernel (%s: GRU recurrence, layer-0 and layer-1 launches)" % ("rec_pp_kernel" if use_pp else "rec_tc_kernel"):
+            (rec_ms_region, p0 * FLOP_REC_PER_LAYER, solo["rec0_ms"] + solo["rec1_ms"], sm_share),
+        "gemm_tc_kernel (layer-1 input projection)": (stage["inproj1_ms"], p0 * FLOP_INPROJ1, solo["inproj1_ms"], 1.0),
     }
     dom = max(kernels, key=lambda k: kernels[k][2])
-    k_ms, k_flop, k_share_ms = kernels[dom]
+    k_ms, k_flop, k_share_ms, k_sms = kernels[dom]
     achieved = k_flop / (k_ms * 1e-3) / 1e12
+    peak = peaks["tflops_sustained"] * k_sms
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if args.config == 2 and args.precision == "tc" and os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
-        traffic = tj.get("rec_pp_kernel" if dom.startswith("recurrent") else "gemm_tc_kernel")
+        traffic = tj.get(("rec_pp_kernel" if use_pp else "rec_tc_kernel") if dom.startswith("recurrent") else "gemm_tc_kernel")
     flop_gru = 2 * FLOP_REC_PER_LAYER + FLOP_INPROJ1 + 2 * (2 * 384 * F)
     roofline = {
-        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tflops_burst"],
-        "unit": "TFLOP/s", "frac": achieved / peaks["tflops_burst"], "traffic": traffic,
-        "peak_source": "MEASURED_PEAKS.json bf16 burst (kernel timed alone: one forward of %d windows on an idle GPU)" % b0
-        if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)",
+        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak,
+        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": ("MEASURED_PEAKS.json bf16 sustained (kernel timed inside a long step) x %d/%d SMs the launch occupies"
+                        % (round(k_sms * sm_count), sm_count)) if peaks["source"] == "measured" else "fallback (B200_PROFILING.md)",
+        "launch": {"windows": b0, "cols": T, "ctas": rec_ctas if dom.startswith("recurrent") else None,
+                   "flop_per_launch": k_flop, "mean_ms_in_timed_region": k_ms},
         "note": "algorithmic FLOPs; operands are fp16 hi/lo pairs so the kernel issues 3 MMAs per product "
                 "(fp32-faithful parity), i.e. executed tensor FLOPs are 3x this figure",
         "kernel_share_of_step": k_share_ms / max(sum(solo.values()), 1e-9),
         "solo_stage_ms": solo, "solo_windows": b0,
         "timed_region_stage_ms": stage,
+        "full_wave_solo": full_wave,
         "whole_pipeline_achieved": value / world * flop_gru / 1e12,
         "whole_pipeline_frac": value / world * flop_gru / 1e12 / peaks["tflops_sustained"],
         "whole_pipeline_note": "all GRU-gate FLOPs (both recurrences + the layer-1 projection, all three on the tensor "
