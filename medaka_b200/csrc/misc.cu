@@ -55,8 +55,12 @@ __global__ void __launch_bounds__(256) normalise_kernel(const uint64_t *__restri
     uint64_t del_p[ND][2];     // parent's original deletion counts (needed only if the parent is a minor column)
     int64_t parent_minor = 0;
     if (mn > 0) {
-        // np.searchsorted(positions['major'], major, side='left'): first column with this major
-        const int64_t j = lower_bound_major(major, n, major[i]);
+        // np.searchsorted(positions['major'], major, side='left'): first column with this major.  Columns of one
+        // major are contiguous with minors counting up from the first one, so the parent is normally mn columns back
+        // (two loads to confirm); anything else (a chunk cut inside an insertion run, repeated majors) takes the search.
+        const int64_t mj = major[i];
+        int64_t j = i - mn;
+        if (j < 0 || major[j] != mj || (j > 0 && major[j - 1] == mj)) j = lower_bound_major(major, n, mj);
         parent_minor = minor[j];
         const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(counts + j * F);
         uint64_t p[F];

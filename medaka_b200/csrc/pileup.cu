@@ -368,7 +368,8 @@ struct PlpScratch {
         if (buf) cudaFree(buf);
     }
 };
-static thread_local PlpScratch g_plp_scratch[2];      // 0: kernel scratch, 1: staging of the host-buffer entry point
+static thread_local PlpScratch g_plp_scratch[4];      // 0: kernel scratch, 1: staging of the host-buffer entry point,
+                                                       // 2 / 3: the stitch entry points (stitch.cu)
 
 cudaError_t plp_scratch(size_t bytes, uint8_t **out, int slot) {
     int dev = 0;

@@ -242,7 +242,8 @@ int mdk_stitch_consensus_dev(int device, const float *probs_dev, int64_t n_rows,
     MDK_CUDA(cudaSetDevice(device));
     uint8_t *buf = nullptr;
     const size_t b_seg = ((size_t)n_seg * 8 + 15) & ~(size_t)15, b_off = ((size_t)(n_seg + 1) * 8 + 15) & ~(size_t)15;
-    MDK_CUDA(cudaMalloc(&buf, b_seg + b_off + stitch_scratch_bytes(n_rows)));
+    // per-host-thread cached scratch: a cudaMalloc / cudaFree pair per call costs more than the kernels of a contig
+    MDK_CUDA(plp_scratch(b_seg + b_off + stitch_scratch_bytes(n_rows), &buf, 2));
     int64_t *d_seg = reinterpret_cast<int64_t *>(buf), *d_off = reinterpret_cast<int64_t *>(buf + b_seg);
     cudaError_t err = cudaMemcpyAsync(d_seg, seg_base, (size_t)n_seg * 8, cudaMemcpyHostToDevice, 0);
     int rc = MDK_OK;
@@ -250,8 +251,6 @@ int mdk_stitch_consensus_dev(int device, const float *probs_dev, int64_t n_rows,
         rc = stitch_dev(probs_dev, n_rows, d_seg, n_seg, seq_out_dev, qual_out_dev, d_off, buf + b_seg + b_off, 0);
     if (rc == MDK_OK && err == cudaSuccess)
         err = cudaMemcpy(seg_out_off, d_off, (size_t)(n_seg + 1) * 8, cudaMemcpyDeviceToHost);
-    if (err == cudaSuccess) err = cudaDeviceSynchronize();
-    cudaFree(buf);
     if (err != cudaSuccess) return cuda_fail(err, "stitch_consensus_dev", __FILE__, __LINE__);
     return rc;
 }
@@ -274,7 +273,7 @@ int mdk_stitch_consensus(int device, const float *const *seg_probs, const int64_
     uint8_t *buf = nullptr;
     const size_t b_probs = ((size_t)n * NCLS * 4 + 15) & ~(size_t)15;
     const size_t b_out = ((size_t)n + 15) & ~(size_t)15;
-    MDK_CUDA(cudaMalloc(&buf, b_probs + 2 * b_out));
+    MDK_CUDA(plp_scratch(b_probs + 2 * b_out, &buf, 3));
     float *d_probs = reinterpret_cast<float *>(buf);
     uint8_t *d_seq = buf + b_probs, *d_qual = d_seq + b_out;
     cudaError_t err = cudaSuccess;
@@ -292,7 +291,6 @@ int mdk_stitch_consensus(int device, const float *const *seg_probs, const int64_
             if (err == cudaSuccess && qual_out) err = cudaMemcpy(qual_out, d_qual, total, cudaMemcpyDeviceToHost);
         }
     }
-    cudaFree(buf);
     if (err != cudaSuccess) return cuda_fail(err, "stitch_consensus", __FILE__, __LINE__);
     return rc;
 }

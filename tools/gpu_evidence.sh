@@ -1,6 +1,6 @@
 #!/bin/bash
 # round-2 evidence: bench lines (config 2 with CPU baseline, reference arm, configs 3-5), precision table, HBM kernel
-# bench, ncu launch list + full captures.  usage: tools/gpu_evidence.sh <tag> [part ...]   parts: bench cfg prec hbm ncu
+# bench, ncu launch list + full captures.  usage: tools/gpu_evidence.sh <tag> [part ...]   parts: bench cfg prec hbm ncu pipe
 tag=${1:-x}; shift
 parts=${@:-bench cfg prec hbm ncu}
 mkdir -p gpurun_out
@@ -24,6 +24,12 @@ ncu)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 10 -c 40 --csv --log-file $O/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${tag}_ncu_l.log 2>&1
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"rec_pp|gemm_tc|head_plog" -s 6 -c 4 -o $O/${tag}_prof_fwd python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/${tag}_ncu_f.log 2>&1
   timeout 1200 ncu --set full --clock-control none -k regex:"normalise|decode_kernel|head_plog|stitch_|plp_|vd_" -c 60 -o $O/${tag}_prof_hbm python tools/hbm_bench.py --n 4000000 > $O/${tag}_ncu_h.log 2>&1
-  ls -la $O/${tag}_prof_*.ncu-rep ;;
+  # the reports stay on the box (gpurun_out is capped at 64 MiB): export the raw metric pages, keep the small one
+  ncu -i $O/${tag}_prof_fwd.ncu-rep --page raw --csv > $O/${tag}_prof_fwd_raw.csv 2>/dev/null
+  ncu -i $O/${tag}_prof_hbm.ncu-rep --page raw --csv > $O/${tag}_prof_hbm_raw.csv 2>/dev/null
+  ls -la $O/${tag}_prof_*; rm -f $O/${tag}_prof_hbm.ncu-rep
+  [ $(stat -c %s $O/${tag}_prof_fwd.ncu-rep) -gt 30000000 ] && rm -f $O/${tag}_prof_fwd.ncu-rep ;;
+pipe)
+  timeout 900 python tools/pipeline_bench.py --mb 20 > $O/${tag}_pipeline_1gpu.json 2> $O/${tag}_pipeline_1gpu.err; tail -n 2 $O/${tag}_pipeline_1gpu.json; tail -n 3 $O/${tag}_pipeline_1gpu.err ;;
 esac
 done
