@@ -206,6 +206,34 @@ int mdk_pileup_counts(int device, int64_t n_rec, const int32_t *pos, const uint1
                       int64_t max_cols, uint64_t *counts_out, int64_t *major_out, int64_t *minor_out,
                       int64_t *n_cols_out);
 
+/* ---- featuriser seam, read-level features: replaces calculate_read_alignment (src/medaka_read_matrix.c:277-615,
+ * declared src/medaka_read_matrix.h:124-129) for one region of one contig.  Records as for mdk_pileup_counts plus
+ *   qual[] base qualities (l_seq bytes per read, 0xff = absent) with qual_off[n+1],
+ *   aux[] the raw optional fields with aux_off[n+1] (read for the `mv` move table -> dwell channel, calculate_dwells
+ *   :154-213, and the `HP` haplotag, :405-414; may be NULL when neither channel is requested),
+ *   names[] query names with name_off[n+1] (alignments of one name share a row, :386-388).
+ * Output like read_aln_data (src/medaka_read_matrix.h:5-17) after the Python wrapper's `[:, :n_reads]` cut
+ * (medaka/features.py:337-347): matrix int8 [n_cols][n_reads][featlen], featlen = 4 (+1 dwells) (+1 haplotype)
+ * (+1 datatype when num_dtypes > 1): base 1..4 = ACGT / 5 = deletion / -1 other, base quality, strand +1 / -1, mapping
+ * quality, ... ; cells no read touches are 0.  Values are NOT clipped (the wrapper's np.maximum(.., 0) is the caller's).
+ * Rows follow the reference's bookkeeping (first row whose previous read ended >= 5 positions ago, or a new row;
+ * row_per_read: always a new row; rows >= max_reads are dropped); n_reads = min(max_reads, deepest column) or the
+ * number of rows used with row_per_read.  left_read_out / right_read_out [n_reads] (may both be NULL): index of the read
+ * whose name the reference reports as read_ids_left / read_ids_right for that row, -1 = "__blank_<k>", -2 = NULL id.
+ * *n_cols_out and *n_reads_out are always set; if n_cols > max_cols or n_cols * n_reads * featlen > max_cells the call
+ * returns MDK_ERR_NOMEM without data and the caller retries with larger buffers (enlarge_read_aln_data_*, :85-138).
+ * Known divergence: a read that finds no free row is dropped for good; the reference can let such a read alias a row
+ * that is pushed after a later growth of its buffer (reads another read's struct - undefined behaviour, not reproduced).
+ * All pointers are HOST pointers. */
+int mdk_read_matrix(int device, int64_t n_rec, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
+                    const uint8_t *dtype, const uint32_t *cigar, const int64_t *cigar_off, const uint8_t *seq,
+                    const int64_t *seq_off, const uint8_t *qual, const int64_t *qual_off, const uint8_t *aux,
+                    const int64_t *aux_off, const char *names, const int64_t *name_off, int32_t start, int32_t end,
+                    int32_t num_dtypes, int32_t min_mapq, int32_t row_per_read, int32_t include_dwells,
+                    int32_t include_haplotype, int32_t max_reads, int64_t max_cols, int64_t max_cells,
+                    int8_t *matrix_out, int64_t *major_out, int64_t *minor_out, int64_t *n_cols_out,
+                    int32_t *n_reads_out, int32_t *left_read_out, int32_t *right_read_out);
+
 /* ---- alignment access: what calculate_pileup gets from htslib (create_bam_fset src/medaka_bamiter.c:52-63,
  * bam_itr_querys src/medaka_counts.c:233, the flag / mapQ part of read_bam src/medaka_bamiter.c:19-21).  Native BGZF
  * inflate (zlib, a thread pool over the independent members), BAI-indexed region fetch (bins + linear index; without an
@@ -231,6 +259,9 @@ int mdk_bam_batch_arrays(mdk_bam_batch *x, const int32_t **pos, const uint16_t *
                          const int32_t **l_seq, const uint32_t **cigar, const int64_t **cigar_off,
                          const uint8_t **seq, const int64_t **seq_off, const uint8_t **aux, const int64_t **aux_off,
                          const char **names, const int64_t **name_off);
+/* base qualities as stored (bam_get_qual, src/medaka_read_matrix.c:428): l_seq bytes per read, 0xff when absent;
+ * qual_off[n+1] */
+int mdk_bam_batch_qual(mdk_bam_batch *x, const uint8_t **qual, const int64_t **qual_off);
 int mdk_bam_batch_free(mdk_bam_batch *x);
 
 /* ---- decode seam: replaces the array part of HaploidLabelScheme.decode_consensus ------------

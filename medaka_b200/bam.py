@@ -25,7 +25,11 @@ _CONSUMES_QRY = np.array([1, 1, 0, 0, 1, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0], dtype
 
 RecordBatch = collections.namedtuple(
     "RecordBatch",
-    ["pos", "flag", "mapq", "dtype", "cigar", "cigar_off", "seq", "seq_off", "l_seq", "names", "tags"])
+    ["pos", "flag", "mapq", "dtype", "cigar", "cigar_off", "seq", "seq_off", "l_seq", "names", "tags", "qual", "aux",
+     "aux_off"])
+# qual: base qualities, l_seq bytes per read back to back (offsets = cumsum(l_seq)); aux / aux_off: the raw optional
+# fields (move table, haplotag).  Only the read-level featuriser asks for them.
+RecordBatch.__new__.__defaults__ = (None, None, None)
 
 
 def _bgzf_blocks(buf):
@@ -66,8 +70,9 @@ def bgzf_decompress(buf, threads=4):
     return b"".join(parts)
 
 
-def _parse_tags(raw):
-    """Aux fields -> dict (only the scalar / string types the read filters look at; arrays are skipped)."""
+def _parse_tags(raw, arrays=False):
+    """Aux fields -> dict (the scalar / string types the read filters look at; B arrays only when ``arrays``: the
+    move table 'mv' of the read-level featuriser)."""
     tags, i, n = {}, 0, len(raw)
     sizes = {"c": ("<b", 1), "C": ("<B", 1), "s": ("<h", 2), "S": ("<H", 2), "i": ("<i", 4), "I": ("<I", 4),
              "f": ("<f", 4)}
@@ -89,7 +94,11 @@ def _parse_tags(raw):
         elif typ == "B":
             sub = chr(raw[i])
             cnt = struct.unpack_from("<I", raw, i + 1)[0]
-            i += 5 + cnt * {"c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}[sub]
+            width = {"c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}[sub]
+            if arrays:
+                tags[tag] = list(struct.unpack_from("<%d%s" % (cnt, {"c": "b", "C": "B", "s": "h", "S": "H", "i": "i",
+                                                                  "I": "I", "f": "f"}[sub]), raw, i + 5))
+            i += 5 + cnt * width
         else:
             break
     return tags
@@ -150,7 +159,8 @@ class BamFile(object):
         return list(zip(self.references, self.lengths))
 
     def fetch(self, ref_name, start, end, dtypes=None, tag_name=None, tag_value=None, keep_missing=False,
-              read_group=None, with_names=False, min_mapq=0, exclude_flags=FILTER_FLAGS):
+              read_group=None, with_names=False, min_mapq=0, exclude_flags=FILTER_FLAGS, with_qual=False,
+              with_tags=False, with_aux=False):
         """Records overlapping [start, end) on ref_name that pass the read filter of src/medaka_bamiter.c:17-45, in the
         reference's order: flag and mapping quality first (native, before anything is parsed), then the tag, read-group
         and datatype tests on the survivors' aux fields."""
@@ -191,20 +201,29 @@ class BamFile(object):
             seq = arr("seq", np.uint8, int(seq_off[-1]))
             aux = bytes(ffi.buffer(ptrs["aux"][0], int(aux_off[-1]))) if n and aux_off[-1] else b""
             names_raw = bytes(ffi.buffer(ptrs["names"][0], int(name_off[-1]))) if n and name_off[-1] else b""
+            qual = None
+            if with_qual:
+                pq, pqo = ffi.new("const uint8_t **"), ffi.new("const int64_t **")
+                lm.check(lib.mdk_bam_batch_qual(batch, pq, pqo))
+                nq = int(l_seq.sum())
+                qual = (np.frombuffer(ffi.buffer(pq[0], nq), dtype=np.uint8).copy() if nq else np.zeros(0, dtype=np.uint8))
         finally:
             lib.mdk_bam_batch_free(batch)
 
         def name(i):
             return names_raw[int(name_off[i]):int(name_off[i + 1])].decode()
 
-        need_tags = bool(tag_name) or read_group is not None or (dtypes is not None and len(dtypes) > 1)
+        aux_arr = np.frombuffer(aux, dtype=np.uint8).copy() if with_aux else None
+        aux_off_out = aux_off if with_aux else None
+
+        need_tags = with_tags or bool(tag_name) or read_group is not None or (dtypes is not None and len(dtypes) > 1)
         dtype = np.zeros(n, dtype=np.uint8)
         tags_out = None
         keep = np.ones(n, dtype=bool)
         if need_tags:
             tags_out = []
             for i in range(n):
-                tg = _parse_tags(aux[int(aux_off[i]):int(aux_off[i + 1])])
+                tg = _parse_tags(aux[int(aux_off[i]):int(aux_off[i + 1])], arrays=with_tags)
                 tags_out.append(tg)
                 keep[i] = _passes_tag_filters(tg, tag_name, tag_value, keep_missing, read_group)
                 if keep[i] and dtypes is not None and len(dtypes) > 1:
@@ -225,18 +244,49 @@ class BamFile(object):
             b_idx = np.arange(int(new_soff[-1])) - np.repeat(new_soff[:-1], n_sb) + np.repeat(seq_off[:-1][sel], n_sb)
             seq = seq[b_idx] if len(b_idx) else np.zeros(0, dtype=np.uint8)
             names = [name(i) for i in sel] if with_names else None
+            if qual is not None:
+                q_off = np.zeros(n + 1, dtype=np.int64)
+                np.cumsum(l_seq, out=q_off[1:])
+                n_q = l_seq[sel].astype(np.int64)
+                new_qoff = np.zeros(len(sel) + 1, dtype=np.int64)
+                np.cumsum(n_q, out=new_qoff[1:])
+                q_idx = np.arange(int(new_qoff[-1])) - np.repeat(new_qoff[:-1], n_q) + np.repeat(q_off[:-1][sel], n_q)
+                qual = qual[q_idx] if len(q_idx) else np.zeros(0, dtype=np.uint8)
+            if aux_arr is not None:
+                n_a = (aux_off[1:] - aux_off[:-1])[sel]
+                new_aoff = np.zeros(len(sel) + 1, dtype=np.int64)
+                np.cumsum(n_a, out=new_aoff[1:])
+                a_idx = np.arange(int(new_aoff[-1])) - np.repeat(new_aoff[:-1], n_a) + np.repeat(aux_off[:-1][sel], n_a)
+                aux_arr = aux_arr[a_idx] if len(a_idx) else np.zeros(0, dtype=np.uint8)
+                aux_off_out = new_aoff
             pos, flag, mapq, l_seq, dtype = pos[sel], flag[sel], mapq[sel], l_seq[sel], dtype[sel]
             cigar_off, seq_off = new_coff, new_soff
         else:
             names = [name(i) for i in range(n)] if with_names else None
         return RecordBatch(pos=pos, flag=flag, mapq=mapq, dtype=dtype, cigar=np.ascontiguousarray(cigar, dtype=np.uint32),
                            cigar_off=cigar_off, seq=np.ascontiguousarray(seq, dtype=np.uint8), seq_off=seq_off,
-                           l_seq=l_seq, names=names, tags=tags_out)
+                           l_seq=l_seq, names=names, tags=tags_out, qual=qual, aux=aux_arr, aux_off=aux_off_out)
+
+
+def _encode_aux(tags):
+    """dict -> raw BAM optional fields (ints as 'i', strings as 'Z', integer lists as a 'B' array of int8 when they
+    fit, int32 otherwise) - what a reader would hand over for the same record."""
+    out = bytearray()
+    for key, v in (tags or {}).items():
+        if isinstance(v, (int, np.integer)):
+            out += key.encode() + b"i" + struct.pack("<i", int(v))
+        elif isinstance(v, str):
+            out += key.encode() + b"Z" + v.encode() + b"\x00"
+        elif isinstance(v, (list, tuple, np.ndarray)) and all(float(x) == int(x) for x in v):
+            small = all(-128 <= int(x) <= 127 for x in v)
+            out += key.encode() + b"B" + (b"c" if small else b"i") + struct.pack("<I", len(v))
+            out += struct.pack("<%d%s" % (len(v), "b" if small else "i"), *[int(x) for x in v])
+    return bytes(out)
 
 
 def records_from_dicts(records, dtypes=None):
     """Build a RecordBatch from plain dict records (the reference's ``simple_data`` style): keys
-    'pos', 'cigar' (string), 'seq', 'flag', 'mapq', optional 'tags'."""
+    'pos', 'cigar' (string), 'seq', 'flag', 'mapq', optional 'tags', 'qual' (list of ints; absent = 0xff)."""
     import re
     code = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
     opc = {c: i for i, c in enumerate("MIDNSHP=X")}
@@ -258,4 +308,8 @@ def records_from_dicts(records, dtypes=None):
         dtype=np.array(dt, dtype=np.uint8), cigar=np.array(cig, dtype=np.uint32),
         cigar_off=np.array(cig_off, dtype=np.int64), seq=np.array(seq, dtype=np.uint8),
         seq_off=np.array(seq_off, dtype=np.int64), l_seq=np.array([len(r["seq"]) for r in records], dtype=np.int32),
-        names=[r.get("query_name") for r in records], tags=[r.get("tags", {}) for r in records])
+        names=[r.get("query_name") for r in records], tags=[r.get("tags", {}) for r in records],
+        qual=np.array([q for r in records for q in (r["qual"] if r.get("qual") is not None else [0xFF] * len(r["seq"]))],
+                      dtype=np.uint8),
+        aux=np.frombuffer(b"".join(_encode_aux(r.get("tags")) for r in records), dtype=np.uint8).copy(),
+        aux_off=np.concatenate([[0], np.cumsum([len(_encode_aux(r.get("tags"))) for r in records])]).astype(np.int64))

@@ -53,6 +53,8 @@ struct mdk_bam_batch {
     std::vector<int64_t> cigar_off{0};
     std::vector<uint8_t> seq;
     std::vector<int64_t> seq_off{0};
+    std::vector<uint8_t> qual;          // l_seq bytes per read (0xff = absent), offsets qual_off
+    std::vector<int64_t> qual_off{0};
     std::vector<uint8_t> aux;
     std::vector<int64_t> aux_off{0};
     std::vector<char> names;
@@ -290,6 +292,8 @@ int64_t parse_records(const uint8_t *data, int64_t u0, int64_t u1, int tid, int3
         out->cigar_off.push_back((int64_t)out->cigar.size());
         out->seq.insert(out->seq.end(), seq, seq + (l_seq + 1) / 2);
         out->seq_off.push_back((int64_t)out->seq.size());
+        out->qual.insert(out->qual.end(), seq + (l_seq + 1) / 2, seq + (l_seq + 1) / 2 + l_seq);
+        out->qual_off.push_back((int64_t)out->qual.size());
         out->aux.insert(out->aux.end(), aux, aux + aux_len);
         out->aux_off.push_back((int64_t)out->aux.size());
         const char *nm = reinterpret_cast<const char *>(r + 32);
@@ -499,6 +503,8 @@ int mdk_bam_fetch(mdk_bam *b, int tid, int32_t start, int32_t end, uint32_t excl
                         clean->cigar_off.push_back((int64_t)clean->cigar.size());
                         clean->seq.insert(clean->seq.end(), batch->seq.begin() + batch->seq_off[i], batch->seq.begin() + batch->seq_off[i + 1]);
                         clean->seq_off.push_back((int64_t)clean->seq.size());
+                        clean->qual.insert(clean->qual.end(), batch->qual.begin() + batch->qual_off[i], batch->qual.begin() + batch->qual_off[i + 1]);
+                        clean->qual_off.push_back((int64_t)clean->qual.size());
                         clean->aux.insert(clean->aux.end(), batch->aux.begin() + batch->aux_off[i], batch->aux.begin() + batch->aux_off[i + 1]);
                         clean->aux_off.push_back((int64_t)clean->aux.size());
                         clean->names.insert(clean->names.end(), batch->names.begin() + batch->name_off[i], batch->names.begin() + batch->name_off[i + 1]);
@@ -538,6 +544,13 @@ int mdk_bam_batch_arrays(mdk_bam_batch *x, const int32_t **pos, const uint16_t *
     if (aux_off) *aux_off = x->aux_off.data();
     if (names) *names = x->names.data();
     if (name_off) *name_off = x->name_off.data();
+    return MDK_OK;
+}
+
+int mdk_bam_batch_qual(mdk_bam_batch *x, const uint8_t **qual, const int64_t **qual_off) {
+    MDK_REQUIRE(x, MDK_ERR_ARG, "bam_batch_qual: NULL batch");
+    if (qual) *qual = x->qual.data();
+    if (qual_off) *qual_off = x->qual_off.data();
     return MDK_OK;
 }
 

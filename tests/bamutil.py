@@ -46,7 +46,8 @@ def encode_record(rec, tid, long_cigar=False):
     packed = bytes((nib[i] << 4) | nib[i + 1] for i in range(0, len(nib), 2))
     body = struct.pack("<iiBBHHHiiii", tid, rec["pos"], len(name), rec.get("mapq", 60),
                        reg2bin(rec["pos"], rec["pos"] + max(ref_len, 1)), len(ops), rec.get("flag", 0), len(seq), -1, -1, 0)
-    body += name + b"".join(struct.pack("<I", o) for o in ops) + packed + b"\xff" * len(seq) + _aux(tags)
+    qual = bytes(rec["qual"]) if rec.get("qual") is not None else b"\xff" * len(seq)
+    body += name + b"".join(struct.pack("<I", o) for o in ops) + packed + qual + _aux(tags)
     return struct.pack("<i", len(body)) + body, ref_len
 
 
