@@ -565,7 +565,8 @@ int mdk_engine_submit(mdk_engine *e, const float *feats_host, int64_t B, int64_t
     while (done < B) {
         if (e->open_lane < 0) {
             int li;
-            if ((rc = acquire_lane(e, (B - done) * T, &li))) return rc;
+            if ((rc = acquire_lane(e, B * T, &li))) return rc;      // size class of the BATCH: the tail piece of a split
+                                                                    // batch stays with the big lanes
             mdk_lane &ln = e->lane[li];
             // the staging grows to this batch (at most one wave of it); a reserved lane is already larger and keeps
             // collecting further batches up to its size

@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -375,8 +376,8 @@ struct PlpScratch {
         if (buf) cudaFree(buf);
     }
 };
-static thread_local PlpScratch g_plp_scratch[4];      // 0: kernel scratch, 1: staging of the host-buffer entry point,
-                                                       // 2 / 3: the stitch entry points (stitch.cu)
+static thread_local PlpScratch g_plp_scratch[5];      // 0: kernel scratch, 1: staging of the host-buffer entry point,
+                                                       // 2 / 3: the stitch entry points (stitch.cu), 4: variant decode
 
 cudaError_t plp_scratch(size_t bytes, uint8_t **out, int slot) {
     int dev = 0;
@@ -892,18 +893,13 @@ extern "C" int mdk_read_matrix(int device, int64_t n_rec, const int32_t *pos, co
     int64_t n_reads = row_per_read ? (int64_t)slots.size() : max_n_reads;
     n_reads = std::min<int64_t>(max_reads, n_reads);
     *n_reads_out = (int32_t)n_reads;
-    if (left_read_out && right_read_out) {
-        // per row of the read array: the read at the first column, and the last read placed if it reaches final_pos (:559-575);
-        // -1 = "__blank_k", -2 = beyond the read array (NULL id)
-        for (int64_t q = 0; q < n_reads; ++q) {
-            if (q < (int64_t)slots.size()) {
-                left_read_out[q] = q < (int64_t)left_of.size() ? left_of[(size_t)q] : -1;
-                right_read_out[q] = slots[(size_t)q].ref_end >= final_pos ? slots[(size_t)q].read : -1;
-            } else {
-                left_read_out[q] = -2;
-                right_read_out[q] = -2;
-            }
-        }
+    // per row of the read array: the read at the first column, and the last read placed if it reaches final_pos (:559-575);
+    // -1 = "__blank_k", -2 = beyond the read array (NULL id).  Handed over only with the data (the caller's arrays hold
+    // n_reads entries once it knows n_reads).
+    std::vector<int32_t> left_ids((size_t)n_reads, -2), right_ids((size_t)n_reads, -2);
+    for (int64_t q = 0; q < n_reads && q < (int64_t)slots.size(); ++q) {
+        left_ids[(size_t)q] = q < (int64_t)left_of.size() ? left_of[(size_t)q] : -1;
+        right_ids[(size_t)q] = slots[(size_t)q].ref_end >= final_pos ? slots[(size_t)q].read : -1;
     }
     // ---- dwell / haplotype channels from the aux fields
     const int64_t n_ops = cigar_off[n_rec], n_seq = seq_off[n_rec], n_qual = qual_off[n_rec];
@@ -973,5 +969,9 @@ extern "C" int mdk_read_matrix(int device, int64_t n_rec, const int32_t *pos, co
             err = cudaMemcpy(matrix_out, buf + o_mat, (size_t)(n_cols * n_reads * featlen), cudaMemcpyDeviceToHost);
     }
     if (err != cudaSuccess) return cuda_fail(err, "read_matrix (copy out)", __FILE__, __LINE__);
+    if (left_read_out && right_read_out && n_reads > 0) {
+        memcpy(left_read_out, left_ids.data(), (size_t)n_reads * 4);
+        memcpy(right_read_out, right_ids.data(), (size_t)n_reads * 4);
+    }
     return MDK_OK;
 }

@@ -192,7 +192,7 @@ int mdk_decode_variants(int device, const float *probs, const int64_t *minor, co
                  o_base = take((size_t)(n_blocks + 1) * 8), o_rs = take((size_t)max_runs * 8),
                  o_rl = take((size_t)max_runs * 8), o_rp = take((size_t)max_runs * 4), o_rr = take((size_t)max_runs * 4);
     uint8_t *buf = nullptr;
-    MDK_CUDA(cudaMalloc(&buf, off + 16));
+    MDK_CUDA(plp_scratch(off + 16, &buf, 4));     // cached per host thread: no cudaMalloc / cudaFree per sample
     cudaStream_t s = 0;
     cudaError_t err = cudaMemcpyAsync(buf + o_probs, probs, (size_t)n * NCLS * 4, cudaMemcpyHostToDevice, s);
     if (err == cudaSuccess) err = cudaMemcpyAsync(buf + o_minor, minor, (size_t)n * 8, cudaMemcpyHostToDevice, s);
@@ -232,7 +232,7 @@ int mdk_decode_variants(int device, const float *probs, const int64_t *minor, co
             if (err == cudaSuccess) err = cudaMemcpy(run_ref_q, buf + o_rr, (size_t)total * 4, cudaMemcpyDeviceToHost);
         }
     }
-    cudaFree(buf);
+    
     if (err != cudaSuccess) return cuda_fail(err, "decode_variants", __FILE__, __LINE__);
     return rc;
 }

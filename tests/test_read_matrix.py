@@ -191,6 +191,10 @@ def test_encoder_on_bam_file_with_sub_regions(tmp_path):
     assert len(samples) == len(want)
     for (m, p), (wm, wp) in zip(samples, want):
         assert np.array_equal(p, wp) and np.array_equal(m, wm)
+    # the encoder's default sub-region size (100 kb) leaves this region in one piece: rows beyond the deepest column are
+    # cut per sub-region (medaka/features.py:337-347), so the result legitimately depends on where the cuts fall
     out = enc.bam_to_sample(path, region)
-    assert len(out) == len(want) and out[0].features.dtype == np.int8
-    assert np.array_equal(out[0].depth, np.count_nonzero(want[0][0][..., 0], axis=-1))
+    whole, wp, _, _ = read_matrix_oracle.read_alignment(recs, region.start, region.end)
+    assert len(out) == 1 and out[0].features.dtype == np.int8
+    assert np.array_equal(out[0].features, whole) and np.array_equal(out[0].positions, wp)
+    assert np.array_equal(out[0].depth, np.count_nonzero(whole[..., 0], axis=-1))

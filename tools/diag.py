@@ -325,7 +325,54 @@ def check_timeline(arg):
     return {"total_ms": float(ms[0]), "ms_per_forward": float(ms[0]) / n, "start_rec0_gemm_rec1_head": rows}
 
 
-CHECKS = {"timeline": check_timeline, "pp": check_pp, "rec_timing": check_rec_timing, "pp_trace": check_pp_trace, "selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism,
+def check_e2e_timeline(arg):
+    """'B,T,bw,steps' -> the bench's host-buffer leg (batches of bw windows submitted with the look-ahead) and the stage
+    completion times of its last groups."""
+    from medaka_b200 import libmedaka as lm, models
+    from oracle import synth
+    B, T, bw, steps = [int(x) for x in arg.split(",")]
+    lib, ffi = lm.load(), lm.ffi
+    m = models.GRUModel()
+    m.load_state_dict(synth.synth_state_dict(0))
+    m.reserve(min(m.preferred_batch_size(), B), T)
+    feats = m.pinned("f", (B, T, 10), np.float32)
+    feats[...] = synth.synth_features_fast(min(B, 64), T, 10, seed=3)[np.arange(B) % min(B, 64)]
+    probs = m.pinned("p", (2, B, T, 5), np.float32)
+    labels = m.pinned("l", (2, B, T), np.uint8)
+    depth = m.lookahead(bw, T)
+    batches = [(a, min(B, a + bw)) for a in range(0, B, bw)]
+    waits = []
+
+    def run(n):
+        pending = []
+        for k in range(n):
+            for a, b in batches:
+                while len(pending) >= depth:
+                    t0 = time.perf_counter()
+                    m.wait(pending.pop(0))
+                    waits.append(time.perf_counter() - t0)
+                pending.append(m.submit_arrays(feats[a:b], probs[k % 2, a:b], labels[k % 2, a:b]))
+        while pending:
+            m.wait(pending.pop(0))
+    run(2)
+    lm.check(lib.mdk_engine_sync(m.engine))
+    del waits[:]
+    ms = ffi.new("float *")
+    lm.check(lib.mdk_engine_timer_start(m.engine))
+    t0 = time.perf_counter()
+    run(steps)
+    host_s = time.perf_counter() - t0
+    lm.check(lib.mdk_engine_timer_stop(m.engine, ms))
+    n = min(16, steps * ((B + 1183) // 1184))
+    out = np.zeros((n, 8), dtype=np.float32)
+    lm.check(lib.mdk_debug_timeline(m.engine, n, ffi.cast("float *", ffi.from_buffer(out))))
+    rows = [[round(float(v), 1) for v in r[[0, 1, 3, 4, 5, 6, 7]]] for r in out]
+    return {"ms_per_step": float(ms[0]) / steps, "host_ms_per_step": host_s * 1e3 / steps, "depth": depth,
+            "wait_ms_total": sum(waits) * 1e3, "n_waits": len(waits),
+            "start_in_rec0_gemm_rec1_head_end": rows}
+
+
+CHECKS = {"e2e_timeline": check_e2e_timeline, "timeline": check_timeline, "pp": check_pp, "rec_timing": check_rec_timing, "pp_trace": check_pp_trace, "selftest": check_selftest, "forward": check_forward, "misc": check_misc, "determinism": check_determinism,
           "rec_trace": check_rec_trace}
 
 PLAN = [
