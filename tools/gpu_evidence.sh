@@ -1,15 +1,18 @@
 #!/bin/bash
 # round-2 evidence: bench lines (config 2 with CPU baseline, reference arm, configs 3-5), precision table, HBM kernel
-# bench, ncu launch list + full captures.  usage: tools/gpu_evidence.sh <tag> [part ...]   parts: bench cfg prec hbm ncu pipe
+# bench, ncu launch list + full captures.  usage: tools/gpu_evidence.sh <tag> [part ...]   parts: tests bench cfg prec hbm ncu pipe
 tag=${1:-x}; shift
 parts=${@:-bench cfg prec hbm ncu}
 mkdir -p gpurun_out
 O=gpurun_out
 for part in $parts; do
 case $part in
+tests)
+  timeout 1800 python -m pytest tests -x -q -m gpu > $O/${tag}_pytest_gpu.log 2>&1; tail -n 4 $O/${tag}_pytest_gpu.log ;;
 bench)
   timeout 900 python bench.py --steps 20 --warmup 5 > $O/${tag}_bench_cfg2.json 2> $O/${tag}_bench_cfg2.err
   timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $O/${tag}_bench_reference.json 2> $O/${tag}_bench_reference.err
+  timeout 900 python bench.py --impl reference --steps 1 --warmup 0 --cpu-cols 10000 > $O/${tag}_bench_reference_fullT.json 2> $O/${tag}_bench_reference_fullT.err
   tail -c 600 $O/${tag}_bench_cfg2.json; tail -c 400 $O/${tag}_bench_reference.json ;;
 cfg)
   for c in 3 4 5; do
