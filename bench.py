@@ -22,6 +22,7 @@ N > 1: one process per GPU (torchrun), weights broadcast once over NCCL from ran
 runs the same per-GPU workload on its own windows (weak scaling, no data-path collective).
 """
 import argparse
+import concurrent.futures
 import json
 import os
 import statistics
@@ -488,8 +489,9 @@ def main():
     bw = max(1, min(args.batch_windows, B))
     batches = [(a, min(B, a + bw)) for a in range(0, B, bw)]
     depth = model.lookahead(bw, T)
-    h_probs = model.pinned("bench_probs", (2, B, T, 5), np.float32)      # two steps' worth: results stay valid while
-    h_labels = model.pinned("bench_labels", (2, B, T), np.uint8)         # the next step is already queued
+    n_slots = 3 if args.config == 4 else 2          # host result buffers: config 4 keeps a step alive while it is decoded
+    h_probs = model.pinned("bench_probs", (n_slots, B, T, 5), np.float32)   # results stay valid while the next step is
+    h_labels = model.pinned("bench_labels", (n_slots, B, T), np.uint8)      # already queued
     variant_ms = []
     vd = None
     if args.config == 4:
@@ -503,24 +505,32 @@ def main():
         vd = (mlabels, vminor, vref)
 
     def run_host(n, timed=False):
+        # the reference-facing loop (medaka/prediction.py:44-52): batches submitted with the engine's look-ahead, results
+        # collected in order.  Config 4: a worker thread runs the variant decode of step k as soon as its last batch is
+        # back (medaka vcf is a separate consumer of the probabilities), the main thread keeps feeding the engine
         pending = []
+        jobs = {}
+        pool = concurrent.futures.ThreadPoolExecutor(1) if vd is not None else None
+
+        def collect_one():
+            tk, kk, a, b = pending.pop(0)
+            model.wait(tk)
+            if pool is not None and b == B:              # last batch of step kk is back
+                jobs[kk] = pool.submit(decode_step, kk, timed)
         for k in range(n):
+            if pool is not None and k - n_slots in jobs:
+                jobs.pop(k - n_slots).result()           # its buffer is about to be overwritten
             for a, b in batches:
                 while len(pending) >= depth:
-                    model.wait(pending.pop(0)[0])
-                tk = model.submit_arrays(feats[a:b], h_probs[k % 2, a:b], h_labels[k % 2, a:b])
+                    collect_one()
+                tk = model.submit_arrays(feats[a:b], h_probs[k % n_slots, a:b], h_labels[k % n_slots, a:b])
                 pending.append((tk, k, a, b))
-            if vd is not None:
-                # config 4: decode the previous step's output while this step runs on the device
-                for tk, kk, a, b in [p for p in pending if p[1] < k]:
-                    model.wait(tk)
-                pending = [p for p in pending if p[1] >= k]
-                if k >= 1:
-                    decode_step(k - 1, timed)
         while pending:
-            model.wait(pending.pop(0)[0])
-        if vd is not None:
-            decode_step(n - 1, timed)
+            collect_one()
+        if pool is not None:
+            for j in jobs.values():
+                j.result()
+            pool.shutdown()
 
     def decode_step(k, timed):
         mlabels, vminor, vref = vd
@@ -528,7 +538,7 @@ def main():
         n_var = 0
         for w in range(0, B, 64):                       # 64 windows per call: 640 k columns, like a joined region
             wb = min(B, w + 64)
-            probs = h_probs[k % 2, w:wb].reshape(-1, 5)
+            probs = h_probs[k % n_slots, w:wb].reshape(-1, 5)
             mn = np.tile(vminor, wb - w)
             rf = np.tile(vref, wb - w)
             n_var += len(mlabels.decode_variant_arrays(probs, mn, rf, dev, want_quals=False)["run_start"])
@@ -544,7 +554,7 @@ def main():
     lm.check(lib.mdk_engine_timer_stop(eng, ms))
     barrier()
     e2e_ms = float(ms[0])
-    assert np.isfinite(h_probs[(args.steps - 1) % 2, :2]).all()
+    assert np.isfinite(h_probs[(args.steps - 1) % n_slots, :2]).all()
 
     if dist is not None:
         t = torch.tensor([dev_ms, e2e_ms], device="cuda")

@@ -206,6 +206,19 @@ int mdk_pileup_counts(int device, int64_t n_rec, const int32_t *pos, const uint1
                       int64_t max_cols, uint64_t *counts_out, int64_t *major_out, int64_t *minor_out,
                       int64_t *n_cols_out);
 
+/* calculate_pileup + _post_process_pileup in one device pass (src/medaka_counts.c:199-372 followed by
+ * medaka/features.py:871-935): the records of mdk_pileup_counts in, the normalised float32 features [n_cols][10*num_dtypes],
+ * depth [n_cols] (may be NULL) and positions out; the uint64 counts stay on the device.  mode / sym_indels as for
+ * mdk_normalise_counts.  Normalising a region before it is split at coverage gaps (medaka/features.py:125-134) gives the
+ * same numbers as normalising the pieces: an insertion column and its parent never sit on different sides of a gap.
+ * *n_cols_out is always set; MDK_ERR_NOMEM (nothing written) when it exceeds max_cols. */
+int mdk_pileup_features(int device, int64_t n_rec, const int32_t *pos, const uint16_t *flag,
+                        const uint8_t *mapq, const uint8_t *dtype, const uint32_t *cigar,
+                        const int64_t *cigar_off, const uint8_t *seq, const int64_t *seq_off,
+                        int32_t start, int32_t end, int32_t num_dtypes, int32_t min_mapq, int32_t mode,
+                        int32_t sym_indels, int64_t max_cols, float *feats_out, int64_t *depth_out,
+                        int64_t *major_out, int64_t *minor_out, int64_t *n_cols_out);
+
 /* ---- featuriser seam, read-level features: replaces calculate_read_alignment (src/medaka_read_matrix.c:277-615,
  * declared src/medaka_read_matrix.h:124-129) for one region of one contig.  Records as for mdk_pileup_counts plus
  *   qual[] base qualities (l_seq bytes per read, 0xff = absent) with qual_off[n+1],

@@ -818,7 +818,7 @@ int mdk_normalise_counts(int device, const uint64_t *counts, const int64_t *majo
     const size_t F = 10 * (size_t)num_dtypes;
     uint8_t *buf = nullptr;
     const size_t b_counts = (size_t)n * F * 8, b_pos = (size_t)n * 8, b_feats = (size_t)n * F * 4;
-    MDK_CUDA(cudaMalloc(&buf, b_counts + 3 * b_pos + b_feats));
+    MDK_CUDA(plp_scratch(b_counts + 3 * b_pos + b_feats + 64, &buf, 1));   // cached per host thread (the loader threads call this per region)
     uint64_t *d_counts = reinterpret_cast<uint64_t *>(buf);
     int64_t *d_major = reinterpret_cast<int64_t *>(buf + b_counts);
     int64_t *d_minor = d_major + n;
@@ -830,7 +830,6 @@ int mdk_normalise_counts(int device, const uint64_t *counts, const int64_t *majo
     if (err == cudaSuccess) err = launch_normalise(d_counts, d_major, d_minor, n, num_dtypes, mode, sym_indels, d_feats, d_depth, 0);
     if (err == cudaSuccess) err = cudaMemcpy(feats_out, d_feats, b_feats, cudaMemcpyDeviceToHost);
     if (err == cudaSuccess && depth_out) err = cudaMemcpy(depth_out, d_depth, b_pos, cudaMemcpyDeviceToHost);
-    cudaFree(buf);
     if (err != cudaSuccess) return cuda_fail(err, "normalise_counts", __FILE__, __LINE__);
     return MDK_OK;
 }
@@ -889,6 +888,65 @@ int mdk_pileup_counts(int device, int64_t n_rec, const int32_t *pos, const uint1
     }
     if (err != cudaSuccess) return cuda_fail(err, "pileup_counts", __FILE__, __LINE__);
     return rc;
+}
+
+// Fused featuriser: records -> counts -> normalised features without the counts ever leaving the device (SURVEY.md 8f row
+// f3: "a1 -> a3 fused").  Same arguments as mdk_pileup_counts plus the normalisation switches of mdk_normalise_counts;
+// copies out 64 B per column (F = 10: features 40, depth 8, positions 16) instead of 96 B out, 96 B back in and 48 B out.
+int mdk_pileup_features(int device, int64_t n_rec, const int32_t *pos, const uint16_t *flag, const uint8_t *mapq,
+                        const uint8_t *dtype, const uint32_t *cigar, const int64_t *cigar_off, const uint8_t *seq,
+                        const int64_t *seq_off, int32_t start, int32_t end, int32_t num_dtypes, int32_t min_mapq,
+                        int32_t mode, int32_t sym_indels, int64_t max_cols, float *feats_out, int64_t *depth_out,
+                        int64_t *major_out, int64_t *minor_out, int64_t *n_cols_out) {
+    MDK_REQUIRE(n_cols_out, MDK_ERR_ARG, "pileup_features: n_cols_out is NULL");
+    *n_cols_out = 0;
+    MDK_REQUIRE(n_rec >= 0 && end >= start && max_cols >= 0, MDK_ERR_ARG, "pileup_features: bad sizes");
+    MDK_REQUIRE(num_dtypes >= 1 && num_dtypes <= 4, MDK_ERR_UNSUPPORTED, "pileup_features: 1..4 dtypes supported");
+    MDK_REQUIRE(mode >= MDK_NORM_TOTAL && mode <= MDK_NORM_NONE, MDK_ERR_ARG, "pileup_features: unknown mode");
+    if (n_rec == 0 || end == start) return MDK_OK;
+    MDK_REQUIRE(pos && flag && mapq && dtype && cigar && cigar_off && seq && seq_off, MDK_ERR_ARG,
+                "pileup_features: NULL record array");
+    MDK_REQUIRE(max_cols == 0 || (feats_out && major_out && minor_out), MDK_ERR_ARG, "pileup_features: NULL output");
+    MDK_CUDA(cudaSetDevice(device));
+    const int64_t n_ops = cigar_off[n_rec], n_seq = seq_off[n_rec];
+    const int F = 10 * num_dtypes;
+    size_t off = 0;
+    auto take = [&off](size_t bytes) { size_t o = off; off += (bytes + 15) / 16 * 16; return o; };
+    const size_t o_pos = take((size_t)n_rec * 4), o_flag = take((size_t)n_rec * 2), o_mapq = take((size_t)n_rec),
+                 o_dt = take((size_t)n_rec), o_cig = take((size_t)n_ops * 4), o_coff = take((size_t)(n_rec + 1) * 8),
+                 o_seq = take((size_t)n_seq), o_soff = take((size_t)(n_rec + 1) * 8),
+                 o_cnt = take((size_t)max_cols * F * 8), o_maj = take((size_t)max_cols * 8),
+                 o_min = take((size_t)max_cols * 8), o_feat = take((size_t)max_cols * F * 4),
+                 o_dep = take((size_t)max_cols * 8);
+    uint8_t *buf = nullptr;
+    MDK_CUDA(plp_scratch(off + 16, &buf, 1));
+    cudaError_t err = cudaSuccess;
+    auto up = [&](size_t o, const void *src, size_t bytes) {
+        if (err == cudaSuccess && bytes) err = cudaMemcpy(buf + o, src, bytes, cudaMemcpyHostToDevice);
+    };
+    up(o_pos, pos, (size_t)n_rec * 4); up(o_flag, flag, (size_t)n_rec * 2); up(o_mapq, mapq, (size_t)n_rec);
+    up(o_dt, dtype, (size_t)n_rec); up(o_cig, cigar, (size_t)n_ops * 4); up(o_coff, cigar_off, (size_t)(n_rec + 1) * 8);
+    up(o_seq, seq, (size_t)n_seq); up(o_soff, seq_off, (size_t)(n_rec + 1) * 8);
+    if (err != cudaSuccess) return cuda_fail(err, "pileup_features (copy in)", __FILE__, __LINE__);
+    int rc = pileup_counts_dev(n_rec, (const int32_t *)(buf + o_pos), (const uint16_t *)(buf + o_flag), buf + o_mapq,
+                               buf + o_dt, (const uint32_t *)(buf + o_cig), (const int64_t *)(buf + o_coff), n_ops,
+                               buf + o_seq, (const int64_t *)(buf + o_soff), start, end, num_dtypes, min_mapq, max_cols,
+                               (uint64_t *)(buf + o_cnt), (int64_t *)(buf + o_maj), (int64_t *)(buf + o_min), n_cols_out, 0);
+    if (rc) return rc;
+    const int64_t n = *n_cols_out;
+    if (n > max_cols) {
+        set_error("pileup_features: output buffers too small (see *n_cols_out)");
+        return MDK_ERR_NOMEM;
+    }
+    if (n == 0) return MDK_OK;
+    MDK_CUDA(launch_normalise((const uint64_t *)(buf + o_cnt), (const int64_t *)(buf + o_maj), (const int64_t *)(buf + o_min), n,
+                              num_dtypes, mode, sym_indels, (float *)(buf + o_feat), (int64_t *)(buf + o_dep), 0));
+    err = cudaMemcpy(feats_out, buf + o_feat, (size_t)n * F * 4, cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess && depth_out) err = cudaMemcpy(depth_out, buf + o_dep, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess) err = cudaMemcpy(major_out, buf + o_maj, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess) err = cudaMemcpy(minor_out, buf + o_min, (size_t)n * 8, cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess) return cuda_fail(err, "pileup_features (copy out)", __FILE__, __LINE__);
+    return MDK_OK;
 }
 
 // ---------------------------------------------------------------------------- decode seam

@@ -89,9 +89,10 @@ def pileup_counts_from_batch(batch, start, end, num_dtypes=1, min_mapq=1, device
                 seq=np.ascontiguousarray(batch.seq, np.uint8), soff=np.ascontiguousarray(batch.seq_off, np.int64))
     n_cols = ffi.new("int64_t *")
     for _ in range(2):
-        counts = np.zeros((max_cols, F), dtype=np.uint64)
-        major = np.zeros(max_cols, dtype=np.int64)
-        minor = np.zeros(max_cols, dtype=np.int64)
+        # (np.empty: untouched pages of the reference-style over-allocation cost nothing; the library writes n rows)
+        counts = np.empty((max_cols, F), dtype=np.uint64)
+        major = np.empty(max_cols, dtype=np.int64)
+        minor = np.empty(max_cols, dtype=np.int64)
         rc = lib.mdk_pileup_counts(
             device, n_rec, ffi.cast("const int32_t *", ffi.from_buffer(arrs["pos"])),
             ffi.cast("const uint16_t *", ffi.from_buffer(arrs["flag"])),
@@ -113,7 +114,49 @@ def pileup_counts_from_batch(batch, start, end, num_dtypes=1, min_mapq=1, device
     positions = np.empty(n, dtype=[('major', '<i8'), ('minor', '<i8')])
     positions['major'] = major[:n]
     positions['minor'] = minor[:n]
-    return counts[:n].copy(), positions
+    return counts[:n], positions
+
+
+def pileup_features_from_batch(batch, start, end, num_dtypes=1, min_mapq=1, normalise='total', sym_indels=False,
+                               device=0):
+    """calculate_pileup + _post_process_pileup in one device pass (mdk_pileup_features): the counts never leave the
+    GPU.  Returns (features float32 [n, 10*num_dtypes], depth int64 [n], positions) for [start, end)."""
+    lib, ffi = _lm.load(), _lm.ffi
+    n_rec = len(batch.pos)
+    F = 10 * num_dtypes
+    max_cols = max(2 * (end - start), 16)
+    arrs = dict(pos=np.ascontiguousarray(batch.pos, np.int32), flag=np.ascontiguousarray(batch.flag, np.uint16),
+                mapq=np.ascontiguousarray(batch.mapq, np.uint8), dtype=np.ascontiguousarray(batch.dtype, np.uint8),
+                cigar=np.ascontiguousarray(batch.cigar, np.uint32), coff=np.ascontiguousarray(batch.cigar_off, np.int64),
+                seq=np.ascontiguousarray(batch.seq, np.uint8), soff=np.ascontiguousarray(batch.seq_off, np.int64))
+    n_cols = ffi.new("int64_t *")
+    for _ in range(2):
+        feats = np.empty((max_cols, F), dtype=np.float32)
+        depth = np.empty(max_cols, dtype=np.int64)
+        major = np.empty(max_cols, dtype=np.int64)
+        minor = np.empty(max_cols, dtype=np.int64)
+        rc = lib.mdk_pileup_features(
+            device, n_rec, ffi.cast("const int32_t *", ffi.from_buffer(arrs["pos"])),
+            ffi.cast("const uint16_t *", ffi.from_buffer(arrs["flag"])),
+            ffi.cast("const uint8_t *", ffi.from_buffer(arrs["mapq"])),
+            ffi.cast("const uint8_t *", ffi.from_buffer(arrs["dtype"])),
+            ffi.cast("const uint32_t *", ffi.from_buffer(arrs["cigar"])),
+            ffi.cast("const int64_t *", ffi.from_buffer(arrs["coff"])),
+            ffi.cast("const uint8_t *", ffi.from_buffer(arrs["seq"])),
+            ffi.cast("const int64_t *", ffi.from_buffer(arrs["soff"])),
+            int(start), int(end), num_dtypes, int(min_mapq), _NORM_MODES[normalise], 1 if sym_indels else 0, max_cols,
+            ffi.cast("float *", ffi.from_buffer(feats)), ffi.cast("int64_t *", ffi.from_buffer(depth)),
+            ffi.cast("int64_t *", ffi.from_buffer(major)), ffi.cast("int64_t *", ffi.from_buffer(minor)), n_cols)
+        if rc == lib.MDK_ERR_NOMEM and n_cols[0] > max_cols:
+            max_cols = int(n_cols[0])
+            continue
+        _lm.check(rc)
+        break
+    n = int(n_cols[0])
+    positions = np.empty(n, dtype=[('major', '<i8'), ('minor', '<i8')])
+    positions['major'] = major[:n]
+    positions['minor'] = minor[:n]
+    return feats[:n], depth[:n], positions
 
 
 class CountsFeatureEncoder(object):
@@ -201,8 +244,43 @@ class CountsFeatureEncoder(object):
             ref_name=region.ref_name, features=feats, labels=None, ref_seq=None,
             positions=positions, label_probs=None, depth=depth)
 
+    _fused_featuriser = True     # counts -> features in one device pass (subclasses with other features switch it off)
+
+    def _fused_samples(self, reads_bam, region):
+        """bam_to_sample through mdk_pileup_features: fetch, pileup + normalise on the device, split at coverage gaps.
+        Same Samples as the two-step path (a minor column and its major never sit on different sides of a gap)."""
+        from medaka_b200 import bam as mbam
+        bam = reads_bam if isinstance(reads_bam, mbam.BamFile) else mbam.BamFile(reads_bam)
+        if self.tag_name is not None and len(self.tag_name) != 2:
+            raise ValueError("'tag_name' must be a length-2 string.")
+        dts = self.dtypes
+        multi = not (dts is None or isinstance(dts, str) or len(dts) == 1)
+        batch = bam.fetch(region.ref_name, region.start, region.end, dtypes=dts if multi else None, tag_name=self.tag_name,
+                          tag_value=self.tag_value, keep_missing=self.tag_keep_missing, read_group=self.read_group,
+                          min_mapq=self.min_mapq)
+        feats, depth, positions = pileup_features_from_batch(
+            batch, region.start, region.end, len(dts) if multi else 1, self.min_mapq, self.normalise, self.sym_indels,
+            self.device)
+        if len(positions) == 0:
+            return None
+        cuts = np.where(np.ediff1d(positions['major']) > 1)[0] + 1
+        bounds = [0] + cuts.tolist() + [len(positions)]
+        samples = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            p = positions[a:b]
+            if p['major'][0] != region.start or p['major'][-1] + 1 != region.end:
+                self.logger.warning('Pileup counts do not span requested region, requested {}, received {}-{}.'.format(
+                    region, p['major'][0], p['major'][-1]))
+            samples.append(common.Sample(ref_name=region.ref_name, features=feats[a:b], labels=None, ref_seq=None,
+                                         positions=p, label_probs=None, depth=depth[a:b]))
+        return samples
+
     def bam_to_sample(self, reads_bam, region):
         """Convert a section of an alignment pileup to samples (features.py:770-798)."""
+        if self._fused_featuriser and self.pileup_source is None:
+            fused = self._fused_samples(reads_bam, region)
+            if fused is not None:
+                return fused
         samples = []
         for counts, positions in self._pileup_function(region, reads_bam):
             if len(counts) == 0:
@@ -412,6 +490,7 @@ class ReadAlignmentFeatureEncoder(CountsFeatureEncoder):
     position: [base, baseQ, strand, mapQ (, dwell) (, haplotype) (, datatype)]; bases 0-5 = [pad, A, C, G, T, deletion]."""
 
     feature_dtype = np.int8
+    _fused_featuriser = False
 
     def __init__(self, dtypes=('',), tag_name=None, tag_value=None, tag_keep_missing=False, read_group=None,
                  min_mapq=1, max_reads=100, row_per_read=False, include_dwells=True, include_haplotype=False,

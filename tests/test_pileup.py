@@ -174,3 +174,73 @@ def test_gpu_bam_to_sample_end_to_end(golden_dir):
     pos["major"], pos["minor"] = g["major"], g["minor"]
     ef, ed = features_oracle.post_process_pileup(g["counts"].copy(), pos, "total")
     assert np.array_equal(samples[0].features, ef) and np.array_equal(np.asarray(samples[0].depth), ed.astype(np.int64))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("normalise,sym,dtypes", [("total", False, None), ("fwd_rev", False, None), (None, True, None),
+                                                  ("total", True, ("dt0", "dt1")), ("fwd_rev", False, ("dt0", "dt1"))])
+def test_gpu_fused_pileup_features_match_two_step(normalise, sym, dtypes):
+    """mdk_pileup_features (counts stay on the device) against oracle pileup + oracle post-processing, on reads with a
+    coverage gap, consecutive insertions and two datatypes."""
+    from medaka_b200 import bam, features
+    recs = synth.synth_reads(140, 2400, seed=31, mean_len=300, num_dtypes=2 if dtypes else 1)
+    recs = [r for r in recs if not (900 <= r["pos"] < 1100)]          # thin out a stretch: a gap in coverage
+    for r in recs:
+        if r["pos"] < 900:
+            r["cigar"] = _clip_cigar(r["cigar"], 900 - r["pos"])
+    batch = bam.records_from_dicts(recs, dtypes=dtypes)
+    nd = len(dtypes) if dtypes else 1
+    feats, depth, pos = features.pileup_features_from_batch(batch, 100, 2300, nd, 1, normalise, sym)
+    ec, ep = pileup_oracle.pileup_counts(recs, 100, 2300, dtypes=dtypes)
+    assert np.array_equal(pos, ep)
+    assert (np.ediff1d(ep["major"]) > 1).any()
+    # the reference normalises each gap-free piece on its own (features.py:125-134 then :871-935)
+    cuts = np.where(np.ediff1d(ep["major"]) > 1)[0] + 1
+    bounds = [0] + cuts.tolist() + [len(ep)]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        ef, ed = features_oracle.post_process_pileup(ec[a:b].copy(), ep[a:b], normalise, dtypes=dtypes or ("",), sym_indels=sym)
+        assert np.array_equal(feats[a:b], ef)
+        assert np.array_equal(depth[a:b], ed.astype(np.int64))
+
+
+def _clip_cigar(cigar, max_ref):
+    """Cut a CIGAR string so that it consumes at most max_ref reference bases (keeps it ending in a match)."""
+    import re
+    out, used = [], 0
+    for n, op in re.findall(r"(\d+)([MIDNSHP=X])", cigar):
+        n = int(n)
+        if op in "MDN=X":
+            if used + n > max_ref:
+                n = max_ref - used
+                if n > 0 and op in "M=X":
+                    out.append("%d%s" % (n, op))
+                break
+            used += n
+        out.append("%d%s" % (n, op))
+    while out and out[-1][-1] not in "M=X":
+        out.pop()
+    return "".join(out) or "1M"
+
+
+@pytest.mark.gpu
+def test_gpu_encoder_fused_path_on_bam_file(tmp_path):
+    """CountsFeatureEncoder.bam_to_sample on a BAM file (native reader -> fused device featuriser) equals the two-step
+    path (pileup_counts -> _post_process_pileup) sample by sample."""
+    from medaka_b200 import common, features
+    from tests import bamutil
+    recs = synth.synth_reads(120, 3000, seed=8, mean_len=400)
+    recs = [r for r in recs if not (1400 <= r["pos"] < 1500)]
+    recs.sort(key=lambda r: r["pos"])
+    for r in recs:
+        r["ref"] = 0
+    path = str(tmp_path / "r.bam")
+    bamutil.write_bam(path, [("ctg", 3000)], recs)
+    region = common.Region("ctg", 0, 3000)
+    for normalise in ("total", "fwd_rev", None):
+        enc = features.CountsFeatureEncoder(normalise=normalise, sym_indels=normalise == "total")
+        fused = enc.bam_to_sample(path, region)
+        two = [enc._post_process_pileup(c, p, region) for c, p in enc._pileup_function(region, path)]
+        assert len(fused) == len(two) >= 1
+        for a, b in zip(fused, two):
+            assert np.array_equal(a.positions, b.positions) and np.array_equal(a.features, b.features)
+            assert np.array_equal(np.asarray(a.depth), np.asarray(b.depth))

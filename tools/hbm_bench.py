@@ -146,6 +146,35 @@ def main():
                                            "call_ms": t * 1e3, "reads_per_s": args.reads / t,
                                            "columns_per_s": len(positions) / t,
                                            "aligned_bases_per_s": aligned / t}
+    def run_fused():
+        holder["fused"] = mfeatures.pileup_features_from_batch(batch, 0, span, 1, 1, "total", False, dev)
+    t = timed(run_fused)
+    res["pileup_features fused (host buffers)"] = {"reads": args.reads, "columns": int(len(holder["fused"][2])),
+                                                   "call_ms": t * 1e3, "reads_per_s": args.reads / t,
+                                                   "columns_per_s": len(holder["fused"][2]) / t,
+                                                   "aligned_bases_per_s": aligned / t}
+
+    def run_two_step():
+        c, p = mfeatures.pileup_counts_from_batch(batch, 0, span, num_dtypes=1, min_mapq=1, device=dev)
+        enc = mfeatures.CountsFeatureEncoder(normalise="total", device=dev)
+
+        class R(object):
+            ref_name, start, end = "x", 0, span
+        holder["two"] = enc._post_process_pileup(c, p, R)
+    t = timed(run_two_step)
+    res["pileup_counts + normalise, two calls (host buffers)"] = {"call_ms": t * 1e3, "columns_per_s": len(positions) / t}
+
+    # ---- a11 read-level feature matrix over the same reads (host pointers; row bookkeeping on the host) ----
+    rbatch = batch._replace(names=["r%d" % i for i in range(args.reads)],
+                            qual=np.tile(b0.qual, reps) if b0.qual is not None else None)
+
+    def run_rm():
+        holder["rm"] = mfeatures.read_matrix_from_batch(rbatch, 0, span, max_reads=100, device=dev)
+    t = timed(run_rm, reps=2)
+    rm = holder["rm"][0]
+    res["read_matrix (host buffers)"] = {"reads": args.reads, "columns": int(rm.shape[0]), "rows": int(rm.shape[1]),
+                                         "call_ms": t * 1e3, "reads_per_s": args.reads / t,
+                                         "cells_per_s": rm.shape[0] * rm.shape[1] / t}
     if args.cpu_pileup:
         from oracle import pileup_oracle
         sub_span = span0 // 8                              # bounded sample of the same reads

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--batch-size", type=int, default=200)
     ap.add_argument("--workers", type=int, default=8)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--profile", action="store_true", help="cProfile every thread of the timed run, print the top entries")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -71,10 +72,41 @@ def main():
                                batch_size=args.batch_size, bam_chunk=1000000, bam_workers=args.workers)
     if dist is not None:
         dist.barrier()
+    acc = {}
+    if args.profile:
+        # wall-clock accumulators around the stages (summed over the threads that run them); cProfile cannot follow
+        # several threads at once under Python 3.12
+        import threading
+        from medaka_b200 import datastore, torch_ext
+        lock = threading.Lock()
+
+        def timed(owner, name, label):
+            fn = getattr(owner, name)
+
+            def wrapper(*a, **k):
+                t = time.perf_counter()
+                try:
+                    return fn(*a, **k)
+                finally:
+                    d = time.perf_counter() - t
+                    with lock:
+                        acc[label] = acc.get(label, 0.0) + d
+                        acc[label + " calls"] = acc.get(label + " calls", 0) + 1
+            setattr(owner, name, wrapper)
+        enc.pileup_source = (lambda f: (lambda *a: f(*a)))(pileup_source)
+        timed(enc, "pileup_source", "synthetic counts (loader threads)")
+        timed(enc, "_post_process_pileup", "normalise on GPU incl. copies (loader threads)")
+        timed(torch_ext.Batch, "collate", "Batch.collate (batcher thread)")
+        timed(model, "predict_async", "predict_async: copy into pinned + submit (main)")
+        timed(model, "wait", "engine wait (main)")
+        timed(datastore._NpzBackend, "write_fields", "store write_fields (writer thread)")
+        timed(datastore.DataStore, "write_sample", "write_sample submit (main)")
     t0 = time.perf_counter()
     prediction.predict_regions(out, None, mine, model, enc, chunk_len=10000, chunk_ovlp=1000,
                                batch_size=args.batch_size, bam_chunk=1000000, bam_workers=args.workers)
     dt = time.perf_counter() - t0
+    if args.profile:
+        sys.stderr.write("stage seconds (wall, summed over threads): %s\n" % json.dumps({k: round(v, 3) for k, v in acc.items()}))
     cols = sum(int((base_pos["major"] < (r.end - r.start)).sum()) for r in mine)
     if dist is not None:
         import torch
