@@ -536,8 +536,8 @@ def main():
         mlabels, vminor, vref = vd
         t0 = time.perf_counter()
         n_var = 0
-        for w in range(0, B, 64):                       # 64 windows per call: 640 k columns, like a joined region
-            wb = min(B, w + 64)
+        for w in range(0, B, 512):                      # 512 windows per call: 5.1 M columns, a joined multi-Mb contig
+            wb = min(B, w + 512)
             probs = h_probs[k % n_slots, w:wb].reshape(-1, 5)
             mn = np.tile(vminor, wb - w)
             rf = np.tile(vref, wb - w)
