@@ -247,6 +247,25 @@ int mdk_read_matrix(int device, int64_t n_rec, const int32_t *pos, const uint16_
                     int8_t *matrix_out, int64_t *major_out, int64_t *minor_out, int64_t *n_cols_out,
                     int32_t *n_reads_out, int32_t *left_read_out, int32_t *right_read_out);
 
+/* ---- read-level model seam: LatentSpaceLSTM (medaka/architectures/latent_space_lstm.py:34-207, the model class of the
+ * `rl_` consensus models) behind TorchModel.predict_on_batch (medaka/models.py:303-313) with
+ * ReadLevelFeaturesModel.get_model_input_features = batch.read_level_features (base_classes.py:29-36).
+ *   mdk_rl_create   lstm_size = cnn_size = 128 (the class defaults), 5 classes, kernel sizes [1, 17], mean pooling,
+ *                   bidirectional; anything else -> MDK_ERR_UNSUPPORTED
+ *   mdk_rl_load     one state-dict tensor by its torch name ("base_embedder.weight", "read_level_conv.convs.0.weight",
+ *                   "read_level_conv.convs.2.running_mean", "lstm.weight_ih_l0_reverse", "linear.bias", ...), host float32,
+ *                   torch's own layouts; tensors the forward does not use (num_batches_tracked,
+ *                   read_level_conv.expansion_layer.*) may be skipped
+ *   mdk_rl_forward  x int8 [B][P][D][F] host (the padded read-level feature tensor, torch_ext.py:127-136: F = 4, or 5 with
+ *                   dwells) -> probs float32 [B][P][5] host (softmax output, normalise = True as at inference) */
+typedef struct mdk_rl_engine mdk_rl_engine;
+int mdk_rl_create(int device, int32_t lstm_size, int32_t cnn_size, int32_t use_dwells, int32_t num_classes,
+                  mdk_rl_engine **out);
+int mdk_rl_destroy(mdk_rl_engine *e);
+int mdk_rl_load(mdk_rl_engine *e, const char *name, const float *data, int64_t n);
+int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P, int64_t D, int64_t F,
+                   float *probs_host);
+
 /* ---- alignment access: what calculate_pileup gets from htslib (create_bam_fset src/medaka_bamiter.c:52-63,
  * bam_itr_querys src/medaka_counts.c:233, the flag / mapQ part of read_bam src/medaka_bamiter.c:19-21).  Native BGZF
  * inflate (zlib, a thread pool over the independent members), BAI-indexed region fetch (bins + linear index; without an

@@ -1,0 +1,616 @@
+// Read-level consensus network: LatentSpaceLSTM.forward (medaka/architectures/latent_space_lstm.py:154-207) with
+// ReadLevelConv (read_level_modules.py:45-78) and MeanPooler (:81-100), fp32 on the CUDA cores - the first correct
+// version of SURVEY.md row f4's network half (the feature tensor comes from mdk_read_matrix, pileup.cu).
+//
+//   x int8 [B][P][D][F]  (base, quality, strand, mapQ [, dwell])                      latent_space_lstm.py:163-183
+//   e = base_embedder[base] + strand_embedder[strand + 1]  (6) ++ q / 25 - 1 (++ dwell)          :168-183
+//   y1 = BN1(ReLU(Conv1d k=1 (7|8 -> C)))          per read, along positions                       read_level_modules.py:31-40
+//   y2 = BN2(ReLU(Conv1d k=17, zero padding 8 (C -> C)))
+//   z  = mean over the non-empty reads of Linear(C -> H)(y2)                                        :192-197, MeanPooler
+//   two bidirectional LSTM layers (H), Linear(2H -> 5), softmax                                    :198-205
+// Sizes: C = cnn_size = H = lstm_size = 128 (the class defaults); other sizes are refused.  BatchNorm runs in inference
+// mode (running statistics), in torch's operation order ((x - mean) * invstd * weight + bias).
+//
+// Kernels:
+//   rl_mask_kernel        which (window, read) rows are non-empty (x.sum((1, -1)) != 0, :163-165)
+//   rl_embed_conv1_kernel embedding lookups + the k = 1 convolution + ReLU + BN1 -> y1 [B][D][P][C]  (non-empty rows only)
+//   rl_conv17_pool_kernel the k = 17 convolution as an implicit GEMM (64 positions x 128 channels per CTA, K = 17 x 128,
+//                         8 x 4 register tiles, weights streamed through shared memory), ReLU + BN2 and the masked SUM
+//                         over a group of reads, all in one pass: y2 never exists in memory
+//   rl_pool_linear_kernel sum of the read groups / number of reads, then Linear(C -> H).  (The reference applies the
+//                         Linear before the mean; the mean of an affine map is the affine map of the mean.)
+//   rl_gemm_kernel        LSTM input projections  gi = X W_ih^T + b_ih + b_hh   (both directions in one launch)
+//   rl_lstm_kernel        the LSTM recurrence: one CTA = 8 windows of one direction, 512 threads (gate g, unit j);
+//                         W_hh^T of gates i, f, g resident in shared memory (192 KiB), gate o's rows distributed over the
+//                         threads' registers (32 weights each); c and h stay on chip for all P steps
+//   head_kernel (misc.cu) Linear(2H -> 5) + softmax, shared with the counts models
+// All of it is CUDA-core fp32: parity first (tests/test_read_level.py against the reference's own class); the convolution
+// is 99 % of the FLOPs (557 kFLOP per read and position) and belongs on tcgen05 next.
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mdk {
+
+constexpr int RL_C = 128;        // cnn_size
+constexpr int RL_H = 128;        // lstm_size
+constexpr int RL_EMB = 6;        // bases_embedding_size
+constexpr int RL_TAPS = 17;
+constexpr int RL_PAD = 8;
+constexpr int RL_G4 = 4 * RL_H;
+
+__device__ __forceinline__ float rl_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------- mask
+__global__ void __launch_bounds__(256) rl_mask_kernel(const int8_t *__restrict__ x, int64_t P, int D, int F,
+                                                      uint8_t *__restrict__ mask) {
+    // one block per (b, d): sum over positions and features != 0  (int sum like torch's int64 reduction of int8 input)
+    const int64_t b = blockIdx.x / D;
+    const int d = (int)(blockIdx.x % D);
+    long long s = 0;
+    for (int64_t i = threadIdx.x; i < P * F; i += blockDim.x) {
+        const int64_t p = i / F;
+        const int f = (int)(i % F);
+        s += x[((b * P + p) * D + d) * F + f];
+    }
+    __shared__ long long red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mask[blockIdx.x] = red[0] != 0;
+}
+
+// ---------------------------------------------------------------------------------------------- embedding + conv k=1
+struct RlConv1 {
+    const float *emb_base;      // [6][6]
+    const float *emb_strand;    // [3][6]
+    const float *w;             // [C][in]   in = 7 (+1 dwell)
+    const float *b;             // [C]
+    const float *bn_mean, *bn_invstd, *bn_w, *bn_b;   // [C]
+};
+
+__global__ void __launch_bounds__(RL_C) rl_embed_conv1_kernel(const int8_t *__restrict__ x, const uint8_t *__restrict__ mask,
+                                                              RlConv1 a, int64_t P, int D, int F, int use_dwells,
+                                                              float *__restrict__ y1) {
+    // grid: (position chunks of 32, B * D); thread = output channel
+    const int64_t bd = blockIdx.y;
+    if (!mask[bd]) return;
+    const int64_t b = bd / D;
+    const int d = (int)(bd % D);
+    const int c = threadIdx.x;
+    const int nin = RL_EMB + 1 + (use_dwells ? 1 : 0);
+    float w[RL_EMB + 2];
+    for (int i = 0; i < nin; ++i) w[i] = a.w[c * nin + i];
+    const float bias = a.b[c], mean = a.bn_mean[c], invstd = a.bn_invstd[c], bw = a.bn_w[c], bb = a.bn_b[c];
+    __shared__ float in[32][RL_EMB + 2];
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    if (threadIdx.x < 32) {
+        const int64_t p = p0 + threadIdx.x;
+        if (p < P) {
+            const int8_t *v = x + ((b * P + p) * D + d) * F;
+            const int base = min(max((int)v[0], 0), 5), strand = min(max((int)v[2] + 1, 0), 2);
+            for (int i = 0; i < RL_EMB; ++i) in[threadIdx.x][i] = a.emb_base[base * RL_EMB + i] + a.emb_strand[strand * RL_EMB + i];
+            in[threadIdx.x][RL_EMB] = (float)v[1] / 25.0f - 1.0f;
+            if (use_dwells) in[threadIdx.x][RL_EMB + 1] = (float)v[4];
+        }
+    }
+    __syncthreads();
+    for (int i = 0; i < 32; ++i) {
+        const int64_t p = p0 + i;
+        if (p >= P) break;
+        float acc = bias;
+        for (int k = 0; k < nin; ++k) acc = fmaf(w[k], in[i][k], acc);
+        acc = fmaxf(acc, 0.f);
+        y1[(bd * P + p) * RL_C + c] = (acc - mean) * invstd * bw + bb;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- conv k=17 + pooling
+struct RlConv17 {
+    const float *w_t;           // [17][C in][C out]  (transposed from torch's [out][in][tap])
+    const float *b;             // [C]
+    const float *bn_mean, *bn_invstd, *bn_w, *bn_b;
+};
+constexpr int RL_PT = 64;                        // positions per CTA
+constexpr int RL_ROWS = RL_PT + 2 * RL_PAD;      // 80 staged input rows
+constexpr int RL_YS = RL_C + 4;                  // padded row stride of the staged input
+constexpr int RL_KC = 32;                        // input channels per weight chunk
+constexpr int RL_CONV_SMEM = (RL_ROWS * RL_YS + RL_KC * RL_C) * 4;
+
+__global__ void __launch_bounds__(256) rl_conv17_pool_kernel(const float *__restrict__ y1, const uint8_t *__restrict__ mask,
+                                                             RlConv17 a, int64_t P, int D, int dgroup,
+                                                             float *__restrict__ partial) {
+    // grid: (position tiles, read groups, B).  partial [B][n_groups][P][C]
+    extern __shared__ __align__(16) float smem_rl[];
+    float *ys = smem_rl;                      // [80][132]
+    float *ws = smem_rl + RL_ROWS * RL_YS;    // [32][128]
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;   // 16 channel groups of 8, 16 position groups of 4
+    const int64_t b = blockIdx.z;
+    const int g = blockIdx.y;
+    const int64_t p0 = (int64_t)blockIdx.x * RL_PT;
+    float bias[8], mean[8], invstd[8], bw[8], bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = tx * 8 + j;
+        bias[j] = a.b[c]; mean[j] = a.bn_mean[c]; invstd[j] = a.bn_invstd[c]; bw[j] = a.bn_w[c]; bb[j] = a.bn_b[c];
+    }
+    float pooled[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pooled[i][j] = 0.f;
+    const int d0 = g * dgroup, d1 = min(D, d0 + dgroup);
+    for (int d = d0; d < d1; ++d) {
+        const int64_t bd = b * D + d;
+        if (!mask[bd]) continue;                                   // (uniform over the CTA)
+        __syncthreads();
+        // stage rows p0-8 .. p0+71 of this read's y1, zeros outside [0, P)  (Conv1d zero padding)
+        for (int i = tid; i < RL_ROWS * (RL_C / 4); i += 256) {
+            const int r = i / (RL_C / 4), q = i % (RL_C / 4);
+            const int64_t p = p0 - RL_PAD + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p >= 0 && p < P) v = *reinterpret_cast<const float4 *>(y1 + (bd * P + p) * RL_C + q * 4);
+            *reinterpret_cast<float4 *>(ys + r * RL_YS + q * 4) = v;
+        }
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int t = 0; t < RL_TAPS; ++t) {
+            for (int cc = 0; cc < RL_C / RL_KC; ++cc) {
+                __syncthreads();                                   // previous chunk consumed (and ys staged)
+                const float *wsrc = a.w_t + ((size_t)t * RL_C + cc * RL_KC) * RL_C;
+                for (int i = tid; i < RL_KC * RL_C / 4; i += 256)
+                    reinterpret_cast<float4 *>(ws)[i] = reinterpret_cast<const float4 *>(wsrc)[i];
+                __syncthreads();
+#pragma unroll 4
+                for (int k = 0; k < RL_KC; ++k) {
+                    float av[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) av[i] = ys[(ty * 4 + i + t) * RL_YS + cc * RL_KC + k];
+                    const float4 b0 = *reinterpret_cast<const float4 *>(ws + k * RL_C + tx * 8);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(ws + k * RL_C + tx * 8 + 4);
+                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float v = fmaxf(acc[i][j] + bias[j], 0.f);
+                pooled[i][j] += (v - mean[j]) * invstd[j] * bw[j] + bb[j];
+            }
+    }
+    const int n_groups = gridDim.y;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t p = p0 + ty * 4 + i;
+        if (p >= P) continue;
+        float *dst = partial + (((b * n_groups + g) * P + p) * RL_C) + tx * 8;
+        *reinterpret_cast<float4 *>(dst) = make_float4(pooled[i][0], pooled[i][1], pooled[i][2], pooled[i][3]);
+        *reinterpret_cast<float4 *>(dst + 4) = make_float4(pooled[i][4], pooled[i][5], pooled[i][6], pooled[i][7]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- mean + Linear(C -> H)
+__global__ void __launch_bounds__(RL_H) rl_pool_linear_kernel(const float *__restrict__ partial, const uint8_t *__restrict__ mask,
+                                                              const float *__restrict__ w, const float *__restrict__ bias,
+                                                              int64_t P, int D, int n_groups, float *__restrict__ out) {
+    // grid: (P, B); thread = output unit.  w [H][C]
+    const int64_t b = blockIdx.y, p = blockIdx.x;
+    __shared__ float v[RL_C];
+    __shared__ int n_reads;
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int d = 0; d < D; ++d) n += mask[b * D + d];
+        n_reads = n;
+    }
+    float s = 0.f;
+    for (int g = 0; g < n_groups; ++g) s += partial[((b * n_groups + g) * P + p) * RL_C + threadIdx.x];
+    __syncthreads();
+    v[threadIdx.x] = s / (float)n_reads;             // 0 / 0 = nan when a window has no reads, like the reference
+    __syncthreads();
+    const int h = threadIdx.x;
+    float acc = bias[h];
+    for (int k = 0; k < RL_C; ++k) acc = fmaf(w[h * RL_C + k], v[k], acc);
+    out[(b * P + p) * RL_H + h] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------- generic fp32 GEMM
+// C[M][N] = A[M][K] . W[N][K]^T + bias[N];  K % 16 == 0, N % 128 == 0.  128 x 128 x 16 tiles, 8 x 8 per thread.
+__global__ void __launch_bounds__(256) rl_gemm_kernel(const float *__restrict__ A, const float *__restrict__ W,
+                                                      const float *__restrict__ bias, float *__restrict__ C, int64_t M,
+                                                      int K, int N) {
+    __shared__ float As[16][128 + 4];
+    __shared__ float Ws[16][128 + 4];
+    const int tid = threadIdx.x;
+    const int64_t m0 = (int64_t)blockIdx.x * 128;
+    const int n0 = blockIdx.y * 128;
+    const int tx = tid % 16, ty = tid / 16;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int lrow = tid / 4, lk = (tid % 4) * 4;
+    for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int r = lrow + half * 64;
+            const int64_t gm = m0 + r;
+            float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gm < M) av = *reinterpret_cast<const float4 *>(A + gm * K + k0 + lk);
+            As[lk + 0][r] = av.x; As[lk + 1][r] = av.y; As[lk + 2][r] = av.z; As[lk + 3][r] = av.w;
+            const float4 wv = *reinterpret_cast<const float4 *>(W + (int64_t)(n0 + r) * K + k0 + lk);
+            Ws[lk + 0][r] = wv.x; Ws[lk + 1][r] = wv.y; Ws[lk + 2][r] = wv.z; Ws[lk + 3][r] = wv.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Ws[k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Ws[k][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float bv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = bias[n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4)];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        if (gm >= M) continue;
+        float *dst = C + gm * N + n0;
+        *reinterpret_cast<float4 *>(dst + tx * 4) = make_float4(acc[i][0] + bv[0], acc[i][1] + bv[1], acc[i][2] + bv[2], acc[i][3] + bv[3]);
+        *reinterpret_cast<float4 *>(dst + 64 + tx * 4) = make_float4(acc[i][4] + bv[4], acc[i][5] + bv[5], acc[i][6] + bv[6], acc[i][7] + bv[7]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- LSTM recurrence
+// gi  [B*P][2 dirs][4H]  (torch gate order i, f, g, o; b_ih + b_hh folded in)
+// out [B*P][2H]          (columns dir*H + j)
+// w3t [dir][H k][3H]     W_hh^T of gates i, f, g;   wo [dir][H j][H k]  W_hh rows of gate o
+constexpr int RL_NB = 8;
+constexpr int RL_LSTM_SMEM = (RL_H * 3 * RL_H + 2 * RL_NB * RL_H + 6 * RL_NB * RL_H) * 4;     // 224 KiB
+
+__global__ void __launch_bounds__(512, 1) rl_lstm_kernel(const float *__restrict__ gi, const float *__restrict__ w3t,
+                                                         const float *__restrict__ wo, float *__restrict__ out, int64_t B,
+                                                         int64_t P) {
+    extern __shared__ __align__(16) float smem_rl[];
+    float *wt = smem_rl;                                  // [128 k][384]
+    float *hs = wt + RL_H * 3 * RL_H;                     // [2][NB][128]
+    float *pre = hs + 2 * RL_NB * RL_H;                   // [3 gates][NB][128]  +  [3 foreign partials of gate o][NB][128]
+    const int tid = threadIdx.x;
+    const int g = tid >> 7, j = tid & 127;                // gate slot 0..3, hidden unit
+    const int dir = blockIdx.y;
+    const int64_t b0 = (int64_t)blockIdx.x * RL_NB;
+    const int nb = (int)min((int64_t)RL_NB, B - b0);
+    {
+        const float *src = w3t + (size_t)dir * RL_H * 3 * RL_H;
+        for (int i = tid; i < RL_H * 3 * RL_H / 4; i += 512) reinterpret_cast<float4 *>(wt)[i] = reinterpret_cast<const float4 *>(src)[i];
+        for (int i = tid; i < 2 * RL_NB * RL_H; i += 512) hs[i] = 0.f;
+    }
+    float wq[32];                                         // gate o, row j, columns g*32 .. g*32+31
+#pragma unroll
+    for (int k = 0; k < 32; ++k) wq[k] = wo[((size_t)dir * RL_H + j) * RL_H + g * 32 + k];
+    // the update phase: thread (g, j) owns windows n = g, g + 4 (NB = 8) of unit j
+    float c_state[RL_NB / 4];
+#pragma unroll
+    for (int q = 0; q < RL_NB / 4; ++q) c_state[q] = 0.f;
+    __syncthreads();
+    int cur = 0;
+    for (int64_t step = 0; step < P; ++step) {
+        const int64_t t = dir ? (P - 1 - step) : step;
+        const float *hc = hs + cur * RL_NB * RL_H;
+        // partial of gate o over this thread's quarter of k
+        float part[RL_NB];
+#pragma unroll
+        for (int n = 0; n < RL_NB; ++n) part[n] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; k += 4) {
+#pragma unroll
+            for (int n = 0; n < RL_NB; ++n) {
+                const float4 hv = *reinterpret_cast<const float4 *>(hc + n * RL_H + g * 32 + k);
+                part[n] = fmaf(wq[k], hv.x, part[n]);
+                part[n] = fmaf(wq[k + 1], hv.y, part[n]);
+                part[n] = fmaf(wq[k + 2], hv.z, part[n]);
+                part[n] = fmaf(wq[k + 3], hv.w, part[n]);
+            }
+        }
+        // a window's owner (thread n % 4 of unit j) keeps its own quarter in registers; the other three quarters go
+        // through shared memory, slot (g - n % 4 + 4) % 4 - 1
+#pragma unroll
+        for (int n = 0; n < RL_NB; ++n) {
+            const int rel = (g - (n & 3) + 4) & 3;
+            if (rel != 0) pre[((3 + rel - 1) * RL_NB + n) * RL_H + j] = part[n];
+        }
+        if (g < 3) {
+            float acc[RL_NB];
+#pragma unroll
+            for (int n = 0; n < RL_NB; ++n) acc[n] = 0.f;
+#pragma unroll 2
+            for (int k = 0; k < RL_H; k += 4) {
+                float4 hv[RL_NB];
+#pragma unroll
+                for (int n = 0; n < RL_NB; ++n) hv[n] = *reinterpret_cast<const float4 *>(hc + n * RL_H + k);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float w = wt[(k + kk) * 3 * RL_H + g * RL_H + j];
+#pragma unroll
+                    for (int n = 0; n < RL_NB; ++n) {
+                        const float hvk = kk == 0 ? hv[n].x : kk == 1 ? hv[n].y : kk == 2 ? hv[n].z : hv[n].w;
+                        acc[n] = fmaf(w, hvk, acc[n]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < RL_NB; ++n) pre[(g * RL_NB + n) * RL_H + j] = acc[n];
+        }
+        float own[RL_NB / 4];
+#pragma unroll
+        for (int n = 0; n < RL_NB; ++n)
+            if ((n & 3) == g) own[n >> 2] = part[n];               // (compile-time n: no dynamic register indexing)
+        __syncthreads();
+        float *hn = hs + (cur ^ 1) * RL_NB * RL_H;
+#pragma unroll
+        for (int q = 0; q < RL_NB / 4; ++q) {
+            const int n = g + 4 * q;
+            const bool ok = n < nb;
+            const float *row = gi + (((b0 + (ok ? n : 0)) * P + t) * 2 + dir) * RL_G4;
+            const float gi_i = ok ? row[j] : 0.f, gi_f = ok ? row[RL_H + j] : 0.f, gi_g = ok ? row[2 * RL_H + j] : 0.f,
+                        gi_o = ok ? row[3 * RL_H + j] : 0.f;
+            // quarters in k order (0..3) whoever computed them: this thread's own is quarter g
+            float po = 0.f;
+#pragma unroll
+            for (int quarter = 0; quarter < 4; ++quarter) {
+                const int rel = (quarter - g + 4) & 3;
+                po += rel == 0 ? own[q] : pre[((3 + rel - 1) * RL_NB + n) * RL_H + j];
+            }
+            const float ig = rl_sigmoid(gi_i + pre[(0 * RL_NB + n) * RL_H + j]);
+            const float fg = rl_sigmoid(gi_f + pre[(1 * RL_NB + n) * RL_H + j]);
+            const float gg = tanhf(gi_g + pre[(2 * RL_NB + n) * RL_H + j]);
+            const float og = rl_sigmoid(gi_o + po);
+            const float c = fg * c_state[q] + ig * gg;
+            c_state[q] = c;
+            const float h = og * tanhf(c);
+            hn[n * RL_H + j] = h;
+            if (ok) out[((b0 + n) * P + t) * (2 * RL_H) + dir * RL_H + j] = h;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- engine
+struct RlLstmLayer {
+    float *w_ih = nullptr;      // [2 dirs * 4H][in]   (both directions stacked: one GEMM)
+    float *bias = nullptr;      // [2 * 4H]  b_ih + b_hh
+    float *w3t = nullptr;       // [2][H][3H]
+    float *wo = nullptr;        // [2][H][H]
+};
+
+}  // namespace mdk
+
+using namespace mdk;
+
+struct mdk_rl_engine {
+    int device = 0;
+    int use_dwells = 0;
+    std::unordered_map<std::string, std::vector<float>> host;     // state-dict tensors as loaded
+    bool prepared = false;
+    // device parameters
+    float *emb_base = nullptr, *emb_strand = nullptr;
+    float *c1_w = nullptr, *c1_b = nullptr, *bn1[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *c17_wt = nullptr, *c17_b = nullptr, *bn2[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *pool_w = nullptr, *pool_b = nullptr;
+    RlLstmLayer lstm[2];
+    float *lin_w = nullptr, *lin_b = nullptr;
+    std::vector<void *> allocs;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+int rl_upload(mdk_rl_engine *e, const std::vector<float> &v, float **out) {
+    void *p = nullptr;
+    MDK_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(float)));
+    e->allocs.push_back(p);
+    if (!v.empty()) MDK_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *out = static_cast<float *>(p);
+    return MDK_OK;
+}
+
+const std::vector<float> *rl_get(mdk_rl_engine *e, const std::string &name, size_t want) {
+    auto it = e->host.find(name);
+    if (it == e->host.end()) { set_error("read-level model: tensor '" + name + "' was not loaded"); return nullptr; }
+    if (it->second.size() != want) {
+        set_error("read-level model: tensor '" + name + "' has " + std::to_string(it->second.size()) + " values, expected " +
+                  std::to_string(want));
+        return nullptr;
+    }
+    return &it->second;
+}
+
+int rl_prepare(mdk_rl_engine *e) {
+    if (e->prepared) return MDK_OK;
+    const int nin = RL_EMB + 1 + (e->use_dwells ? 1 : 0);
+    int rc;
+#define RL_NEED(var, name, n) const std::vector<float> *var = rl_get(e, name, (size_t)(n)); if (!var) return MDK_ERR_STATE;
+    RL_NEED(eb, "base_embedder.weight", 6 * RL_EMB)
+    RL_NEED(es, "strand_embedder.weight", 3 * RL_EMB)
+    RL_NEED(c1w, "read_level_conv.convs.0.weight", RL_C * nin)
+    RL_NEED(c1b, "read_level_conv.convs.0.bias", RL_C)
+    RL_NEED(c17w, "read_level_conv.convs.3.weight", RL_C * RL_C * RL_TAPS)
+    RL_NEED(c17b, "read_level_conv.convs.3.bias", RL_C)
+    RL_NEED(pw, "pre_pool_expansion_layer.weight", RL_H * RL_C)
+    RL_NEED(pb, "pre_pool_expansion_layer.bias", RL_H)
+    RL_NEED(lw, "linear.weight", NCLS * 2 * RL_H)
+    RL_NEED(lb, "linear.bias", NCLS)
+    if ((rc = rl_upload(e, *eb, &e->emb_base)) || (rc = rl_upload(e, *es, &e->emb_strand)) || (rc = rl_upload(e, *c1w, &e->c1_w)) ||
+        (rc = rl_upload(e, *c1b, &e->c1_b)) || (rc = rl_upload(e, *c17b, &e->c17_b)) || (rc = rl_upload(e, *pw, &e->pool_w)) ||
+        (rc = rl_upload(e, *pb, &e->pool_b)) || (rc = rl_upload(e, *lw, &e->lin_w)) || (rc = rl_upload(e, *lb, &e->lin_b)))
+        return rc;
+    // conv k = 17 weights: torch [out][in][tap] -> [tap][in][out]
+    {
+        std::vector<float> wt((size_t)RL_TAPS * RL_C * RL_C);
+        for (int o = 0; o < RL_C; ++o)
+            for (int i = 0; i < RL_C; ++i)
+                for (int t = 0; t < RL_TAPS; ++t) wt[((size_t)t * RL_C + i) * RL_C + o] = (*c17w)[((size_t)o * RL_C + i) * RL_TAPS + t];
+        if ((rc = rl_upload(e, wt, &e->c17_wt))) return rc;
+    }
+    // BatchNorm (inference): mean, 1 / sqrt(var + eps), weight, bias
+    for (int l = 0; l < 2; ++l) {
+        const std::string base = std::string("read_level_conv.convs.") + (l == 0 ? "2" : "5") + ".";
+        RL_NEED(mean, base + "running_mean", RL_C)
+        RL_NEED(var, base + "running_var", RL_C)
+        RL_NEED(w, base + "weight", RL_C)
+        RL_NEED(b, base + "bias", RL_C)
+        std::vector<float> invstd(RL_C);
+        for (int c = 0; c < RL_C; ++c) invstd[c] = 1.0f / sqrtf((*var)[c] + 1e-5f);
+        float **dst = l == 0 ? e->bn1 : e->bn2;
+        if ((rc = rl_upload(e, *mean, &dst[0])) || (rc = rl_upload(e, invstd, &dst[1])) || (rc = rl_upload(e, *w, &dst[2])) ||
+            (rc = rl_upload(e, *b, &dst[3])))
+            return rc;
+    }
+    for (int l = 0; l < 2; ++l) {
+        const int in = l == 0 ? RL_H : 2 * RL_H;
+        std::vector<float> w_ih((size_t)2 * RL_G4 * in), bias((size_t)2 * RL_G4), w3t((size_t)2 * RL_H * 3 * RL_H),
+            wo((size_t)2 * RL_H * RL_H);
+        for (int d = 0; d < 2; ++d) {
+            const std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
+            RL_NEED(wih, "lstm.weight_ih" + sfx, RL_G4 * in)
+            RL_NEED(whh, "lstm.weight_hh" + sfx, RL_G4 * RL_H)
+            RL_NEED(bih, "lstm.bias_ih" + sfx, RL_G4)
+            RL_NEED(bhh, "lstm.bias_hh" + sfx, RL_G4)
+            std::copy(wih->begin(), wih->end(), w_ih.begin() + (size_t)d * RL_G4 * in);
+            for (int r = 0; r < RL_G4; ++r) bias[(size_t)d * RL_G4 + r] = (*bih)[r] + (*bhh)[r];
+            for (int gate = 0; gate < 3; ++gate)
+                for (int jj = 0; jj < RL_H; ++jj)
+                    for (int k = 0; k < RL_H; ++k)
+                        w3t[((size_t)d * RL_H + k) * 3 * RL_H + gate * RL_H + jj] = (*whh)[((size_t)gate * RL_H + jj) * RL_H + k];
+            for (int jj = 0; jj < RL_H; ++jj)
+                for (int k = 0; k < RL_H; ++k) wo[((size_t)d * RL_H + jj) * RL_H + k] = (*whh)[((size_t)3 * RL_H + jj) * RL_H + k];
+        }
+        if ((rc = rl_upload(e, w_ih, &e->lstm[l].w_ih)) || (rc = rl_upload(e, bias, &e->lstm[l].bias)) ||
+            (rc = rl_upload(e, w3t, &e->lstm[l].w3t)) || (rc = rl_upload(e, wo, &e->lstm[l].wo)))
+            return rc;
+    }
+#undef RL_NEED
+    e->prepared = true;
+    return MDK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdk_rl_create(int device, int32_t lstm_size, int32_t cnn_size, int32_t use_dwells, int32_t num_classes,
+                  mdk_rl_engine **out) {
+    MDK_REQUIRE(out, MDK_ERR_ARG, "rl_create: out is NULL");
+    *out = nullptr;
+    MDK_REQUIRE(lstm_size == RL_H && cnn_size == RL_C, MDK_ERR_UNSUPPORTED, "rl_create: lstm_size = cnn_size = 128 only");
+    MDK_REQUIRE(num_classes == NCLS, MDK_ERR_UNSUPPORTED, "rl_create: 5 classes only");
+    MDK_CUDA(cudaSetDevice(device));
+    mdk_rl_engine *e = new (std::nothrow) mdk_rl_engine();
+    MDK_REQUIRE(e, MDK_ERR_NOMEM, "rl_create: out of host memory");
+    e->device = device;
+    e->use_dwells = use_dwells ? 1 : 0;
+    cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
+    *out = e;
+    return MDK_OK;
+}
+
+int mdk_rl_destroy(mdk_rl_engine *e) {
+    if (!e) return MDK_OK;
+    cudaSetDevice(e->device);
+    if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    for (void *p : e->allocs) cudaFree(p);
+    delete e;
+    cudaGetLastError();
+    return MDK_OK;
+}
+
+int mdk_rl_load(mdk_rl_engine *e, const char *name, const float *data, int64_t n) {
+    MDK_REQUIRE(e && name && (data || n == 0) && n >= 0, MDK_ERR_ARG, "rl_load: bad arguments");
+    MDK_REQUIRE(!e->prepared, MDK_ERR_STATE, "rl_load: the model has already run; create a new engine to change weights");
+    e->host[name] = std::vector<float>(data, data + n);
+    return MDK_OK;
+}
+
+int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P, int64_t D, int64_t F, float *probs_host) {
+    MDK_REQUIRE(e && x_host && probs_host, MDK_ERR_ARG, "rl_forward: NULL argument");
+    MDK_REQUIRE(B >= 1 && P >= 1 && D >= 1, MDK_ERR_ARG, "rl_forward: need B, P, D >= 1");
+    MDK_REQUIRE(F == (e->use_dwells ? 5 : 4) || (!e->use_dwells && F >= 4), MDK_ERR_ARG,
+                "rl_forward: feature vector length does not match the model (4, or 5 with dwells)");
+    MDK_REQUIRE(D <= 65535 && B <= 65535, MDK_ERR_ARG, "rl_forward: B, D <= 65535");
+    MDK_CUDA(cudaSetDevice(e->device));
+    int rc = rl_prepare(e);
+    if (rc) return rc;
+    cudaStream_t s = e->stream;
+    const int dgroup = 4;
+    const int n_groups = (int)((D + dgroup - 1) / dgroup);
+    const int64_t BP = B * P;
+    size_t off = 0;
+    auto take = [&off](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_x = take((size_t)BP * D * F), o_mask = take((size_t)B * D), o_y1 = take((size_t)B * D * P * RL_C * 4),
+                 o_part = take((size_t)B * n_groups * P * RL_C * 4), o_z = take((size_t)BP * RL_H * 4),
+                 o_gi = take((size_t)BP * 2 * RL_G4 * 4), o_h0 = take((size_t)BP * 2 * RL_H * 4),
+                 o_h1 = take((size_t)BP * 2 * RL_H * 4), o_probs = take((size_t)BP * NCLS * 4);
+    uint8_t *buf = nullptr;
+    MDK_CUDA(cudaMalloc(&buf, off));
+    struct Guard { uint8_t *p; ~Guard() { cudaFree(p); } } guard{buf};
+    int8_t *d_x = (int8_t *)(buf + o_x);
+    uint8_t *d_mask = buf + o_mask;
+    float *d_y1 = (float *)(buf + o_y1), *d_part = (float *)(buf + o_part), *d_z = (float *)(buf + o_z),
+          *d_gi = (float *)(buf + o_gi), *d_h0 = (float *)(buf + o_h0), *d_h1 = (float *)(buf + o_h1),
+          *d_probs = (float *)(buf + o_probs);
+    MDK_CUDA(cudaMemcpyAsync(d_x, x_host, (size_t)BP * D * F, cudaMemcpyHostToDevice, s));
+    rl_mask_kernel<<<(unsigned)(B * D), 256, 0, s>>>(d_x, P, (int)D, (int)F, d_mask);
+    RlConv1 c1{e->emb_base, e->emb_strand, e->c1_w, e->c1_b, e->bn1[0], e->bn1[1], e->bn1[2], e->bn1[3]};
+    rl_embed_conv1_kernel<<<dim3((unsigned)((P + 31) / 32), (unsigned)(B * D)), RL_C, 0, s>>>(d_x, d_mask, c1, P, (int)D, (int)F,
+                                                                                         e->use_dwells, d_y1);
+    MDK_CUDA(cudaFuncSetAttribute(rl_conv17_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_CONV_SMEM));
+    RlConv17 c17{e->c17_wt, e->c17_b, e->bn2[0], e->bn2[1], e->bn2[2], e->bn2[3]};
+    rl_conv17_pool_kernel<<<dim3((unsigned)((P + RL_PT - 1) / RL_PT), (unsigned)n_groups, (unsigned)B), 256, RL_CONV_SMEM, s>>>(
+        d_y1, d_mask, c17, P, (int)D, dgroup, d_part);
+    rl_pool_linear_kernel<<<dim3((unsigned)P, (unsigned)B), RL_H, 0, s>>>(d_part, d_mask, e->pool_w, e->pool_b, P, (int)D,
+                                                                          n_groups, d_z);
+    MDK_CUDA(cudaFuncSetAttribute(rl_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_LSTM_SMEM));
+    const float *layer_in = d_z;
+    float *layer_out[2] = {d_h0, d_h1};
+    for (int l = 0; l < 2; ++l) {
+        const int in = l == 0 ? RL_H : 2 * RL_H;
+        rl_gemm_kernel<<<dim3((unsigned)((BP + 127) / 128), 2 * RL_G4 / 128), 256, 0, s>>>(layer_in, e->lstm[l].w_ih, e->lstm[l].bias,
+                                                                                       d_gi, BP, in, 2 * RL_G4);
+        rl_lstm_kernel<<<dim3((unsigned)((B + RL_NB - 1) / RL_NB), 2), 512, RL_LSTM_SMEM, s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
+                                                                                            layer_out[l], B, P);
+        layer_in = layer_out[l];
+    }
+    MDK_CUDA(cudaGetLastError());
+    MDK_CUDA(launch_head(d_h1, e->lin_w, e->lin_b, B, P, 0, d_probs, nullptr, nullptr, s));
+    MDK_CUDA(cudaMemcpyAsync(probs_host, d_probs, (size_t)BP * NCLS * 4, cudaMemcpyDeviceToHost, s));
+    MDK_CUDA(cudaStreamSynchronize(s));
+    return MDK_OK;
+}
+
+}  // extern "C"
