@@ -318,9 +318,28 @@ __global__ void __launch_bounds__(512, 1) rl_lstm_kernel(const float *__restrict
     for (int q = 0; q < RL_NB / 4; ++q) c_state[q] = 0.f;
     __syncthreads();
     int cur = 0;
+    // the input pre-activations of this thread's windows are fetched one step ahead (the loads fly under the matvec)
+    float gnext[RL_NB / 4][4];
+    auto fetch = [&](int64_t t, float (&dst)[RL_NB / 4][4]) {
+#pragma unroll
+        for (int q = 0; q < RL_NB / 4; ++q) {
+            const int n = g + 4 * q;
+            const bool ok = n < nb;
+            const float *row = gi + (((b0 + (ok ? n : 0)) * P + t) * 2 + dir) * RL_G4;
+#pragma unroll
+            for (int gate = 0; gate < 4; ++gate) dst[q][gate] = ok ? __ldg(row + gate * RL_H + j) : 0.f;
+        }
+    };
+    fetch(dir ? (P - 1) : 0, gnext);
     for (int64_t step = 0; step < P; ++step) {
         const int64_t t = dir ? (P - 1 - step) : step;
         const float *hc = hs + cur * RL_NB * RL_H;
+        float gcur[RL_NB / 4][4];
+#pragma unroll
+        for (int q = 0; q < RL_NB / 4; ++q)
+#pragma unroll
+            for (int gate = 0; gate < 4; ++gate) gcur[q][gate] = gnext[q][gate];
+        if (step + 1 < P) fetch(dir ? (t - 1) : (t + 1), gnext);
         // partial of gate o over this thread's quarter of k
         float part[RL_NB];
 #pragma unroll
@@ -375,9 +394,7 @@ __global__ void __launch_bounds__(512, 1) rl_lstm_kernel(const float *__restrict
         for (int q = 0; q < RL_NB / 4; ++q) {
             const int n = g + 4 * q;
             const bool ok = n < nb;
-            const float *row = gi + (((b0 + (ok ? n : 0)) * P + t) * 2 + dir) * RL_G4;
-            const float gi_i = ok ? row[j] : 0.f, gi_f = ok ? row[RL_H + j] : 0.f, gi_g = ok ? row[2 * RL_H + j] : 0.f,
-                        gi_o = ok ? row[3 * RL_H + j] : 0.f;
+            const float gi_i = gcur[q][0], gi_f = gcur[q][1], gi_g = gcur[q][2], gi_o = gcur[q][3];
             // quarters in k order (0..3) whoever computed them: this thread's own is quarter g
             float po = 0.f;
 #pragma unroll
