@@ -22,7 +22,8 @@
 //   rl_gemm_kernel        LSTM input projections  gi = X W_ih^T + b_ih + b_hh   (both directions in one launch)
 //   rl_lstm_kernel        the LSTM recurrence: one CTA = 8 windows of one direction, 512 threads (gate g, unit j);
 //                         W_hh^T of gates i, f, g resident in shared memory (192 KiB), gate o's rows distributed over the
-//                         threads' registers (32 weights each); c and h stay on chip for all P steps
+//                         threads' registers (32 weights each); c and h stay on chip for all P steps.  4 windows per CTA
+//                         while that still fits one wave of CTAs (the step time is latency, not FLOPs)
 //   head_kernel (misc.cu) Linear(2H -> 5) + softmax, shared with the counts models
 // All of it is CUDA-core fp32: parity first (tests/test_read_level.py against the reference's own class); the convolution
 // is 99 % of the FLOPs (557 kFLOP per read and position) and belongs on tcgen05 next.
@@ -289,9 +290,9 @@ __global__ void __launch_bounds__(256) rl_gemm_kernel(const float *__restrict__ 
 // gi  [B*P][2 dirs][4H]  (torch gate order i, f, g, o; b_ih + b_hh folded in)
 // out [B*P][2H]          (columns dir*H + j)
 // w3t [dir][H k][3H]     W_hh^T of gates i, f, g;   wo [dir][H j][H k]  W_hh rows of gate o
-constexpr int RL_NB = 8;
-constexpr int RL_LSTM_SMEM = (RL_H * 3 * RL_H + 2 * RL_NB * RL_H + 6 * RL_NB * RL_H) * 4;     // 224 KiB
+constexpr int rl_lstm_smem(int nb) { return (RL_H * 3 * RL_H + 2 * nb * RL_H + 6 * nb * RL_H) * 4; }     // 224 KiB at 8 windows
 
+template <int RL_NB>
 __global__ void __launch_bounds__(512, 1) rl_lstm_kernel(const float *__restrict__ gi, const float *__restrict__ w3t,
                                                          const float *__restrict__ wo, float *__restrict__ out, int64_t B,
                                                          int64_t P) {
@@ -612,15 +613,21 @@ int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P,
         d_y1, d_mask, c17, P, (int)D, dgroup, d_part);
     rl_pool_linear_kernel<<<dim3((unsigned)P, (unsigned)B), RL_H, 0, s>>>(d_part, d_mask, e->pool_w, e->pool_b, P, (int)D,
                                                                           n_groups, d_z);
-    MDK_CUDA(cudaFuncSetAttribute(rl_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_LSTM_SMEM));
+    const bool small = (B + 3) / 4 * 2 <= 296;             // 4 windows per CTA while two CTAs per SM-pair are not exceeded
+    MDK_CUDA(cudaFuncSetAttribute(rl_lstm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_lstm_smem(4)));
+    MDK_CUDA(cudaFuncSetAttribute(rl_lstm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_lstm_smem(8)));
     const float *layer_in = d_z;
     float *layer_out[2] = {d_h0, d_h1};
     for (int l = 0; l < 2; ++l) {
         const int in = l == 0 ? RL_H : 2 * RL_H;
         rl_gemm_kernel<<<dim3((unsigned)((BP + 127) / 128), 2 * RL_G4 / 128), 256, 0, s>>>(layer_in, e->lstm[l].w_ih, e->lstm[l].bias,
                                                                                        d_gi, BP, in, 2 * RL_G4);
-        rl_lstm_kernel<<<dim3((unsigned)((B + RL_NB - 1) / RL_NB), 2), 512, RL_LSTM_SMEM, s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
-                                                                                            layer_out[l], B, P);
+        if (small)
+            rl_lstm_kernel<4><<<dim3((unsigned)((B + 3) / 4), 2), 512, rl_lstm_smem(4), s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
+                                                                                          layer_out[l], B, P);
+        else
+            rl_lstm_kernel<8><<<dim3((unsigned)((B + 7) / 8), 2), 512, rl_lstm_smem(8), s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
+                                                                                          layer_out[l], B, P);
         layer_in = layer_out[l];
     }
     MDK_CUDA(cudaGetLastError());

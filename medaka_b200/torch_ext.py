@@ -23,14 +23,25 @@ class Batch:
 
     @classmethod
     def collate(cls, samples, counts_matrix=False, out=None):
-        """Construct a batch from a list of `Sample` objects with 2-D (counts-matrix) features.
+        """Construct a batch from a list of `Sample` objects (2-D counts-matrix or 3-D read-level features).
 
         :param out: optional float32 array [len(samples), T, F] to fill (e.g. pinned memory).
         """
         first = samples[0].features
         if first.ndim == 3:
-            raise NotImplementedError(
-                "read-level (3-D) features belong to the rl_ models, outside this engine's hot path")
+            # read-level features [positions, reads, features]: padded with empty reads to the deepest sample of the
+            # batch, uint8 like the reference (torch_ext.py:127-141)
+            npos, _, nfeats = first.shape
+            depths = [s.features.shape[1] for s in samples]
+            padded = np.zeros((len(samples), npos, max(depths), nfeats), dtype=np.uint8)
+            for i, s in enumerate(samples):
+                if s.features.shape[0] != npos or s.features.shape[2] != nfeats:
+                    raise RuntimeError("read-level samples of one batch must share positions and feature length")
+                padded[i, :, :depths[i], :] = s.features
+            fields = {"read_level_features": torch.from_numpy(padded)}
+            if samples[0].labels is not None:
+                fields["labels"] = torch.stack([torch.from_numpy(np.asarray(s.labels)) for s in samples])
+            return cls(**fields)
         if first.ndim != 2:
             raise ValueError(
                 f"Unknown feature dimension {first.ndim}. Expect 3 for"

@@ -79,3 +79,56 @@ def test_predict_on_batch_interface_and_encoder_check():
     out = m.predict_on_batch(B)
     assert tuple(out.shape) == (2, 80, 5) and abs(float(out.sum(-1).mean()) - 1.0) < 1e-5
     m.close()
+
+
+def test_collate_pads_read_level_samples():
+    """Batch.collate on 3-D features (medaka/torch_ext.py:127-141): zero-padded to the deepest sample, uint8."""
+    from medaka_b200 import common, torch_ext
+    rs = np.random.RandomState(0)
+    feats = [rs.randint(0, 6, size=(50, d, 4)).astype(np.int8) for d in (3, 7, 5)]
+    samples = [common.Sample(ref_name="c", features=f, labels=None, ref_seq=None, positions=None, label_probs=None,
+                             depth=None) for f in feats]
+    b = torch_ext.Batch.collate(samples)
+    x = b.read_level_features.numpy()
+    assert b.counts_matrix is None and x.shape == (3, 50, 7, 4) and x.dtype == np.uint8
+    for i, f in enumerate(feats):
+        assert np.array_equal(x[i, :, :f.shape[1]], f.astype(np.uint8)) and not x[i, :, f.shape[1]:].any()
+    assert b.features is b.read_level_features
+
+
+@pytest.mark.gpu
+def test_read_level_prediction_end_to_end(tmp_path):
+    """BAM file -> native reader -> mdk_read_matrix -> windows -> Batch.collate -> LatentSpaceLSTM engine -> store, against
+    the oracles driven over the same reads."""
+    from medaka_b200 import common, datastore, features, prediction, read_level
+    from oracle import read_matrix_oracle, synth
+    from tests import bamutil
+    rs = np.random.RandomState(3)
+    recs = synth.synth_reads(90, 2600, seed=21, mean_len=700)
+    recs.sort(key=lambda r: r["pos"])
+    for i, r in enumerate(recs):
+        r["query_name"], r["ref"], r["tags"] = "q%d" % i, 0, {}
+        r["qual"] = rs.randint(1, 50, len(r["seq"])).tolist()
+    path = str(tmp_path / "reads.bam")
+    bamutil.write_bam(path, [("ctg", 2600)], recs)
+    sd = rl_oracle.synth_rl_state_dict(9)
+    model = read_level.LatentSpaceLSTM()
+    model.load_state_dict(sd)
+    enc = features.ReadAlignmentFeatureEncoder(include_dwells=False)
+    region = common.Region("ctg", 0, 2600)
+    out = str(tmp_path / "probs.npzstore")
+    prediction.predict_regions(out, path, [region], model, enc, chunk_len=500, chunk_ovlp=100, batch_size=3, bam_chunk=100000)
+    mat, pos, _, _ = read_matrix_oracle.read_alignment(recs, 0, 2600)
+    oracle_model = rl_oracle.build(sd)
+    n = 0
+    with datastore.DataStore(out, "r") as ds:
+        for name in sorted(ds.sample_registry):
+            s = ds.load_sample(name)
+            a = int(np.flatnonzero((pos["major"] == s.positions["major"][0]) & (pos["minor"] == s.positions["minor"][0]))[0])
+            b = a + len(s.positions)
+            assert np.array_equal(pos[a:b], s.positions)
+            want = rl_oracle.predict(oracle_model, mat[a:b][None].astype(np.int8))[0]
+            assert np.abs(s.label_probs - want).max() < TOL
+            n += 1
+    assert n >= 5
+    model.close()
