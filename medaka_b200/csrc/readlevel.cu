@@ -27,11 +27,13 @@
 //   head_kernel (misc.cu) Linear(2H -> 5) + softmax, shared with the counts models
 // All of it is CUDA-core fp32: parity first (tests/test_read_level.py against the reference's own class); the convolution
 // is 99 % of the FLOPs (557 kFLOP per read and position) and belongs on tcgen05 next.
+#include <cstdlib>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace mdk {
 
@@ -203,6 +205,185 @@ __global__ void __launch_bounds__(256) rl_conv17_pool_kernel(const float *__rest
         *reinterpret_cast<float4 *>(dst) = make_float4(pooled[i][0], pooled[i][1], pooled[i][2], pooled[i][3]);
         *reinterpret_cast<float4 *>(dst + 4) = make_float4(pooled[i][4], pooled[i][5], pooled[i][6], pooled[i][7]);
     }
+}
+
+// ---------------------------------------------------------------------------------------------- conv k=17 on tcgen05
+// The same convolution as an implicit GEMM on the tensor cores:  D[co][p] = sum_t sum_ci W[co][ci][t] . y1[p + t - 8][ci].
+//   A = one tap's weights [128 co][128 ci]  (K-major fp16 hi | lo planes, pre-tiled in HBM, streamed through a two-stage
+//       shared-memory ring with bulk copies; SS mode: 17 x 64 KiB of weights fit neither tensor memory nor shared memory)
+//   B = ONE staged activation tile [144 positions][128 ci] (hi | lo) serves all 17 taps: tap t is the same buffer with the
+//       descriptor's start address moved down t rows (K-major SWIZZLE_NONE: a row is 16 bytes inside its k-group block)
+//   D = 128 columns of tensor memory (lane = output channel, column = position), three fp16 products per contraction like
+//       the GRU kernels (fp32-faithful)
+// A CTA owns (window b, 128 positions, a group of reads): per read it builds the activation tile in shared memory straight
+// from the int8 features (embedding + k = 1 convolution + ReLU + BN1, never written to HBM), runs 17 x 24 MMAs, drains the
+// accumulators through ReLU + BN2 and adds them to per-thread sums (one output channel x 128 positions per thread), and
+// writes the group's sum once.  Warp 0: weight producer; warp 1: MMA issuer, TMEM owner; warps 4-7: epilogue; all eight
+// warps build the activation tile.
+constexpr int CT_NPOS = 128;
+constexpr int CT_ROWS = CT_NPOS + 2 * RL_PAD;            // 144 staged positions
+constexpr int CT_BPLANE = (RL_C / 8) * CT_ROWS * 16;     // 36 864 B
+constexpr int CT_WPLANE = (RL_C / 8) * RL_C * 16;        // 32 768 B
+constexpr int CT_WSTAGE = 2 * CT_WPLANE;                 // hi + lo of one tap
+constexpr int CT_STAGES = 2;
+constexpr int CT_OFF_W = 2 * CT_BPLANE;
+constexpr int CT_OFF_IN = CT_OFF_W + CT_STAGES * CT_WSTAGE;
+constexpr int CT_OFF_BAR = CT_OFF_IN + CT_ROWS * 8 * 4;
+constexpr int CT_SMEM = CT_OFF_BAR + 128;
+
+__global__ void __launch_bounds__(256, 1) rl_conv17_tc_kernel(const int8_t *__restrict__ x, const uint8_t *__restrict__ mask,
+                                                              RlConv1 c1, RlConv17 c17, const uint8_t *__restrict__ w_tc,
+                                                              int64_t P, int D, int F, int use_dwells, int dgroup,
+                                                              float *__restrict__ partial) {
+    extern __shared__ __align__(128) uint8_t smem_ct[];
+    uint8_t *sb = smem_ct;
+    uint8_t *sw = smem_ct + CT_OFF_W;
+    float *sin = reinterpret_cast<float *>(smem_ct + CT_OFF_IN);       // [144][8]
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_ct + CT_OFF_BAR);
+    uint64_t *empty = full + CT_STAGES;
+    uint64_t *acc_full = empty + CT_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t b = blockIdx.z;
+    const int g = blockIdx.y;
+    const int64_t p0 = (int64_t)blockIdx.x * CT_NPOS;
+    const int nin = RL_EMB + 1 + (use_dwells ? 1 : 0);
+
+    if (tid == 0) {
+        for (int i = 0; i < CT_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // builder constants: this thread's k = 1 convolution channel
+    const int bc = tid & 127;
+    float w1[RL_EMB + 2];
+    for (int i = 0; i < nin; ++i) w1[i] = c1.w[bc * nin + i];
+    const float b1 = c1.b[bc], m1 = c1.bn_mean[bc], s1 = c1.bn_invstd[bc], g1 = c1.bn_w[bc], o1 = c1.bn_b[bc];
+    // epilogue constants: this thread's output channel (TMEM lane)
+    const int co = (warp & 3) * 32 + lane;
+    const float b2 = c17.b[co], m2 = c17.bn_mean[co], s2 = c17.bn_invstd[co], g2 = c17.bn_w[co], o2 = c17.bn_b[co];
+    float pooled[CT_NPOS];
+    if (warp >= 4) {
+#pragma unroll
+        for (int i = 0; i < CT_NPOS; ++i) pooled[i] = 0.f;
+    }
+    const uint32_t idesc = make_idesc_f16(128, CT_NPOS);
+    const int d0 = g * dgroup, d1 = min(D, d0 + dgroup);
+    uint32_t it = 0;             // weight stages handed over so far (producer and issuer count alike)
+    uint32_t n_done = 0;         // reads processed
+    for (int d = d0; d < d1; ++d) {
+        const int64_t bd = b * D + d;
+        if (!mask[bd]) continue;                                   // uniform over the CTA
+        // ---- build the activation tile (the previous read's MMAs are complete: everybody waited on acc_full below)
+        if (tid < CT_ROWS) {
+            const int64_t p = p0 - RL_PAD + tid;
+            float *row = sin + tid * 8;
+            if (p >= 0 && p < P) {
+                const int8_t *v = x + ((b * P + p) * D + d) * F;
+                const int base = min(max((int)v[0], 0), 5), strand = min(max((int)v[2] + 1, 0), 2);
+                for (int i = 0; i < RL_EMB; ++i) row[i] = c1.emb_base[base * RL_EMB + i] + c1.emb_strand[strand * RL_EMB + i];
+                row[RL_EMB] = (float)v[1] / 25.0f - 1.0f;
+                row[RL_EMB + 1] = use_dwells ? (float)v[4] : 0.f;
+            } else {
+                row[0] = __int_as_float(0x7fc00000);              // marker: outside the window -> zero row (conv padding)
+            }
+        }
+        __syncthreads();
+        for (int r = tid >> 7; r < CT_ROWS; r += 2) {
+            const float *row = sin + r * 8;
+            float y = 0.f;
+            if (!(row[0] != row[0])) {
+                float acc = b1;
+                for (int k = 0; k < nin; ++k) acc = fmaf(w1[k], row[k], acc);
+                acc = fmaxf(acc, 0.f);
+                y = (acc - m1) * s1 * g1 + o1;
+            }
+            __half hi, lo;
+            split_f16(y, hi, lo);
+            const int off = (bc >> 3) * (CT_ROWS * 16) + r * 16 + (bc & 7) * 2;
+            *reinterpret_cast<__half *>(sb + off) = hi;
+            *reinterpret_cast<__half *>(sb + CT_BPLANE + off) = lo;
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        __syncthreads();
+        tc_fence_after_sync();
+        // ---- 17 taps
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int t = 0; t < RL_TAPS; ++t, ++it) {
+                    const uint32_t st = it % CT_STAGES;
+                    mbar_wait(&empty[st], ((it / CT_STAGES) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&full[st], CT_WSTAGE);
+                    const uint8_t *src = w_tc + (size_t)t * CT_WSTAGE;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) bulk_g2s(sw + st * CT_WSTAGE + c * (CT_WSTAGE / 4), src + c * (CT_WSTAGE / 4), CT_WSTAGE / 4, &full[st]);
+                }
+            }
+        } else if (warp == 1) {
+            for (int t = 0; t < RL_TAPS; ++t, ++it) {
+                const uint32_t st = it % CT_STAGES;
+                mbar_wait(&full[st], (it / CT_STAGES) & 1);
+                tc_fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t a0 = smem_u32(sw + st * CT_WSTAGE), bb0 = smem_u32(sb) + (uint32_t)t * 16u;
+#pragma unroll
+                    for (int prod = 0; prod < 3; ++prod) {
+                        const int pa = prod == 2, pb = prod == 1;          // W part, activation part
+#pragma unroll
+                        for (int ks = 0; ks < RL_C / 16; ++ks) {
+                            const uint64_t ad = make_smem_desc(a0 + pa * CT_WPLANE + ks * 2 * (RL_C * 16), RL_C * 16, 128);
+                            const uint64_t bdsc = make_smem_desc(bb0 + pb * CT_BPLANE + ks * 2 * (CT_ROWS * 16), CT_ROWS * 16, 128);
+                            umma_f16(tmem_base, ad, bdsc, idesc, (t | prod | ks) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty[st]);
+                    if (t == RL_TAPS - 1) umma_commit(acc_full);
+                }
+                __syncwarp();
+            }
+        } else {
+            it += RL_TAPS;
+        }
+        if (warp == 0 && lane != 0) it += RL_TAPS;
+        // ---- everybody waits for the read's accumulators (the activation tile may then be rebuilt)
+        mbar_wait(acc_full, n_done & 1);
+        tc_fence_after_sync();
+        if (warp >= 4) {
+            const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+            for (int c32 = 0; c32 < CT_NPOS; c32 += 32) {
+                uint32_t v[32];
+                tmem_ld_x32(t_lane + c32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float a = fmaxf(__uint_as_float(v[i]) + b2, 0.f);
+                    pooled[c32 + i] += (a - m2) * s2 * g2 + o2;
+                }
+            }
+        }
+        tc_fence_before_sync();
+        __syncthreads();                                           // accumulators drained, tile free
+        tc_fence_after_sync();
+        ++n_done;
+    }
+    if (warp >= 4) {
+        const int n_groups = gridDim.y;
+        float *dst = partial + ((b * n_groups + g) * P + p0) * RL_C + co;
+#pragma unroll
+        for (int i = 0; i < CT_NPOS; ++i)
+            if (p0 + i < P) dst[(int64_t)i * RL_C] = pooled[i];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 128); }
 }
 
 // ---------------------------------------------------------------------------------------------- mean + Linear(C -> H)
@@ -439,6 +620,8 @@ struct mdk_rl_engine {
     float *emb_base = nullptr, *emb_strand = nullptr;
     float *c1_w = nullptr, *c1_b = nullptr, *bn1[4] = {nullptr, nullptr, nullptr, nullptr};
     float *c17_wt = nullptr, *c17_b = nullptr, *bn2[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint8_t *c17_tc = nullptr;     // [17 taps][hi | lo][k-group 16][co 128][8 halfs]: the tensor-core kernel's A operand tiles
+    int conv_tc = 1;               // 1: k = 17 convolution on tcgen05 (default), 0: fp32 CUDA cores
     float *pool_w = nullptr, *pool_b = nullptr;
     RlLstmLayer lstm[2];
     float *lin_w = nullptr, *lin_b = nullptr;
@@ -494,6 +677,23 @@ int rl_prepare(mdk_rl_engine *e) {
             for (int i = 0; i < RL_C; ++i)
                 for (int t = 0; t < RL_TAPS; ++t) wt[((size_t)t * RL_C + i) * RL_C + o] = (*c17w)[((size_t)o * RL_C + i) * RL_TAPS + t];
         if ((rc = rl_upload(e, wt, &e->c17_wt))) return rc;
+        // the same weights as K-major fp16 hi / lo operand tiles, one 64 KiB block per tap
+        std::vector<__half> tc((size_t)RL_TAPS * 2 * RL_C * RL_C);
+        for (int t = 0; t < RL_TAPS; ++t)
+            for (int o = 0; o < RL_C; ++o)
+                for (int i = 0; i < RL_C; ++i) {
+                    const float v = (*c17w)[((size_t)o * RL_C + i) * RL_TAPS + t];
+                    const __half hi = __float2half_rn(v);
+                    const __half lo = __float2half_rn(v - __half2float(hi));
+                    const size_t off = (size_t)(i / 8) * (RL_C * 8) + (size_t)o * 8 + (i % 8);
+                    tc[((size_t)t * 2 + 0) * RL_C * RL_C + off] = hi;
+                    tc[((size_t)t * 2 + 1) * RL_C * RL_C + off] = lo;
+                }
+        void *p = nullptr;
+        MDK_CUDA(cudaMalloc(&p, tc.size() * sizeof(__half)));
+        e->allocs.push_back(p);
+        MDK_CUDA(cudaMemcpy(p, tc.data(), tc.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        e->c17_tc = static_cast<uint8_t *>(p);
     }
     // BatchNorm (inference): mean, 1 / sqrt(var + eps), weight, bias
     for (int l = 0; l < 2; ++l) {
@@ -552,6 +752,10 @@ int mdk_rl_create(int device, int32_t lstm_size, int32_t cnn_size, int32_t use_d
     MDK_REQUIRE(e, MDK_ERR_NOMEM, "rl_create: out of host memory");
     e->device = device;
     e->use_dwells = use_dwells ? 1 : 0;
+    {
+        const char *v = getenv("MDK_RL_CONV");      // "fp32": CUDA-core convolution (validation)
+        if (v && v[0] == 'f') e->conv_tc = 0;
+    }
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
     *out = e;
@@ -575,6 +779,12 @@ int mdk_rl_load(mdk_rl_engine *e, const char *name, const float *data, int64_t n
     return MDK_OK;
 }
 
+int mdk_rl_set_conv(mdk_rl_engine *e, int tensor_cores) {
+    MDK_REQUIRE(e, MDK_ERR_ARG, "rl_set_conv: engine is NULL");
+    e->conv_tc = tensor_cores ? 1 : 0;
+    return MDK_OK;
+}
+
 int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P, int64_t D, int64_t F, float *probs_host) {
     MDK_REQUIRE(e && x_host && probs_host, MDK_ERR_ARG, "rl_forward: NULL argument");
     MDK_REQUIRE(B >= 1 && P >= 1 && D >= 1, MDK_ERR_ARG, "rl_forward: need B, P, D >= 1");
@@ -590,7 +800,7 @@ int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P,
     const int64_t BP = B * P;
     size_t off = 0;
     auto take = [&off](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    const size_t o_x = take((size_t)BP * D * F), o_mask = take((size_t)B * D), o_y1 = take((size_t)B * D * P * RL_C * 4),
+    const size_t o_x = take((size_t)BP * D * F), o_mask = take((size_t)B * D), o_y1 = take(e->conv_tc ? 256 : (size_t)B * D * P * RL_C * 4),
                  o_part = take((size_t)B * n_groups * P * RL_C * 4), o_z = take((size_t)BP * RL_H * 4),
                  o_gi = take((size_t)BP * 2 * RL_G4 * 4), o_h0 = take((size_t)BP * 2 * RL_H * 4),
                  o_h1 = take((size_t)BP * 2 * RL_H * 4), o_probs = take((size_t)BP * NCLS * 4);
@@ -605,12 +815,18 @@ int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P,
     MDK_CUDA(cudaMemcpyAsync(d_x, x_host, (size_t)BP * D * F, cudaMemcpyHostToDevice, s));
     rl_mask_kernel<<<(unsigned)(B * D), 256, 0, s>>>(d_x, P, (int)D, (int)F, d_mask);
     RlConv1 c1{e->emb_base, e->emb_strand, e->c1_w, e->c1_b, e->bn1[0], e->bn1[1], e->bn1[2], e->bn1[3]};
-    rl_embed_conv1_kernel<<<dim3((unsigned)((P + 31) / 32), (unsigned)(B * D)), RL_C, 0, s>>>(d_x, d_mask, c1, P, (int)D, (int)F,
-                                                                                         e->use_dwells, d_y1);
-    MDK_CUDA(cudaFuncSetAttribute(rl_conv17_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_CONV_SMEM));
     RlConv17 c17{e->c17_wt, e->c17_b, e->bn2[0], e->bn2[1], e->bn2[2], e->bn2[3]};
-    rl_conv17_pool_kernel<<<dim3((unsigned)((P + RL_PT - 1) / RL_PT), (unsigned)n_groups, (unsigned)B), 256, RL_CONV_SMEM, s>>>(
-        d_y1, d_mask, c17, P, (int)D, dgroup, d_part);
+    if (e->conv_tc) {
+        MDK_CUDA(cudaFuncSetAttribute(rl_conv17_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM));
+        rl_conv17_tc_kernel<<<dim3((unsigned)((P + CT_NPOS - 1) / CT_NPOS), (unsigned)n_groups, (unsigned)B), 256, CT_SMEM, s>>>(
+            d_x, d_mask, c1, c17, e->c17_tc, P, (int)D, (int)F, e->use_dwells, dgroup, d_part);
+    } else {
+        rl_embed_conv1_kernel<<<dim3((unsigned)((P + 31) / 32), (unsigned)(B * D)), RL_C, 0, s>>>(d_x, d_mask, c1, P, (int)D, (int)F,
+                                                                                             e->use_dwells, d_y1);
+        MDK_CUDA(cudaFuncSetAttribute(rl_conv17_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_CONV_SMEM));
+        rl_conv17_pool_kernel<<<dim3((unsigned)((P + RL_PT - 1) / RL_PT), (unsigned)n_groups, (unsigned)B), 256, RL_CONV_SMEM, s>>>(
+            d_y1, d_mask, c17, P, (int)D, dgroup, d_part);
+    }
     rl_pool_linear_kernel<<<dim3((unsigned)P, (unsigned)B), RL_H, 0, s>>>(d_part, d_mask, e->pool_w, e->pool_b, P, (int)D,
                                                                           n_groups, d_z);
     const bool small = (B + 3) / 4 * 2 <= 296;             // 4 windows per CTA while two CTAs per SM-pair are not exceeded

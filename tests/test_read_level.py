@@ -37,20 +37,24 @@ def _check(got, want):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("conv", ["tc", "fp32"])
 @pytest.mark.parametrize("name", ["small", "deep", "dwells", "hot"])
-def test_device_matches_reference_class(name):
+def test_device_matches_reference_class(name, conv):
+    """Both implementations of the k = 17 convolution: tcgen05 implicit GEMM (default) and fp32 CUDA cores."""
     from medaka_b200 import read_level
     g = np.load(GOLD)
     sd, x, dw, want = _case(g, name)
     m = read_level.LatentSpaceLSTM(use_dwells=dw)
     m.load_state_dict(sd)
+    m.set_conv(conv == "tc")
     _check(m.forward_arrays(x), want)
     m.close()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,P,D", [(1, 17, 1), (9, 65, 5), (3, 1000, 30), (17, 200, 3)])
-def test_device_matches_oracle_ragged_shapes(B, P, D):
+@pytest.mark.parametrize("conv", ["tc", "fp32"])
+@pytest.mark.parametrize("B,P,D", [(1, 17, 1), (9, 65, 5), (3, 1000, 30), (17, 200, 3), (2, 129, 9)])
+def test_device_matches_oracle_ragged_shapes(B, P, D, conv):
     """Position counts off the 64-position tile, windows off the 8-window LSTM group, single reads, windows split over
     several device calls."""
     from medaka_b200 import read_level
@@ -60,6 +64,7 @@ def test_device_matches_oracle_ragged_shapes(B, P, D):
     m = read_level.LatentSpaceLSTM()
     m.load_state_dict(sd)
     m.max_cells = 40000                      # forces several device calls for the larger shapes
+    m.set_conv(conv == "tc")
     _check(m.forward_arrays(x), want)
     m.close()
 

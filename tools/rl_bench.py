@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--windows", type=int, default=16)
     ap.add_argument("--positions", type=int, default=1000)
     ap.add_argument("--reads", type=int, default=50)
-    ap.add_argument("--cpu-windows", type=int, default=2)
+    ap.add_argument("--cpu-windows", type=int, default=2, help="0 = skip the CPU arm")
     args = ap.parse_args()
     from medaka_b200 import read_level
     from oracle import rl_oracle
@@ -29,17 +29,27 @@ def main():
     m = read_level.LatentSpaceLSTM()
     m.load_state_dict(sd)
     m.forward_arrays(x[:2])
-    ts = []
-    for _ in range(3):
-        t0 = time.perf_counter()
-        probs = m.forward_arrays(x)
-        ts.append(time.perf_counter() - t0)
-    t = min(ts)
+    def best():
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            out = m.forward_arrays(x)
+            ts.append(time.perf_counter() - t0)
+        return min(ts), out
+    m.set_conv(False)
+    t_fp32, probs_fp32 = best()
+    m.set_conv(True)
+    m.forward_arrays(x[:2])
+    t, probs = best()
     cells = args.windows * args.positions * args.reads
     flop_conv = cells * 2.0 * 17 * 128 * 128
     res = {"windows": args.windows, "positions": args.positions, "reads": args.reads, "gpu_call_ms": t * 1e3,
            "positions_per_s": args.windows * args.positions / t, "read_cells_per_s": cells / t,
-           "conv17_TFLOPs_fp32_algorithmic": flop_conv / t / 1e12}
+           "conv17_TFLOPs_algorithmic_whole_call": flop_conv / t / 1e12, "gpu_call_ms_fp32_conv": t_fp32 * 1e3,
+           "max_abs_prob_diff_tc_vs_fp32_conv": float(np.abs(probs - probs_fp32).max())}
+    if args.cpu_windows <= 0:
+        print(json.dumps(res))
+        return
     import torch
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)
     threads = min(threads, 16)
