@@ -387,27 +387,40 @@ __global__ void __launch_bounds__(256, 1) rl_conv17_tc_kernel(const int8_t *__re
 }
 
 // ---------------------------------------------------------------------------------------------- mean + Linear(C -> H)
+constexpr int RL_PLT = 16;        // positions per CTA of the pooling kernel
 __global__ void __launch_bounds__(RL_H) rl_pool_linear_kernel(const float *__restrict__ partial, const uint8_t *__restrict__ mask,
-                                                              const float *__restrict__ w, const float *__restrict__ bias,
+                                                              const float *__restrict__ w_t, const float *__restrict__ bias,
                                                               int64_t P, int D, int n_groups, float *__restrict__ out) {
-    // grid: (P, B); thread = output unit.  w [H][C]
-    const int64_t b = blockIdx.y, p = blockIdx.x;
-    __shared__ float v[RL_C];
+    // grid: (position tiles of 16, B); thread = channel while summing, output unit afterwards.  w_t [C k][H] (transposed)
+    const int64_t b = blockIdx.y, p0 = (int64_t)blockIdx.x * RL_PLT;
+    __shared__ float v[RL_PLT][RL_C];
     __shared__ int n_reads;
     if (threadIdx.x == 0) {
         int n = 0;
         for (int d = 0; d < D; ++d) n += mask[b * D + d];
         n_reads = n;
     }
-    float s = 0.f;
-    for (int g = 0; g < n_groups; ++g) s += partial[((b * n_groups + g) * P + p) * RL_C + threadIdx.x];
     __syncthreads();
-    v[threadIdx.x] = s / (float)n_reads;             // 0 / 0 = nan when a window has no reads, like the reference
+    for (int i = 0; i < RL_PLT; ++i) {
+        const int64_t p = p0 + i;
+        float s = 0.f;
+        if (p < P)
+            for (int g = 0; g < n_groups; ++g) s += partial[((b * n_groups + g) * P + p) * RL_C + threadIdx.x];
+        v[i][threadIdx.x] = s / (float)n_reads;            // 0 / 0 = nan when a window has no reads, like the reference
+    }
     __syncthreads();
     const int h = threadIdx.x;
-    float acc = bias[h];
-    for (int k = 0; k < RL_C; ++k) acc = fmaf(w[h * RL_C + k], v[k], acc);
-    out[(b * P + p) * RL_H + h] = acc;
+    float acc[RL_PLT];
+#pragma unroll
+    for (int i = 0; i < RL_PLT; ++i) acc[i] = bias[h];
+    for (int k = 0; k < RL_C; ++k) {
+        const float w = w_t[k * RL_H + h];
+#pragma unroll
+        for (int i = 0; i < RL_PLT; ++i) acc[i] = fmaf(w, v[i][k], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < RL_PLT; ++i)
+        if (p0 + i < P) out[(b * P + p0 + i) * RL_H + h] = acc[i];
 }
 
 // ---------------------------------------------------------------------------------------------- generic fp32 GEMM
@@ -667,9 +680,15 @@ int rl_prepare(mdk_rl_engine *e) {
     RL_NEED(lw, "linear.weight", NCLS * 2 * RL_H)
     RL_NEED(lb, "linear.bias", NCLS)
     if ((rc = rl_upload(e, *eb, &e->emb_base)) || (rc = rl_upload(e, *es, &e->emb_strand)) || (rc = rl_upload(e, *c1w, &e->c1_w)) ||
-        (rc = rl_upload(e, *c1b, &e->c1_b)) || (rc = rl_upload(e, *c17b, &e->c17_b)) || (rc = rl_upload(e, *pw, &e->pool_w)) ||
+        (rc = rl_upload(e, *c1b, &e->c1_b)) || (rc = rl_upload(e, *c17b, &e->c17_b)) ||
         (rc = rl_upload(e, *pb, &e->pool_b)) || (rc = rl_upload(e, *lw, &e->lin_w)) || (rc = rl_upload(e, *lb, &e->lin_b)))
         return rc;
+    {   // Linear(C -> H) weights transposed to [k][h]: coalesced across the output units
+        std::vector<float> wt((size_t)RL_C * RL_H);
+        for (int h = 0; h < RL_H; ++h)
+            for (int k = 0; k < RL_C; ++k) wt[(size_t)k * RL_H + h] = (*pw)[(size_t)h * RL_C + k];
+        if ((rc = rl_upload(e, wt, &e->pool_w))) return rc;
+    }
     // conv k = 17 weights: torch [out][in][tap] -> [tap][in][out]
     {
         std::vector<float> wt((size_t)RL_TAPS * RL_C * RL_C);
@@ -827,7 +846,7 @@ int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P,
         rl_conv17_pool_kernel<<<dim3((unsigned)((P + RL_PT - 1) / RL_PT), (unsigned)n_groups, (unsigned)B), 256, RL_CONV_SMEM, s>>>(
             d_y1, d_mask, c17, P, (int)D, dgroup, d_part);
     }
-    rl_pool_linear_kernel<<<dim3((unsigned)P, (unsigned)B), RL_H, 0, s>>>(d_part, d_mask, e->pool_w, e->pool_b, P, (int)D,
+    rl_pool_linear_kernel<<<dim3((unsigned)((P + RL_PLT - 1) / RL_PLT), (unsigned)B), RL_H, 0, s>>>(d_part, d_mask, e->pool_w, e->pool_b, P, (int)D,
                                                                           n_groups, d_z);
     const bool small = (B + 3) / 4 * 2 <= 296;             // 4 windows per CTA while two CTAs per SM-pair are not exceeded
     MDK_CUDA(cudaFuncSetAttribute(rl_lstm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_lstm_smem(4)));
