@@ -20,10 +20,9 @@
 //   rl_pool_linear_kernel sum of the read groups / number of reads, then Linear(C -> H).  (The reference applies the
 //                         Linear before the mean; the mean of an affine map is the affine map of the mean.)
 //   rl_gemm_kernel        LSTM input projections  gi = X W_ih^T + b_ih + b_hh   (both directions in one launch)
-//   rl_lstm_kernel        the LSTM recurrence: one CTA = 8 windows of one direction, 512 threads (gate g, unit j);
-//                         W_hh^T of gates i, f, g resident in shared memory (192 KiB), gate o's rows distributed over the
-//                         threads' registers (32 weights each); c and h stay on chip for all P steps.  4 windows per CTA
-//                         while that still fits one wave of CTAs (the step time is latency, not FLOPs)
+//   rl_lstm_kernel        the LSTM recurrence: one CTA = 4 windows of one direction, 256 threads (gate pair, unit j);
+//                         W_hh^T of gates i, f, g resident in shared memory (192 KiB), gate o's rows in registers (128
+//                         per thread of the second half); c and h stay on chip for all P steps
 //   head_kernel (misc.cu) Linear(2H -> 5) + softmax, shared with the counts models
 // All of it is CUDA-core fp32: parity first (tests/test_read_level.py against the reference's own class); the convolution
 // is 99 % of the FLOPs (557 kFLOP per read and position) and belongs on tcgen05 next.
@@ -484,41 +483,49 @@ __global__ void __launch_bounds__(256) rl_gemm_kernel(const float *__restrict__ 
 // gi  [B*P][2 dirs][4H]  (torch gate order i, f, g, o; b_ih + b_hh folded in)
 // out [B*P][2H]          (columns dir*H + j)
 // w3t [dir][H k][3H]     W_hh^T of gates i, f, g;   wo [dir][H j][H k]  W_hh rows of gate o
-constexpr int rl_lstm_smem(int nb) { return (RL_H * 3 * RL_H + 2 * nb * RL_H + 6 * nb * RL_H) * 4; }     // 224 KiB at 8 windows
+// One CTA = 4 windows of one direction, 256 threads = (half, unit j).  Half 0 computes gates i and f of unit j, half 1
+// gates g and o; W_hh^T of i, f, g is resident in shared memory (192 KiB), gate o's row j lives in the 128 registers of
+// thread (1, j).  The step is bound by shared-memory wavefronts (weights: 3 x 128 per warp pair; h: one broadcast
+// 16-byte load per window and 4 k), so every load of h feeds two gates.
+constexpr int RL_NB = 4;
+constexpr int RL_LSTM_SMEM = (RL_H * 3 * RL_H + 2 * RL_NB * RL_H + 4 * RL_NB * RL_H) * 4;      // 208 KiB
 
-template <int RL_NB>
-__global__ void __launch_bounds__(512, 1) rl_lstm_kernel(const float *__restrict__ gi, const float *__restrict__ w3t,
+__global__ void __launch_bounds__(256, 1) rl_lstm_kernel(const float *__restrict__ gi, const float *__restrict__ w3t,
                                                          const float *__restrict__ wo, float *__restrict__ out, int64_t B,
                                                          int64_t P) {
     extern __shared__ __align__(16) float smem_rl[];
     float *wt = smem_rl;                                  // [128 k][384]
     float *hs = wt + RL_H * 3 * RL_H;                     // [2][NB][128]
-    float *pre = hs + 2 * RL_NB * RL_H;                   // [3 gates][NB][128]  +  [3 foreign partials of gate o][NB][128]
+    float *pre = hs + 2 * RL_NB * RL_H;                   // [4 gates][NB][128]
     const int tid = threadIdx.x;
-    const int g = tid >> 7, j = tid & 127;                // gate slot 0..3, hidden unit
+    const int half = tid >> 7, j = tid & 127;
     const int dir = blockIdx.y;
     const int64_t b0 = (int64_t)blockIdx.x * RL_NB;
     const int nb = (int)min((int64_t)RL_NB, B - b0);
     {
         const float *src = w3t + (size_t)dir * RL_H * 3 * RL_H;
-        for (int i = tid; i < RL_H * 3 * RL_H / 4; i += 512) reinterpret_cast<float4 *>(wt)[i] = reinterpret_cast<const float4 *>(src)[i];
-        for (int i = tid; i < 2 * RL_NB * RL_H; i += 512) hs[i] = 0.f;
+        for (int i = tid; i < RL_H * 3 * RL_H / 4; i += 256) reinterpret_cast<float4 *>(wt)[i] = reinterpret_cast<const float4 *>(src)[i];
+        for (int i = tid; i < 2 * RL_NB * RL_H; i += 256) hs[i] = 0.f;
     }
-    float wq[32];                                         // gate o, row j, columns g*32 .. g*32+31
+    float wq[RL_H];                                       // gate o, row j (half 1 only)
+    if (half == 1) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) wq[k] = wo[((size_t)dir * RL_H + j) * RL_H + g * 32 + k];
-    // the update phase: thread (g, j) owns windows n = g, g + 4 (NB = 8) of unit j
-    float c_state[RL_NB / 4];
+        for (int k = 0; k < RL_H; k += 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(wo + ((size_t)dir * RL_H + j) * RL_H + k);
+            wq[k] = v.x; wq[k + 1] = v.y; wq[k + 2] = v.z; wq[k + 3] = v.w;
+        }
+    }
+    // update phase: thread (half, j) owns windows n = half, half + 2 of unit j
+    float c_state[RL_NB / 2];
 #pragma unroll
-    for (int q = 0; q < RL_NB / 4; ++q) c_state[q] = 0.f;
+    for (int q = 0; q < RL_NB / 2; ++q) c_state[q] = 0.f;
     __syncthreads();
     int cur = 0;
-    // the input pre-activations of this thread's windows are fetched one step ahead (the loads fly under the matvec)
-    float gnext[RL_NB / 4][4];
-    auto fetch = [&](int64_t t, float (&dst)[RL_NB / 4][4]) {
+    float gnext[RL_NB / 2][4];
+    auto fetch = [&](int64_t t, float (&dst)[RL_NB / 2][4]) {
 #pragma unroll
-        for (int q = 0; q < RL_NB / 4; ++q) {
-            const int n = g + 4 * q;
+        for (int q = 0; q < RL_NB / 2; ++q) {
+            const int n = half + 2 * q;
             const bool ok = n < nb;
             const float *row = gi + (((b0 + (ok ? n : 0)) * P + t) * 2 + dir) * RL_G4;
 #pragma unroll
@@ -529,78 +536,67 @@ __global__ void __launch_bounds__(512, 1) rl_lstm_kernel(const float *__restrict
     for (int64_t step = 0; step < P; ++step) {
         const int64_t t = dir ? (P - 1 - step) : step;
         const float *hc = hs + cur * RL_NB * RL_H;
-        float gcur[RL_NB / 4][4];
+        float gcur[RL_NB / 2][4];
 #pragma unroll
-        for (int q = 0; q < RL_NB / 4; ++q)
+        for (int q = 0; q < RL_NB / 2; ++q)
 #pragma unroll
             for (int gate = 0; gate < 4; ++gate) gcur[q][gate] = gnext[q][gate];
         if (step + 1 < P) fetch(dir ? (t - 1) : (t + 1), gnext);
-        // partial of gate o over this thread's quarter of k
-        float part[RL_NB];
+        float a0[RL_NB], a1[RL_NB];                       // half 0: i, f     half 1: g, o
 #pragma unroll
-        for (int n = 0; n < RL_NB; ++n) part[n] = 0.f;
-#pragma unroll
-        for (int k = 0; k < 32; k += 4) {
-#pragma unroll
-            for (int n = 0; n < RL_NB; ++n) {
-                const float4 hv = *reinterpret_cast<const float4 *>(hc + n * RL_H + g * 32 + k);
-                part[n] = fmaf(wq[k], hv.x, part[n]);
-                part[n] = fmaf(wq[k + 1], hv.y, part[n]);
-                part[n] = fmaf(wq[k + 2], hv.z, part[n]);
-                part[n] = fmaf(wq[k + 3], hv.w, part[n]);
-            }
-        }
-        // a window's owner (thread n % 4 of unit j) keeps its own quarter in registers; the other three quarters go
-        // through shared memory, slot (g - n % 4 + 4) % 4 - 1
-#pragma unroll
-        for (int n = 0; n < RL_NB; ++n) {
-            const int rel = (g - (n & 3) + 4) & 3;
-            if (rel != 0) pre[((3 + rel - 1) * RL_NB + n) * RL_H + j] = part[n];
-        }
-        if (g < 3) {
-            float acc[RL_NB];
-#pragma unroll
-            for (int n = 0; n < RL_NB; ++n) acc[n] = 0.f;
-#pragma unroll 2
+        for (int n = 0; n < RL_NB; ++n) { a0[n] = 0.f; a1[n] = 0.f; }
+        if (half == 0) {
+#pragma unroll 4
             for (int k = 0; k < RL_H; k += 4) {
                 float4 hv[RL_NB];
 #pragma unroll
                 for (int n = 0; n < RL_NB; ++n) hv[n] = *reinterpret_cast<const float4 *>(hc + n * RL_H + k);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    const float w = wt[(k + kk) * 3 * RL_H + g * RL_H + j];
+                    const float wi = wt[(k + kk) * 3 * RL_H + j];
+                    const float wf = wt[(k + kk) * 3 * RL_H + RL_H + j];
 #pragma unroll
                     for (int n = 0; n < RL_NB; ++n) {
                         const float hvk = kk == 0 ? hv[n].x : kk == 1 ? hv[n].y : kk == 2 ? hv[n].z : hv[n].w;
-                        acc[n] = fmaf(w, hvk, acc[n]);
+                        a0[n] = fmaf(wi, hvk, a0[n]);
+                        a1[n] = fmaf(wf, hvk, a1[n]);
                     }
                 }
             }
+        } else {
 #pragma unroll
-            for (int n = 0; n < RL_NB; ++n) pre[(g * RL_NB + n) * RL_H + j] = acc[n];
+            for (int k = 0; k < RL_H; k += 4) {            // fully unrolled: wq[] must stay in registers
+                float4 hv[RL_NB];
+#pragma unroll
+                for (int n = 0; n < RL_NB; ++n) hv[n] = *reinterpret_cast<const float4 *>(hc + n * RL_H + k);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const float wg = wt[(k + kk) * 3 * RL_H + 2 * RL_H + j];
+                    const float wov = wq[k + kk];
+#pragma unroll
+                    for (int n = 0; n < RL_NB; ++n) {
+                        const float hvk = kk == 0 ? hv[n].x : kk == 1 ? hv[n].y : kk == 2 ? hv[n].z : hv[n].w;
+                        a0[n] = fmaf(wg, hvk, a0[n]);
+                        a1[n] = fmaf(wov, hvk, a1[n]);
+                    }
+                }
+            }
         }
-        float own[RL_NB / 4];
 #pragma unroll
-        for (int n = 0; n < RL_NB; ++n)
-            if ((n & 3) == g) own[n >> 2] = part[n];               // (compile-time n: no dynamic register indexing)
+        for (int n = 0; n < RL_NB; ++n) {
+            pre[((2 * half) * RL_NB + n) * RL_H + j] = a0[n];
+            pre[((2 * half + 1) * RL_NB + n) * RL_H + j] = a1[n];
+        }
         __syncthreads();
         float *hn = hs + (cur ^ 1) * RL_NB * RL_H;
 #pragma unroll
-        for (int q = 0; q < RL_NB / 4; ++q) {
-            const int n = g + 4 * q;
+        for (int q = 0; q < RL_NB / 2; ++q) {
+            const int n = half + 2 * q;
             const bool ok = n < nb;
-            const float gi_i = gcur[q][0], gi_f = gcur[q][1], gi_g = gcur[q][2], gi_o = gcur[q][3];
-            // quarters in k order (0..3) whoever computed them: this thread's own is quarter g
-            float po = 0.f;
-#pragma unroll
-            for (int quarter = 0; quarter < 4; ++quarter) {
-                const int rel = (quarter - g + 4) & 3;
-                po += rel == 0 ? own[q] : pre[((3 + rel - 1) * RL_NB + n) * RL_H + j];
-            }
-            const float ig = rl_sigmoid(gi_i + pre[(0 * RL_NB + n) * RL_H + j]);
-            const float fg = rl_sigmoid(gi_f + pre[(1 * RL_NB + n) * RL_H + j]);
-            const float gg = tanhf(gi_g + pre[(2 * RL_NB + n) * RL_H + j]);
-            const float og = rl_sigmoid(gi_o + po);
+            const float ig = rl_sigmoid(gcur[q][0] + pre[(0 * RL_NB + n) * RL_H + j]);
+            const float fg = rl_sigmoid(gcur[q][1] + pre[(1 * RL_NB + n) * RL_H + j]);
+            const float gg = tanhf(gcur[q][2] + pre[(2 * RL_NB + n) * RL_H + j]);
+            const float og = rl_sigmoid(gcur[q][3] + pre[(3 * RL_NB + n) * RL_H + j]);
             const float c = fg * c_state[q] + ig * gg;
             c_state[q] = c;
             const float h = og * tanhf(c);
@@ -848,21 +844,15 @@ int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P,
     }
     rl_pool_linear_kernel<<<dim3((unsigned)((P + RL_PLT - 1) / RL_PLT), (unsigned)B), RL_H, 0, s>>>(d_part, d_mask, e->pool_w, e->pool_b, P, (int)D,
                                                                           n_groups, d_z);
-    const bool small = (B + 3) / 4 * 2 <= 296;             // 4 windows per CTA while two CTAs per SM-pair are not exceeded
-    MDK_CUDA(cudaFuncSetAttribute(rl_lstm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_lstm_smem(4)));
-    MDK_CUDA(cudaFuncSetAttribute(rl_lstm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_lstm_smem(8)));
+    MDK_CUDA(cudaFuncSetAttribute(rl_lstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RL_LSTM_SMEM));
     const float *layer_in = d_z;
     float *layer_out[2] = {d_h0, d_h1};
     for (int l = 0; l < 2; ++l) {
         const int in = l == 0 ? RL_H : 2 * RL_H;
         rl_gemm_kernel<<<dim3((unsigned)((BP + 127) / 128), 2 * RL_G4 / 128), 256, 0, s>>>(layer_in, e->lstm[l].w_ih, e->lstm[l].bias,
                                                                                        d_gi, BP, in, 2 * RL_G4);
-        if (small)
-            rl_lstm_kernel<4><<<dim3((unsigned)((B + 3) / 4), 2), 512, rl_lstm_smem(4), s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
-                                                                                          layer_out[l], B, P);
-        else
-            rl_lstm_kernel<8><<<dim3((unsigned)((B + 7) / 8), 2), 512, rl_lstm_smem(8), s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
-                                                                                          layer_out[l], B, P);
+        rl_lstm_kernel<<<dim3((unsigned)((B + RL_NB - 1) / RL_NB), 2), 256, RL_LSTM_SMEM, s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
+                                                                                            layer_out[l], B, P);
         layer_in = layer_out[l];
     }
     MDK_CUDA(cudaGetLastError());
