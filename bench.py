@@ -281,12 +281,50 @@ CONFIGS = {
             name="r1041_e82_400bps_sup_v5 consensus, synthetic 200 Mb draft region-sharded over 8 GPUs: this rank's share, "
                  "2778 of 22223 windows x 10000 cols x 10 feats"),
     4: dict(windows=5556, cols=10000, feats=10,
-            name="r1041_e82_400bps_sup_variant_v5, synthetic 50 Mb: 5556 windows x 10000 cols x 10 feats; the e2e leg adds "
-                 "the variant decode of every step's output on the GPU (mdk_decode_variants)"),
+            name="r1041_e82_400bps_sup_variant_v5, synthetic 50 Mb: 5556 windows x 10000 cols x 10 feats; the variant decode "
+                 "of a step's output (mdk_decode_variants) is timed additionally, see variant_decode"),
     5: dict(windows=1111, cols=10000, feats=20,
             name="r941_min_hac_g507-style legacy encoder, synthetic 10 Mb: 1111 windows x 10000 cols x 20 feats (two "
                  "datatypes, normalise='fwd_rev'); a step starts from raw uint64 counts (normalise kernel + forward)"),
 }
+
+
+def variant_leg(probs, B, T, dev):
+    """BASELINE config 4's extra: the variant decode of one step's probabilities (argmax with gaps, variant-column rule,
+    run detection, quality sums: medaka/labels.py:889-1014) on the GPU through host buffers, per 512-window joined
+    sample, beside the numpy restatement on a bounded sample."""
+    from medaka_b200 import labels as mlabels
+    from oracle import variants_oracle
+    rs = np.random.RandomState(5)
+    vminor = (rs.uniform(size=T) < 0.12).astype(np.int64)       # synthetic draft: ~12 % insertion columns
+    vminor[0] = 0
+    vref = np.where(vminor == 0, rs.randint(1, 5, T), 0).astype(np.uint8)
+
+    def gpu_pass():
+        n_var = 0
+        for w in range(0, B, 512):
+            wb = min(B, w + 512)
+            mn, rf = np.tile(vminor, wb - w), np.tile(vref, wb - w)
+            n_var += len(mlabels.decode_variant_arrays(probs[w:wb].reshape(-1, 5), mn, rf, dev, want_quals=False)["run_start"])
+        return n_var
+    gpu_pass()
+    t0 = time.perf_counter()
+    n_var = gpu_pass()
+    t_gpu = time.perf_counter() - t0
+    # numpy restatement (oracle/variants_oracle.py) on 8 windows
+    nw = min(B, 8)
+    major = np.cumsum(vminor == 0) - 1
+    pos = np.empty(T, dtype=[("major", "<i8"), ("minor", "<i8")])
+    pos["major"], pos["minor"] = major, vminor
+    draft = "".join("*ACGT"[c] for c in vref[vminor == 0])
+    t0 = time.perf_counter()
+    for w in range(nw):
+        variants_oracle.decode_variants(pos, probs[w], draft)
+    t_cpu = time.perf_counter() - t0
+    return {"columns_per_step": int(B) * int(T), "gpu_ms_per_step": t_gpu * 1e3, "gpu_columns_per_s": B * T / t_gpu,
+            "variant_runs": int(n_var), "cpu_columns_per_s": nw * T / t_cpu,
+            "cpu_sample": "%d windows, numpy restatement incl. Variant record building" % nw,
+            "note": "timed separately from the inference legs (medaka vcf is a separate consumer of the stored probabilities)"}
 
 
 def workload_name(cfg=2):
@@ -489,68 +527,27 @@ def main():
     bw = max(1, min(args.batch_windows, B))
     batches = [(a, min(B, a + bw)) for a in range(0, B, bw)]
     depth = model.lookahead(bw, T)
-    n_slots = 3 if args.config == 4 else 2          # host result buffers: config 4 keeps a step alive while it is decoded
+    n_slots = 2
     h_probs = model.pinned("bench_probs", (n_slots, B, T, 5), np.float32)   # results stay valid while the next step is
     h_labels = model.pinned("bench_labels", (n_slots, B, T), np.uint8)      # already queued
-    variant_ms = []
-    vd = None
-    if args.config == 4:
-        # synthetic draft for the variant decode: every window is decoded against a random draft with ~12 % insertion
-        # columns (the decode is per joined sample; here one call per batch of windows)
-        rs = np.random.RandomState(5)
-        vminor = (rs.uniform(size=T) < 0.12).astype(np.int64)
-        vminor[0] = 0
-        vref = np.where(vminor == 0, rs.randint(1, 5, T), 0).astype(np.uint8)
-        from medaka_b200 import labels as mlabels
-        vd = (mlabels, vminor, vref)
 
-    def run_host(n, timed=False):
+    def run_host(n):
         # the reference-facing loop (medaka/prediction.py:44-52): batches submitted with the engine's look-ahead, results
-        # collected in order.  Config 4: a worker thread runs the variant decode of step k as soon as its last batch is
-        # back (medaka vcf is a separate consumer of the probabilities), the main thread keeps feeding the engine
+        # collected in order
         pending = []
-        jobs = {}
-        pool = concurrent.futures.ThreadPoolExecutor(1) if vd is not None else None
-
-        def collect_one():
-            tk, kk, a, b = pending.pop(0)
-            model.wait(tk)
-            if pool is not None and b == B:              # last batch of step kk is back
-                jobs[kk] = pool.submit(decode_step, kk, timed)
         for k in range(n):
-            if pool is not None and k - n_slots in jobs:
-                jobs.pop(k - n_slots).result()           # its buffer is about to be overwritten
             for a, b in batches:
                 while len(pending) >= depth:
-                    collect_one()
-                tk = model.submit_arrays(feats[a:b], h_probs[k % n_slots, a:b], h_labels[k % n_slots, a:b])
-                pending.append((tk, k, a, b))
+                    model.wait(pending.pop(0))
+                pending.append(model.submit_arrays(feats[a:b], h_probs[k % n_slots, a:b], h_labels[k % n_slots, a:b]))
         while pending:
-            collect_one()
-        if pool is not None:
-            for j in jobs.values():
-                j.result()
-            pool.shutdown()
-
-    def decode_step(k, timed):
-        mlabels, vminor, vref = vd
-        t0 = time.perf_counter()
-        n_var = 0
-        for w in range(0, B, 512):                      # 512 windows per call: 5.1 M columns, a joined multi-Mb contig
-            wb = min(B, w + 512)
-            probs = h_probs[k % n_slots, w:wb].reshape(-1, 5)
-            mn = np.tile(vminor, wb - w)
-            rf = np.tile(vref, wb - w)
-            n_var += len(mlabels.decode_variant_arrays(probs, mn, rf, dev, want_quals=False)["run_start"])
-        if timed:
-            variant_ms.append((time.perf_counter() - t0) * 1e3)
-        return n_var
+            model.wait(pending.pop(0))
 
     log("host-buffer leg (%d-window batches, %d in flight)" % (bw, depth))
     run_host(max(1, min(args.warmup, 2)))
     barrier()
     lm.check(lib.mdk_engine_timer_start(eng))
-    run_host(args.steps, timed=True)
+    run_host(args.steps)
     lm.check(lib.mdk_engine_timer_stop(eng, ms))
     barrier()
     e2e_ms = float(ms[0])
@@ -650,8 +647,8 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    if variant_ms:
-        line["e2e"]["variant_decode_ms_per_step"] = float(np.mean(variant_ms))
+    if args.config == 4:
+        line["variant_decode"] = variant_leg(h_probs[(args.steps - 1) % n_slots], B, T, dev)
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
