@@ -292,6 +292,7 @@ def check_timeline(arg):
     from oracle import synth
     parts = arg.split(",")
     mode, B, T, n = parts[0], int(parts[1]), int(parts[2]), int(parts[3])
+    stagger_ms = float(parts[4]) if len(parts) > 4 else 0.0      # host-side delay before the second lane's first forward
     lib, ffi = lm.load(), lm.ffi
     m = models.GRUModel()
     m.load_state_dict(synth.synth_state_dict(0))
@@ -318,6 +319,8 @@ def check_timeline(arg):
     lm.check(lib.mdk_engine_timer_start(eng))
     for i in range(n):
         fwd(i)
+        if i == 0 and stagger_ms > 0:
+            time.sleep(stagger_ms * 1e-3)
     lm.check(lib.mdk_engine_timer_stop(eng, ms))
     out = np.zeros((n, 8), dtype=np.float32)
     lm.check(lib.mdk_debug_timeline(eng, n, ffi.cast("float *", ffi.from_buffer(out))))

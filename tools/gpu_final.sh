@@ -1,9 +1,12 @@
 #!/bin/bash
-# round-end evidence: bench line (with CPU baseline), NT=2 shape, ncu launch list, ncu full capture of the hot kernels
+# round-end check on one B200: smoke, the GPU test suite, the two bench arms the driver runs.  usage: tools/gpu_final.sh <tag>
 tag=${1:-x}
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
-timeout 600 python bench.py --windows 2368 --no-cpu-baseline > gpurun_out/bench2368_$tag.json 2>> gpurun_out/bench_$tag.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 8 -c 16 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/ncu_l_$tag.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"rec_tc|gemm_tc|head_kernel" -s 4 -c 4 -o gpurun_out/prof_$tag python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_f_$tag.log 2>&1
-tail -c 400 gpurun_out/bench_$tag.json; tail -c 300 gpurun_out/bench2368_$tag.json
+O=gpurun_out
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4
+timeout 1200 python -m pytest tests -x -q -m gpu > $O/${tag}_pytest_gpu.log 2>&1; tail -n 3 $O/${tag}_pytest_gpu.log
+timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/${tag}_bench_reference.json 2> $O/${tag}_bench_reference.err; tail -c 300 $O/${tag}_bench_reference.json
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/${tag}_bench_cfg2.json 2> $O/${tag}_bench_cfg2.err; python -c "
+import json; d=json.loads(open('$O/${tag}_bench_cfg2.json').read().strip().splitlines()[-1]); print('cfg2 value %.3e e2e %.3e ms %.1f'%(d['value'], d['e2e']['value'], d['ms_per_step']), d['clocks'], round(d['roofline']['frac'],3), round(d['roofline']['full_wave_solo']['frac'],3), d['cpu_baseline']['value'])"
+timeout 600 python bench.py --config 4 --steps 4 --warmup 3 --no-cpu-baseline > $O/${tag}_bench_cfg4.json 2> $O/${tag}_bench_cfg4.err; python -c "
+import json; d=json.loads(open('$O/${tag}_bench_cfg4.json').read().strip().splitlines()[-1]); print('cfg4 value %.3e e2e %.3e'%(d['value'], d['e2e']['value']), d.get('variant_decode'))" || tail -5 $O/${tag}_bench_cfg4.err
