@@ -130,6 +130,48 @@ def main():
     out["joined_mat"] = joined[0][0]
     out["joined_major"] = joined[0][1]["major"]
     print("reference chunk join:", [c[0].shape for c in chunk_in], "->", joined[0][0].shape)
+    # 5. a harder join: short synthetic reads that come and go, five sub-regions of unequal depth, one of them behind a
+    #    coverage gap (so: row re-ordering, rows filled from vacated slots, appended rows, padding, a split)
+    from oracle import synth
+    rs = np.random.RandomState(12)
+    srecs = synth.synth_reads(160, 2600, seed=77, mean_len=260)
+    srecs = [r for r in srecs if not (1480 <= r["pos"] < 1640)]
+    srecs.sort(key=lambda r: r["pos"])
+    for i, r in enumerate(srecs):
+        r["query_name"], r["tags"] = "s%d" % i, {}
+        r["qual"] = rs.randint(1, 40, len(r["seq"])).tolist()
+    import re
+    for r in srecs:                                   # nothing may bridge the gap
+        if r["pos"] < 1480:
+            used, out_ops = 0, []
+            for n_, op in re.findall(r"(\d+)([MIDNSHP=X])", r["cigar"]):
+                n_ = int(n_)
+                if op in "MDN=X":
+                    if r["pos"] + used + n_ > 1480:
+                        n_ = 1480 - r["pos"] - used
+                        if n_ > 0 and op in "M=X":
+                            out_ops.append("%d%s" % (n_, op))
+                        break
+                    used += n_
+                out_ops.append("%d%s" % (n_, op))
+            while out_ops and out_ops[-1][-1] not in "M=X":
+                out_ops.pop()
+            r["cigar"] = "".join(out_ops) or "1M"
+    hard_in = []
+    for k, (a, b) in enumerate([(100, 600), (600, 1100), (1100, 1700), (1700, 2100), (2100, 2500)]):
+        mm, pp_, left, right = read_matrix_oracle.read_alignment(srecs, a, b)
+        out["hard%d_mat" % k] = mm
+        out["hard%d_major" % k] = pp_["major"]
+        out["hard%d_minor" % k] = pp_["minor"]
+        out["hard%d_left" % k] = np.array([x.encode() for x in left], dtype="S")
+        out["hard%d_right" % k] = np.array([x.encode() for x in right], dtype="S")
+        hard_in.append((mm, pp_, (out["hard%d_left" % k], out["hard%d_right" % k])))
+    hard = join(hard_in)
+    out["hard_n"] = len(hard)
+    for i, (mm, pp_) in enumerate(hard):
+        out["hard_joined%d_mat" % i] = mm
+        out["hard_joined%d_major" % i] = pp_["major"]
+    print("reference chunk join (hard):", [c[0].shape for c in hard_in], "->", [h[0].shape for h in hard])
     name_off = np.concatenate([[0], np.cumsum([len(n) for n in rb.names])]).astype(np.int64)
     np.savez_compressed(
         os.path.join(HERE, "read_matrix.npz"),

@@ -93,6 +93,21 @@ def test_chunk_join_matches_reference_function(gold):
     assert len(parts) == 2 and sum(len(x[1]) for x in parts) == int(keep.sum())
 
 
+def test_chunk_join_hard_case_matches_reference_function(gold):
+    """Five sub-regions of unequal depth with reads entering and leaving and a coverage gap inside the third."""
+    from medaka_b200 import features
+    chunks = []
+    for k in range(5):
+        pos = np.empty(len(gold["hard%d_major" % k]), dtype=[("major", "<i8"), ("minor", "<i8")])
+        pos["major"], pos["minor"] = gold["hard%d_major" % k], gold["hard%d_minor" % k]
+        chunks.append((gold["hard%d_mat" % k], pos, (gold["hard%d_left" % k], gold["hard%d_right" % k])))
+    joined = features._join_read_matrix_chunks(chunks)
+    assert len(joined) == int(gold["hard_n"]) >= 2
+    for i, (m, p) in enumerate(joined):
+        assert np.array_equal(m, gold["hard_joined%d_mat" % i]), i
+        assert np.array_equal(p["major"], gold["hard_joined%d_major" % i])
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 def _device(batch, start, end, **kw):
     from medaka_b200 import features
