@@ -74,9 +74,11 @@ def _ref_globals():
         ('medaka.models', 'model_from_dict'): _ref_model_from_dict,
         ('medaka.models', 'build_model_torch'): _ref_build_model_torch,
         ('medaka.features', 'CountsFeatureEncoder'): features.CountsFeatureEncoder,
+        ('medaka.features', 'ReadAlignmentFeatureEncoder'): features.ReadAlignmentFeatureEncoder,
         ('medaka.labels', 'HaploidLabelScheme'): labels.HaploidLabelScheme,
         # archives written by this package
         ('medaka_b200.features', 'CountsFeatureEncoder'): features.CountsFeatureEncoder,
+        ('medaka_b200.features', 'ReadAlignmentFeatureEncoder'): features.ReadAlignmentFeatureEncoder,
         ('medaka_b200.labels', 'HaploidLabelScheme'): labels.HaploidLabelScheme,
         ('medaka_b200.datastore', '_ref_model_from_dict'): _ref_model_from_dict,
         ('medaka_b200.datastore', '_ref_build_model_torch'): _ref_build_model_torch,
@@ -89,8 +91,8 @@ class _RefUnpickler(pickle.Unpickler):
             return _ref_globals()[module, name]
         except KeyError:
             raise pickle.UnpicklingError(
-                "refusing to unpickle {}.{}: medaka_b200 loads counts-matrix GRU models with a CountsFeatureEncoder and "
-                "a HaploidLabelScheme only".format(module, name))
+                "refusing to unpickle {}.{}: medaka_b200 loads GRU / LatentSpaceLSTM models with a Counts- or "
+                "ReadAlignmentFeatureEncoder and a HaploidLabelScheme only".format(module, name))
 
 
 def ref_loads(data):
@@ -112,6 +114,7 @@ def _reference_module_names():
     renamed = [(_ref_model_from_dict, 'medaka.models', 'model_from_dict'),
                (_ref_build_model_torch, 'medaka.models', 'build_model_torch'),
                (features.CountsFeatureEncoder, 'medaka.features', 'CountsFeatureEncoder'),
+               (features.ReadAlignmentFeatureEncoder, 'medaka.features', 'ReadAlignmentFeatureEncoder'),
                (labels.HaploidLabelScheme, 'medaka.labels', 'HaploidLabelScheme')]
     saved_mods = {k: sys.modules.get(k) for k in fakes}
     saved_names = [(o, o.__module__, o.__qualname__, o.__name__) for o, _, _ in renamed]
@@ -151,7 +154,9 @@ def as_reference_meta(meta):
         out['model_function'] = functools.partial(_ref_model_from_dict, mf)
     fe = out.get('feature_encoder')
     if isinstance(fe, dict):
-        out['feature_encoder'] = features.CountsFeatureEncoder(**fe.get('kwargs', {}))
+        cls = features.ReadAlignmentFeatureEncoder if fe.get('type') == 'ReadAlignmentFeatureEncoder' else \
+            features.CountsFeatureEncoder
+        out['feature_encoder'] = cls(**fe.get('kwargs', {}))
     ls = out.get('label_scheme')
     if isinstance(ls, str):
         if ls != 'HaploidLabelScheme':

@@ -366,8 +366,11 @@ def model_from_dict(d, time_steps=None, device=0):
     """medaka/models.py:392-400 for the architectures this engine implements."""
     name, kwargs = d["type"], dict(d["kwargs"])
     kwargs.pop("read_majority_threshold", None)
+    if name == "LatentSpaceLSTM":
+        from medaka_b200 import read_level
+        return read_level.LatentSpaceLSTM(device=device, **kwargs)
     if name != "GRUModel":
-        raise NotImplementedError("medaka_b200 implements the counts-matrix GRUModel; got {}".format(name))
+        raise NotImplementedError("medaka_b200 implements GRUModel and LatentSpaceLSTM; got {}".format(name))
     return GRUModel(device=device, **kwargs)
 
 

@@ -40,8 +40,18 @@ def main():
         "feature_encoder": ref_features.CountsFeatureEncoder(),
         "label_scheme": ref_labels.HaploidLabelScheme(),
     }
+    rl_cfg = {"type": "LatentSpaceLSTM", "kwargs": {"num_classes": 5, "lstm_size": 128, "cnn_size": 128,
+                                                      "kernel_sizes": [1, 17], "pooler_type": "mean", "pooler_args": {},
+                                                      "use_dwells": True, "bases_alphabet_size": 6,
+                                                      "bases_embedding_size": 6, "bidirectional": True}}
+    read_level = {
+        "model_function": functools.partial(ref_models.model_from_dict, rl_cfg),
+        "feature_encoder": ref_features.ReadAlignmentFeatureEncoder(max_reads=80, include_dwells=True, min_mapq=2),
+        "label_scheme": ref_labels.HaploidLabelScheme(),
+    }
     out = {"v2": np.frombuffer(pickle.dumps(meta, protocol=4), dtype=np.uint8),
-           "legacy": np.frombuffer(pickle.dumps(legacy, protocol=2), dtype=np.uint8)}
+           "legacy": np.frombuffer(pickle.dumps(legacy, protocol=2), dtype=np.uint8),
+           "read_level": np.frombuffer(pickle.dumps(read_level, protocol=4), dtype=np.uint8)}
     np.savez_compressed(os.path.join(HERE, "ref_meta.npz"), meta="medaka v%s" % __import__('medaka').__version__, **out)
 
     # ---- the other direction: our pickles in the reference's hands
@@ -61,6 +71,16 @@ def main():
     assert mf.func is ref_models.model_from_dict and mf.args[0]["type"] == "GRUModel"
     model = mf(time_steps=None)
     assert type(model).__name__ == "GRUModel" and model.gru.hidden_size == 128
+    ours_rl = datastore.ref_dumps(datastore.as_reference_meta({
+        "model_function": rl_cfg,
+        "feature_encoder": {"type": "ReadAlignmentFeatureEncoder", "kwargs": {"max_reads": 60, "include_dwells": False}},
+        "label_scheme": "HaploidLabelScheme"}))
+    got_rl = pickle.loads(ours_rl)
+    fe = got_rl["feature_encoder"]
+    assert isinstance(fe, ref_features.ReadAlignmentFeatureEncoder) and fe.max_reads == 60 and fe.include_dwells is False
+    assert fe.normalise is None and fe.feature_vector_length == 4 and fe.row_per_read is False
+    rl_model = got_rl["model_function"](time_steps=None)
+    assert type(rl_model).__name__ == "LatentSpaceLSTM" and rl_model.use_dwells is True and rl_model.lstm_size == 128
     print("reference -> ours: ref_meta.npz written;  ours -> reference: unpickled into", type(got["feature_encoder"]),
           type(got["label_scheme"]), type(model))
 

@@ -274,6 +274,16 @@ def test_reference_pickled_meta_loads(golden_dir):
             ms._meta = datastore.ref_loads(g[key].tobytes())
             ms._weights = {}
             assert ms.model_kwargs() == {"type": "GRUModel", "kwargs": expect}
+    # a read-level (rl_) archive: LatentSpaceLSTM + ReadAlignmentFeatureEncoder as the reference pickles them
+    rl = datastore.ref_loads(g["read_level"].tobytes())
+    fe = rl["feature_encoder"]
+    assert type(fe).__name__ == "ReadAlignmentFeatureEncoder"
+    assert (fe.max_reads, fe.include_dwells, fe.min_mapq, fe.row_per_read, fe.normalise) == (80, True, 2, False, None)
+    assert fe.feature_vector_length == 5
+    ms = datastore.ModelStoreTGZ("unused.tar.gz")
+    ms._meta, ms._weights = rl, {}
+    kw = ms.model_kwargs()
+    assert kw["type"] == "LatentSpaceLSTM" and kw["kwargs"]["use_dwells"] is True and kw["kwargs"]["lstm_size"] == 128
     evil = pickle.dumps(os.system)
     with pytest.raises(pickle.UnpicklingError):
         datastore.ref_loads(evil)
