@@ -263,8 +263,8 @@ int mdk_rl_create(int device, int32_t lstm_size, int32_t cnn_size, int32_t use_d
                   mdk_rl_engine **out);
 int mdk_rl_destroy(mdk_rl_engine *e);
 int mdk_rl_load(mdk_rl_engine *e, const char *name, const float *data, int64_t n);
-/* the k = 17 convolution (99 % of the network's FLOPs): 1 = tcgen05 implicit GEMM with fp16 hi/lo operand pairs (default),
- * 0 = fp32 CUDA cores (validation) */
+/* which parts run on tcgen05 with fp16 hi/lo operand pairs (bit set) or on the fp32 CUDA cores (validation twins):
+ * bit 0 = the k = 17 convolution (99 % of the network's FLOPs), bit 1 = the LSTM recurrences.  Default 3. */
 int mdk_rl_set_conv(mdk_rl_engine *e, int tensor_cores);
 int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P, int64_t D, int64_t F,
                    float *probs_host);

@@ -608,8 +608,169 @@ __global__ void __launch_bounds__(256, 1) rl_lstm_kernel(const float *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------- LSTM on tcgen05
+// The recurrence with the matvec on the tensor cores:  G^T[4H][16 windows] = W_hh[4H][H] . h^T[H][16]  per time step.
+//   A = W_hh: the fp16 hi plane of all four gates lives in TENSOR MEMORY (4 x 64 columns, TS mode), the lo plane in
+//       shared memory as K-major operand tiles (4 x 32 KiB, SS mode) - hi + lo of four gates would fill all 512 columns
+//   B = the h tile [16 windows][128] the gate warps publish every step (fp16 hi | lo, K-major)
+//   D = four 16-column accumulators (lane = hidden unit, column = window); three products per contraction:
+//       W_hi.h_hi and W_hi.h_lo from tensor memory, W_lo.h_hi from shared memory
+// One CTA = 16 windows of one direction; warps 0-7: gate warps (thread = hidden unit x 8 windows: c and h stay in
+// registers, the input pre-activations are fetched one step ahead), warp 8: MMA issuer.  A step is the dependent chain
+// publish h -> 96 MMAs -> gate arithmetic, like the one-tile GRU kernel.
+constexpr int LT_N = 16;
+constexpr int LT_WLO_GATE = (RL_H / 8) * RL_H * 16;          // 32 768 B: one gate's lo plane as A operand tiles
+constexpr int LT_HPLANE = (RL_H / 8) * LT_N * 16;            // 4 096 B
+constexpr int LT_OFF_H = 4 * LT_WLO_GATE;
+constexpr int LT_OFF_BAR = LT_OFF_H + 2 * LT_HPLANE;
+constexpr int LT_SMEM = LT_OFF_BAR + 64;
+constexpr uint32_t LT_ACC_COL = 256;                         // accumulators behind the four 64-column weight blocks
+constexpr int LT_W = LT_N / 2;                               // windows per gate thread
+constexpr int LT_ISSUER = 8;                                 // warps 0-7 gate warps, warp 8 issues
+constexpr int LT_THREADS = 32 * (LT_ISSUER + 1);
+// MUFU-based gate functions (ex2.approx / rcp.approx, ~2 ulp): the gate phase is instruction bound
+__device__ __forceinline__ float lt_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lt_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lt_sigmoid(float x) { return lt_rcp(1.0f + lt_ex2(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float lt_tanh(float x) { return fmaf(-2.0f, lt_rcp(1.0f + lt_ex2(2.8853900817779268f * x)), 1.0f); }
+
+__global__ void __launch_bounds__(LT_THREADS, 1) rl_lstm_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hi,
+                                                            const uint8_t *__restrict__ w_lo_tiles, float *__restrict__ out,
+                                                            int64_t B, int64_t P) {
+    extern __shared__ __align__(128) uint8_t smem_lt[];
+    uint8_t *swlo = smem_lt;
+    uint8_t *sh = smem_lt + LT_OFF_H;
+    uint64_t *acc_full = reinterpret_cast<uint64_t *>(smem_lt + LT_OFF_BAR);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dir = blockIdx.y;
+    const int64_t b0 = (int64_t)blockIdx.x * LT_N;
+    const int nb = (int)min((int64_t)LT_N, B - b0);
+    if (tid == 0) { mbar_init(acc_full, 1); fence_mbar_init(); }
+    if (warp == LT_ISSUER) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    // lo plane of W_hh -> shared memory (pre-tiled per direction: [gate][k-group][row][8 halfs]); h tile = 0
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(w_lo_tiles + (size_t)dir * 4 * LT_WLO_GATE);
+        for (int i = tid; i < 4 * LT_WLO_GATE / 16; i += LT_THREADS) reinterpret_cast<uint4 *>(swlo)[i] = src[i];
+        for (int i = tid; i < 2 * LT_HPLANE / 16; i += LT_THREADS) reinterpret_cast<uint4 *>(sh)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int j = tid & 127;                                 // hidden unit of a gate thread
+    if (warp < 4) {
+        // (one warp per lane quarter) hi plane of W_hh (row-major fp16 [dir][4H][H]) -> tensor memory: gate g, k-step ks at column g*64 + ks*8
+        const uint32_t t_w = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int g = 0; g < 4; ++g) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(w_hi + (((size_t)dir * 4 + g) * RL_H + j) * RL_H);
+#pragma unroll
+            for (int ks = 0; ks < RL_H / 16; ++ks) {
+                const uint4 lo4 = src[2 * ks], hi4 = src[2 * ks + 1];
+                const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                tmem_st_x8(t_w + (uint32_t)(g * 64 + ks * 8), v);
+            }
+        }
+        tmem_st_wait();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+
+    if (warp == LT_ISSUER) {
+        const uint32_t idesc = make_idesc_f16(128, LT_N);
+        const uint32_t h_hi = smem_u32(sh), h_lo = smem_u32(sh + LT_HPLANE), wl = smem_u32(swlo);
+        for (int64_t step = 0; step < P; ++step) {
+            if (elect_one()) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t d = tmem_base + LT_ACC_COL + (uint32_t)(g * LT_N);
+#pragma unroll
+                    for (int ks = 0; ks < RL_H / 16; ++ks) {
+                        const uint64_t bh = make_smem_desc(h_hi + ks * 2 * (LT_N * 16), LT_N * 16, 128);
+                        umma_f16_ts(d, tmem_base + (uint32_t)(g * 64 + ks * 8), bh, idesc, ks ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < RL_H / 16; ++ks) {
+                        const uint64_t bl = make_smem_desc(h_lo + ks * 2 * (LT_N * 16), LT_N * 16, 128);
+                        umma_f16_ts(d, tmem_base + (uint32_t)(g * 64 + ks * 8), bl, idesc, 1u);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < RL_H / 16; ++ks) {
+                        const uint64_t ad = make_smem_desc(wl + g * LT_WLO_GATE + ks * 2 * (RL_H * 16), RL_H * 16, 128);
+                        const uint64_t bh = make_smem_desc(h_hi + ks * 2 * (LT_N * 16), LT_N * 16, 128);
+                        umma_f16(d, ad, bh, idesc, 1u);
+                    }
+                }
+                umma_commit(acc_full);
+            }
+            __syncwarp();
+            tc_fence_before_sync();
+            __syncthreads();                                   // the gate warps have published the next h tile
+            tc_fence_after_sync();
+        }
+    } else {
+        // warps w and w + 4 share TMEM lane quarter w (hidden units 32 w .. 32 w + 31) and split the 16 windows.
+        // the input pre-activations of the NEXT step are loaded right after this step's arithmetic has consumed the
+        // current ones: the loads fly under the publish and the next step's MMAs (one register set, not two)
+        const int half = warp >> 2;
+        float c_state[LT_W], gcur[4][LT_W];
+#pragma unroll
+        for (int n = 0; n < LT_W; ++n) c_state[n] = 0.f;
+        auto fetch = [&](int64_t t) {
+#pragma unroll
+            for (int n = 0; n < LT_W; ++n) {
+                const int wdw = half * LT_W + n;
+                const bool ok = wdw < nb;
+                const float *row = gi + (((b0 + (ok ? wdw : 0)) * P + t) * 2 + dir) * RL_G4 + j;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) gcur[g][n] = ok ? __ldg(row + g * RL_H) : 0.f;
+            }
+        };
+        fetch(dir ? (P - 1) : 0);
+        const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + LT_ACC_COL + (uint32_t)(half * LT_W);
+        const int hoff = (j >> 3) * (LT_N * 16) + (j & 7) * 2 + half * LT_W * 16;
+        for (int64_t step = 0; step < P; ++step) {
+            const int64_t t = dir ? (P - 1 - step) : step;
+            mbar_wait(acc_full, (uint32_t)(step & 1));
+            tc_fence_after_sync();
+            uint32_t a[4][LT_W];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tmem_ld_x8(t_lane + (uint32_t)(g * LT_N), a[g]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int n = 0; n < LT_W; ++n) {
+                const float ig = lt_sigmoid(gcur[0][n] + __uint_as_float(a[0][n]));
+                const float fg = lt_sigmoid(gcur[1][n] + __uint_as_float(a[1][n]));
+                const float gg = lt_tanh(gcur[2][n] + __uint_as_float(a[2][n]));
+                const float og = lt_sigmoid(gcur[3][n] + __uint_as_float(a[3][n]));
+                const float c = fmaf(fg, c_state[n], ig * gg);
+                c_state[n] = c;
+                const float h = og * lt_tanh(c);
+                const int wdw = half * LT_W + n;
+                if (wdw < nb) out[((b0 + wdw) * P + t) * (2 * RL_H) + dir * RL_H + j] = h;
+                __half hi, lo;
+                split_f16(h, hi, lo);
+                *reinterpret_cast<__half *>(sh + hoff + n * 16) = hi;
+                *reinterpret_cast<__half *>(sh + LT_HPLANE + hoff + n * 16) = lo;
+            }
+            if (step + 1 < P) fetch(dir ? (t - 1) : (t + 1));
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncthreads();
+            tc_fence_after_sync();
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == LT_ISSUER) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 512); }
+}
+
 // ---------------------------------------------------------------------------------------------- engine
 struct RlLstmLayer {
+    __half *w_hi = nullptr;     // [2][4H][H] fp16 hi plane of W_hh (tensor-core kernel: -> tensor memory)
+    uint8_t *w_lo = nullptr;    // [2][4 gates][k-group 16][row 128][8 halfs] lo plane as shared-memory A operand tiles
     float *w_ih = nullptr;      // [2 dirs * 4H][in]   (both directions stacked: one GEMM)
     float *bias = nullptr;      // [2 * 4H]  b_ih + b_hh
     float *w3t = nullptr;       // [2][H][3H]
@@ -631,6 +792,7 @@ struct mdk_rl_engine {
     float *c17_wt = nullptr, *c17_b = nullptr, *bn2[4] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t *c17_tc = nullptr;     // [17 taps][hi | lo][k-group 16][co 128][8 halfs]: the tensor-core kernel's A operand tiles
     int conv_tc = 1;               // 1: k = 17 convolution on tcgen05 (default), 0: fp32 CUDA cores
+    int lstm_tc = 1;               // 1: LSTM recurrence on tcgen05 (default), 0: fp32 CUDA cores
     float *pool_w = nullptr, *pool_b = nullptr;
     RlLstmLayer lstm[2];
     float *lin_w = nullptr, *lin_b = nullptr;
@@ -746,6 +908,30 @@ int rl_prepare(mdk_rl_engine *e) {
         if ((rc = rl_upload(e, w_ih, &e->lstm[l].w_ih)) || (rc = rl_upload(e, bias, &e->lstm[l].bias)) ||
             (rc = rl_upload(e, w3t, &e->lstm[l].w3t)) || (rc = rl_upload(e, wo, &e->lstm[l].wo)))
             return rc;
+        // tensor-core operands: hi plane row-major (torch's [4H][H] as it is), lo plane as K-major tiles per gate
+        std::vector<__half> hi((size_t)2 * RL_G4 * RL_H), lo_t((size_t)2 * RL_G4 * RL_H);
+        for (int d = 0; d < 2; ++d) {
+            const std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
+            const std::vector<float> &whh = e->host["lstm.weight_hh" + sfx];
+            for (int r = 0; r < RL_G4; ++r)
+                for (int k = 0; k < RL_H; ++k) {
+                    const float v = whh[(size_t)r * RL_H + k];
+                    const __half h16 = __float2half_rn(v);
+                    hi[((size_t)d * RL_G4 + r) * RL_H + k] = h16;
+                    const int g = r / RL_H, jj = r % RL_H;
+                    lo_t[(size_t)d * RL_G4 * RL_H + (((size_t)g * (RL_H / 8) + k / 8) * RL_H + jj) * 8 + (k % 8)] =
+                        __float2half_rn(v - __half2float(h16));
+                }
+        }
+        void *p1 = nullptr, *p2 = nullptr;
+        MDK_CUDA(cudaMalloc(&p1, hi.size() * sizeof(__half)));
+        e->allocs.push_back(p1);
+        MDK_CUDA(cudaMalloc(&p2, lo_t.size() * sizeof(__half)));
+        e->allocs.push_back(p2);
+        MDK_CUDA(cudaMemcpy(p1, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        MDK_CUDA(cudaMemcpy(p2, lo_t.data(), lo_t.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        e->lstm[l].w_hi = static_cast<__half *>(p1);
+        e->lstm[l].w_lo = static_cast<uint8_t *>(p2);
     }
 #undef RL_NEED
     e->prepared = true;
@@ -769,7 +955,7 @@ int mdk_rl_create(int device, int32_t lstm_size, int32_t cnn_size, int32_t use_d
     e->use_dwells = use_dwells ? 1 : 0;
     {
         const char *v = getenv("MDK_RL_CONV");      // "fp32": CUDA-core convolution (validation)
-        if (v && v[0] == 'f') e->conv_tc = 0;
+        if (v && v[0] == 'f') { e->conv_tc = 0; e->lstm_tc = 0; }
     }
     cudaError_t err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
     if (err != cudaSuccess) { delete e; return cuda_fail(err, "cudaStreamCreate", __FILE__, __LINE__); }
@@ -796,7 +982,8 @@ int mdk_rl_load(mdk_rl_engine *e, const char *name, const float *data, int64_t n
 
 int mdk_rl_set_conv(mdk_rl_engine *e, int tensor_cores) {
     MDK_REQUIRE(e, MDK_ERR_ARG, "rl_set_conv: engine is NULL");
-    e->conv_tc = tensor_cores ? 1 : 0;
+    e->conv_tc = (tensor_cores & 1) ? 1 : 0;
+    e->lstm_tc = (tensor_cores & 2) ? 1 : 0;
     return MDK_OK;
 }
 
@@ -851,8 +1038,14 @@ int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P,
         const int in = l == 0 ? RL_H : 2 * RL_H;
         rl_gemm_kernel<<<dim3((unsigned)((BP + 127) / 128), 2 * RL_G4 / 128), 256, 0, s>>>(layer_in, e->lstm[l].w_ih, e->lstm[l].bias,
                                                                                        d_gi, BP, in, 2 * RL_G4);
-        rl_lstm_kernel<<<dim3((unsigned)((B + RL_NB - 1) / RL_NB), 2), 256, RL_LSTM_SMEM, s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
+        if (e->lstm_tc) {
+            MDK_CUDA(cudaFuncSetAttribute(rl_lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
+            rl_lstm_tc_kernel<<<dim3((unsigned)((B + LT_N - 1) / LT_N), 2), LT_THREADS, LT_SMEM, s>>>(d_gi, e->lstm[l].w_hi, e->lstm[l].w_lo,
                                                                                             layer_out[l], B, P);
+        } else {
+            rl_lstm_kernel<<<dim3((unsigned)((B + RL_NB - 1) / RL_NB), 2), 256, RL_LSTM_SMEM, s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
+                                                                                                layer_out[l], B, P);
+        }
         layer_in = layer_out[l];
     }
     MDK_CUDA(cudaGetLastError());

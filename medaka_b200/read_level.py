@@ -47,9 +47,11 @@ class LatentSpaceLSTM(object):
             _lm.check(lib.mdk_rl_load(self._engine, name.encode(), ffi.cast("const float *", ffi.from_buffer(a)), a.size))
         return self
 
-    def set_conv(self, tensor_cores=True):
-        """k = 17 convolution on the tensor cores (default) or on the fp32 CUDA cores (validation)."""
-        _lm.check(_lm.lib.mdk_rl_set_conv(self._engine, 1 if tensor_cores else 0))
+    def set_conv(self, tensor_cores=True, lstm_tensor_cores=None):
+        """k = 17 convolution / LSTM recurrences on the tensor cores (default) or on the fp32 CUDA cores (validation)."""
+        if lstm_tensor_cores is None:
+            lstm_tensor_cores = tensor_cores
+        _lm.check(_lm.lib.mdk_rl_set_conv(self._engine, (1 if tensor_cores else 0) | (2 if lstm_tensor_cores else 0)))
 
     def eval(self):
         return self
