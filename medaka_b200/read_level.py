@@ -35,7 +35,7 @@ class LatentSpaceLSTM(object):
         pe = ffi.new("mdk_rl_engine **")
         _lm.check(lib.mdk_rl_create(device, lstm_size, cnn_size, 1 if use_dwells else 0, num_classes, pe))
         self._engine = pe[0]
-        self.max_cells = 1 << 28            # positions x reads per device call (bounds the 512 B / cell intermediate)
+        self.max_cells = 1 << 26            # positions x reads per device call (bounds the per-call device scratch)
 
     # ---- TorchModel interface (medaka/models.py:233-313) ----
     def load_state_dict(self, state_dict, strict=True):
