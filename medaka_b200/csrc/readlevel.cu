@@ -214,20 +214,21 @@ __global__ void __launch_bounds__(256) rl_conv17_pool_kernel(const float *__rest
 //       descriptor's start address moved down t rows (K-major SWIZZLE_NONE: a row is 16 bytes inside its k-group block)
 //   D = 128 columns of tensor memory (lane = output channel, column = position), three fp16 products per contraction like
 //       the GRU kernels (fp32-faithful)
-// A CTA owns (window b, 128 positions, a group of reads): per read it builds the activation tile in shared memory straight
-// from the int8 features (embedding + k = 1 convolution + ReLU + BN1, never written to HBM), runs 17 x 24 MMAs, drains the
-// accumulators through ReLU + BN2 and adds them to per-thread sums (one output channel x 128 positions per thread), and
-// writes the group's sum once.  Warp 0: weight producer; warp 1: MMA issuer, TMEM owner; warps 4-7: epilogue; all eight
+// A CTA owns (window b, 128 positions, a group of reads): for TWO reads at a time it builds the activation tiles in shared
+// memory straight from the int8 features (embedding + k = 1 convolution + ReLU + BN1, never written to HBM), runs
+// 17 x 24 MMAs per read against one pass of the weights, drains the two accumulators through ReLU + BN2 into per-thread
+// sums (one output channel x 128 positions per thread), and writes the group's sum once.  Warp 0: weight producer; warp 1: MMA issuer, TMEM owner; warps 4-7: epilogue; all eight
 // warps build the activation tile.
 constexpr int CT_NPOS = 128;
 constexpr int CT_ROWS = CT_NPOS + 2 * RL_PAD;            // 144 staged positions
 constexpr int CT_BPLANE = (RL_C / 8) * CT_ROWS * 16;     // 36 864 B
-constexpr int CT_WPLANE = (RL_C / 8) * RL_C * 16;        // 32 768 B
-constexpr int CT_WSTAGE = 2 * CT_WPLANE;                 // hi + lo of one tap
+constexpr int CT_BTILE = 2 * CT_BPLANE;                  // hi + lo of one read's activation tile
+constexpr int CT_PAIR = 2;                               // reads that share one pass over the weights
+constexpr int CT_WPLANE = (RL_C / 8) * RL_C * 16;        // 32 768 B: one plane of one tap = one ring stage
 constexpr int CT_STAGES = 2;
-constexpr int CT_OFF_W = 2 * CT_BPLANE;
-constexpr int CT_OFF_IN = CT_OFF_W + CT_STAGES * CT_WSTAGE;
-constexpr int CT_OFF_BAR = CT_OFF_IN + CT_ROWS * 8 * 4;
+constexpr int CT_OFF_W = CT_PAIR * CT_BTILE;
+constexpr int CT_OFF_IN = CT_OFF_W + CT_STAGES * CT_WPLANE;
+constexpr int CT_OFF_BAR = CT_OFF_IN + CT_PAIR * CT_ROWS * 8 * 4;
 constexpr int CT_SMEM = CT_OFF_BAR + 128;
 
 __global__ void __launch_bounds__(256, 1) rl_conv17_tc_kernel(const int8_t *__restrict__ x, const uint8_t *__restrict__ mask,
@@ -235,9 +236,9 @@ __global__ void __launch_bounds__(256, 1) rl_conv17_tc_kernel(const int8_t *__re
                                                               int64_t P, int D, int F, int use_dwells, int dgroup,
                                                               float *__restrict__ partial) {
     extern __shared__ __align__(128) uint8_t smem_ct[];
-    uint8_t *sb = smem_ct;
-    uint8_t *sw = smem_ct + CT_OFF_W;
-    float *sin = reinterpret_cast<float *>(smem_ct + CT_OFF_IN);       // [144][8]
+    uint8_t *sb = smem_ct;                                             // [pair][hi | lo][k-group][144][8 halfs]
+    uint8_t *sw = smem_ct + CT_OFF_W;                                  // [stage][k-group][128][8 halfs]
+    float *sin = reinterpret_cast<float *>(smem_ct + CT_OFF_IN);       // [pair][144][8]
     uint64_t *full = reinterpret_cast<uint64_t *>(smem_ct + CT_OFF_BAR);
     uint64_t *empty = full + CT_STAGES;
     uint64_t *acc_full = empty + CT_STAGES;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(256, 1) rl_conv17_tc_kernel(const int8_t *__re
         mbar_init(acc_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) { tmem_alloc(tmem_slot, 128); tmem_relinquish(); }
+    if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -274,102 +275,123 @@ __global__ void __launch_bounds__(256, 1) rl_conv17_tc_kernel(const int8_t *__re
     }
     const uint32_t idesc = make_idesc_f16(128, CT_NPOS);
     const int d0 = g * dgroup, d1 = min(D, d0 + dgroup);
-    uint32_t it = 0;             // weight stages handed over so far (producer and issuer count alike)
-    uint32_t n_done = 0;         // reads processed
-    for (int d = d0; d < d1; ++d) {
-        const int64_t bd = b * D + d;
-        if (!mask[bd]) continue;                                   // uniform over the CTA
-        // ---- build the activation tile (the previous read's MMAs are complete: everybody waited on acc_full below)
-        if (tid < CT_ROWS) {
-            const int64_t p = p0 - RL_PAD + tid;
-            float *row = sin + tid * 8;
-            if (p >= 0 && p < P) {
-                const int8_t *v = x + ((b * P + p) * D + d) * F;
-                const int base = min(max((int)v[0], 0), 5), strand = min(max((int)v[2] + 1, 0), 2);
-                for (int i = 0; i < RL_EMB; ++i) row[i] = c1.emb_base[base * RL_EMB + i] + c1.emb_strand[strand * RL_EMB + i];
-                row[RL_EMB] = (float)v[1] / 25.0f - 1.0f;
-                row[RL_EMB + 1] = use_dwells ? (float)v[4] : 0.f;
-            } else {
-                row[0] = __int_as_float(0x7fc00000);              // marker: outside the window -> zero row (conv padding)
+    uint32_t it = 0;             // weight-plane stages handed over so far (producer and issuer count alike)
+    uint32_t n_done = 0;         // passes over the weights
+    int d = d0;
+    while (true) {
+        // ---- the next one or two non-empty reads of the group share one pass over the 17 taps' weights (the weights
+        //      come from L2 each time: with one read per pass all SMs together ask for more than L2 delivers)
+        int dq[CT_PAIR], n_pair = 0;
+        while (d < d1 && n_pair < CT_PAIR) {
+            if (mask[b * D + d]) dq[n_pair++] = d;
+            ++d;
+        }
+        if (n_pair == 0) break;                                    // uniform over the CTA
+        // ---- build the activation tiles (the previous pass's MMAs are complete: everybody waited on acc_full below)
+        for (int q = 0; q < n_pair; ++q) {
+            if (tid < CT_ROWS) {
+                const int64_t p = p0 - RL_PAD + tid;
+                float *row = sin + (q * CT_ROWS + tid) * 8;
+                if (p >= 0 && p < P) {
+                    const int8_t *v = x + ((b * P + p) * D + dq[q]) * F;
+                    const int base = min(max((int)v[0], 0), 5), strand = min(max((int)v[2] + 1, 0), 2);
+                    for (int i = 0; i < RL_EMB; ++i) row[i] = c1.emb_base[base * RL_EMB + i] + c1.emb_strand[strand * RL_EMB + i];
+                    row[RL_EMB] = (float)v[1] / 25.0f - 1.0f;
+                    row[RL_EMB + 1] = use_dwells ? (float)v[4] : 0.f;
+                } else {
+                    row[0] = __int_as_float(0x7fc00000);          // marker: outside the window -> zero row (conv padding)
+                }
             }
         }
         __syncthreads();
-        for (int r = tid >> 7; r < CT_ROWS; r += 2) {
-            const float *row = sin + r * 8;
-            float y = 0.f;
-            if (!(row[0] != row[0])) {
-                float acc = b1;
-                for (int k = 0; k < nin; ++k) acc = fmaf(w1[k], row[k], acc);
-                acc = fmaxf(acc, 0.f);
-                y = (acc - m1) * s1 * g1 + o1;
+        for (int q = 0; q < n_pair; ++q) {
+            uint8_t *tile = sb + q * CT_BTILE;
+            for (int r = tid >> 7; r < CT_ROWS; r += 2) {
+                const float *row = sin + (q * CT_ROWS + r) * 8;
+                float y = 0.f;
+                if (!(row[0] != row[0])) {
+                    float acc = b1;
+                    for (int k = 0; k < nin; ++k) acc = fmaf(w1[k], row[k], acc);
+                    acc = fmaxf(acc, 0.f);
+                    y = (acc - m1) * s1 * g1 + o1;
+                }
+                __half hi, lo;
+                split_f16(y, hi, lo);
+                const int off = (bc >> 3) * (CT_ROWS * 16) + r * 16 + (bc & 7) * 2;
+                *reinterpret_cast<__half *>(tile + off) = hi;
+                *reinterpret_cast<__half *>(tile + CT_BPLANE + off) = lo;
             }
-            __half hi, lo;
-            split_f16(y, hi, lo);
-            const int off = (bc >> 3) * (CT_ROWS * 16) + r * 16 + (bc & 7) * 2;
-            *reinterpret_cast<__half *>(sb + off) = hi;
-            *reinterpret_cast<__half *>(sb + CT_BPLANE + off) = lo;
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
         __syncthreads();
         tc_fence_after_sync();
-        // ---- 17 taps
+        // ---- 17 taps x (hi plane, lo plane)
         if (warp == 0) {
             if (lane == 0) {
-                for (int t = 0; t < RL_TAPS; ++t, ++it) {
+                for (int ps = 0; ps < 2 * RL_TAPS; ++ps, ++it) {
                     const uint32_t st = it % CT_STAGES;
                     mbar_wait(&empty[st], ((it / CT_STAGES) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&full[st], CT_WSTAGE);
-                    const uint8_t *src = w_tc + (size_t)t * CT_WSTAGE;
+                    mbar_arrive_expect_tx(&full[st], CT_WPLANE);
+                    const uint8_t *src = w_tc + (size_t)ps * CT_WPLANE;           // [tap][hi | lo] back to back
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) bulk_g2s(sw + st * CT_WSTAGE + c * (CT_WSTAGE / 4), src + c * (CT_WSTAGE / 4), CT_WSTAGE / 4, &full[st]);
+                    for (int c = 0; c < 2; ++c) bulk_g2s(sw + st * CT_WPLANE + c * (CT_WPLANE / 2), src + c * (CT_WPLANE / 2), CT_WPLANE / 2, &full[st]);
                 }
+            } else {
+                it += 2 * RL_TAPS;
             }
         } else if (warp == 1) {
-            for (int t = 0; t < RL_TAPS; ++t, ++it) {
+            for (int ps = 0; ps < 2 * RL_TAPS; ++ps, ++it) {
                 const uint32_t st = it % CT_STAGES;
+                const int t = ps >> 1, lo_plane = ps & 1;
                 mbar_wait(&full[st], (it / CT_STAGES) & 1);
                 tc_fence_after_sync();
                 if (elect_one()) {
-                    const uint32_t a0 = smem_u32(sw + st * CT_WSTAGE), bb0 = smem_u32(sb) + (uint32_t)t * 16u;
+                    const uint32_t a0 = smem_u32(sw + st * CT_WPLANE);
+                    for (int q = 0; q < n_pair; ++q) {
+                        const uint32_t dcol = tmem_base + (uint32_t)(q * CT_NPOS);
+                        const uint32_t bb0 = smem_u32(sb + q * CT_BTILE) + (uint32_t)t * 16u;
+                        // hi plane of the weights: x activation hi, then x activation lo;  lo plane: x activation hi
+                        const int n_prod = lo_plane ? 1 : 2;
+                        for (int prod = 0; prod < n_prod; ++prod) {
+                            const int pb = lo_plane ? 0 : prod;
 #pragma unroll
-                    for (int prod = 0; prod < 3; ++prod) {
-                        const int pa = prod == 2, pb = prod == 1;          // W part, activation part
-#pragma unroll
-                        for (int ks = 0; ks < RL_C / 16; ++ks) {
-                            const uint64_t ad = make_smem_desc(a0 + pa * CT_WPLANE + ks * 2 * (RL_C * 16), RL_C * 16, 128);
-                            const uint64_t bdsc = make_smem_desc(bb0 + pb * CT_BPLANE + ks * 2 * (CT_ROWS * 16), CT_ROWS * 16, 128);
-                            umma_f16(tmem_base, ad, bdsc, idesc, (t | prod | ks) ? 1u : 0u);
+                            for (int ks = 0; ks < RL_C / 16; ++ks) {
+                                const uint64_t ad = make_smem_desc(a0 + ks * 2 * (RL_C * 16), RL_C * 16, 128);
+                                const uint64_t bdsc = make_smem_desc(bb0 + pb * CT_BPLANE + ks * 2 * (CT_ROWS * 16), CT_ROWS * 16, 128);
+                                umma_f16(dcol, ad, bdsc, idesc, (ps | prod | ks) ? 1u : 0u);
+                            }
                         }
                     }
                     umma_commit(&empty[st]);
-                    if (t == RL_TAPS - 1) umma_commit(acc_full);
+                    if (ps == 2 * RL_TAPS - 1) umma_commit(acc_full);
                 }
                 __syncwarp();
             }
         } else {
-            it += RL_TAPS;
+            it += 2 * RL_TAPS;
         }
-        if (warp == 0 && lane != 0) it += RL_TAPS;
-        // ---- everybody waits for the read's accumulators (the activation tile may then be rebuilt)
+        // ---- everybody waits for the pass's accumulators (the activation tiles may then be rebuilt)
         mbar_wait(acc_full, n_done & 1);
         tc_fence_after_sync();
         if (warp >= 4) {
-            const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            for (int q = 0; q < n_pair; ++q) {
+                const uint32_t t_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(q * CT_NPOS);
 #pragma unroll
-            for (int c32 = 0; c32 < CT_NPOS; c32 += 32) {
-                uint32_t v[32];
-                tmem_ld_x32(t_lane + c32, v);
-                tmem_ld_wait();
+                for (int c32 = 0; c32 < CT_NPOS; c32 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_x32(t_lane + c32, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float a = fmaxf(__uint_as_float(v[i]) + b2, 0.f);
-                    pooled[c32 + i] += (a - m2) * s2 * g2 + o2;
+                    for (int i = 0; i < 32; ++i) {
+                        const float av = fmaxf(__uint_as_float(v[i]) + b2, 0.f);
+                        pooled[c32 + i] += (av - m2) * s2 * g2 + o2;
+                    }
                 }
             }
         }
         tc_fence_before_sync();
-        __syncthreads();                                           // accumulators drained, tile free
+        __syncthreads();                                           // accumulators drained, tiles free
         tc_fence_after_sync();
         ++n_done;
     }
@@ -382,7 +404,7 @@ __global__ void __launch_bounds__(256, 1) rl_conv17_tc_kernel(const int8_t *__re
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 128); }
+    if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, 256); }
 }
 
 // ---------------------------------------------------------------------------------------------- mean + Linear(C -> H)
@@ -797,6 +819,8 @@ struct mdk_rl_engine {
     RlLstmLayer lstm[2];
     float *lin_w = nullptr, *lin_b = nullptr;
     std::vector<void *> allocs;
+    uint8_t *scratch = nullptr;    // per-call intermediates, grown on demand and kept
+    size_t scratch_bytes = 0;
     cudaStream_t stream = nullptr;
 };
 
@@ -968,6 +992,7 @@ int mdk_rl_destroy(mdk_rl_engine *e) {
     cudaSetDevice(e->device);
     if (e->stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
     for (void *p : e->allocs) cudaFree(p);
+    if (e->scratch) cudaFree(e->scratch);
     delete e;
     cudaGetLastError();
     return MDK_OK;
@@ -1006,9 +1031,14 @@ int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P,
                  o_part = take((size_t)B * n_groups * P * RL_C * 4), o_z = take((size_t)BP * RL_H * 4),
                  o_gi = take((size_t)BP * 2 * RL_G4 * 4), o_h0 = take((size_t)BP * 2 * RL_H * 4),
                  o_h1 = take((size_t)BP * 2 * RL_H * 4), o_probs = take((size_t)BP * NCLS * 4);
-    uint8_t *buf = nullptr;
-    MDK_CUDA(cudaMalloc(&buf, off));
-    struct Guard { uint8_t *p; ~Guard() { cudaFree(p); } } guard{buf};
+    if (off > e->scratch_bytes) {
+        if (e->scratch) cudaFree(e->scratch);
+        e->scratch = nullptr;
+        e->scratch_bytes = 0;
+        MDK_CUDA(cudaMalloc(&e->scratch, off + off / 8));
+        e->scratch_bytes = off + off / 8;
+    }
+    uint8_t *buf = e->scratch;
     int8_t *d_x = (int8_t *)(buf + o_x);
     uint8_t *d_mask = buf + o_mask;
     float *d_y1 = (float *)(buf + o_y1), *d_part = (float *)(buf + o_part), *d_z = (float *)(buf + o_z),
