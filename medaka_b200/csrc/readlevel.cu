@@ -632,8 +632,9 @@ __global__ void __launch_bounds__(256, 1) rl_lstm_kernel(const float *__restrict
 
 // ---------------------------------------------------------------------------------------------- LSTM on tcgen05
 // The recurrence with the matvec on the tensor cores:  G^T[4H][16 windows] = W_hh[4H][H] . h^T[H][16]  per time step.
-//   A = W_hh: the fp16 hi plane of all four gates lives in TENSOR MEMORY (4 x 64 columns, TS mode), the lo plane in
-//       shared memory as K-major operand tiles (4 x 32 KiB, SS mode) - hi + lo of four gates would fill all 512 columns
+//   A = W_hh: the fp16 hi plane of all four gates lives in TENSOR MEMORY (4 x 64 columns, TS mode) and so does the lo
+//       plane of gates i and f (2 x 64 columns behind the accumulators); the lo plane of gates g and o comes from shared
+//       memory as K-major operand tiles (SS mode) - hi + lo of all four gates would fill all 512 columns
 //   B = the h tile [16 windows][128] the gate warps publish every step (fp16 hi | lo, K-major)
 //   D = four 16-column accumulators (lane = hidden unit, column = window); three products per contraction:
 //       W_hi.h_hi and W_hi.h_lo from tensor memory, W_lo.h_hi from shared memory
@@ -647,6 +648,8 @@ constexpr int LT_OFF_H = 4 * LT_WLO_GATE;
 constexpr int LT_OFF_BAR = LT_OFF_H + 2 * LT_HPLANE;
 constexpr int LT_SMEM = LT_OFF_BAR + 64;
 constexpr uint32_t LT_ACC_COL = 256;                         // accumulators behind the four 64-column weight blocks
+constexpr uint32_t LT_LO_COL = 320;                          // lo plane of the first LT_LO_TMEM_GATES gates
+constexpr int LT_LO_TMEM_GATES = 2;
 constexpr int LT_W = LT_N / 2;                               // windows per gate thread
 constexpr int LT_ISSUER = 8;                                 // warps 0-7 gate warps, warp 8 issues
 constexpr int LT_THREADS = 32 * (LT_ISSUER + 1);
@@ -657,6 +660,7 @@ __device__ __forceinline__ float lt_sigmoid(float x) { return lt_rcp(1.0f + lt_e
 __device__ __forceinline__ float lt_tanh(float x) { return fmaf(-2.0f, lt_rcp(1.0f + lt_ex2(2.8853900817779268f * x)), 1.0f); }
 
 __global__ void __launch_bounds__(LT_THREADS, 1) rl_lstm_tc_kernel(const float *__restrict__ gi, const __half *__restrict__ w_hi,
+                                                            const __half *__restrict__ w_lo_rm,
                                                             const uint8_t *__restrict__ w_lo_tiles, float *__restrict__ out,
                                                             int64_t B, int64_t P) {
     extern __shared__ __align__(128) uint8_t smem_lt[];
@@ -693,6 +697,17 @@ __global__ void __launch_bounds__(LT_THREADS, 1) rl_lstm_tc_kernel(const float *
                 tmem_st_x8(t_w + (uint32_t)(g * 64 + ks * 8), v);
             }
         }
+        // the lo plane of gates i and f fits behind the accumulators (columns 320..447): their third product runs in
+        // TS mode too (10 instead of 40 cycles per MMA); gates g and o take theirs from shared memory
+        for (int g = 0; g < LT_LO_TMEM_GATES; ++g) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(w_lo_rm + (((size_t)dir * 4 + g) * RL_H + j) * RL_H);
+#pragma unroll
+            for (int ks = 0; ks < RL_H / 16; ++ks) {
+                const uint4 lo4 = src[2 * ks], hi4 = src[2 * ks + 1];
+                const uint32_t v[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+                tmem_st_x8(t_w + LT_LO_COL + (uint32_t)(g * 64 + ks * 8), v);
+            }
+        }
         tmem_st_wait();
     }
     fence_proxy_async_smem();
@@ -720,9 +735,13 @@ __global__ void __launch_bounds__(LT_THREADS, 1) rl_lstm_tc_kernel(const float *
                     }
 #pragma unroll
                     for (int ks = 0; ks < RL_H / 16; ++ks) {
-                        const uint64_t ad = make_smem_desc(wl + g * LT_WLO_GATE + ks * 2 * (RL_H * 16), RL_H * 16, 128);
                         const uint64_t bh = make_smem_desc(h_hi + ks * 2 * (LT_N * 16), LT_N * 16, 128);
-                        umma_f16(d, ad, bh, idesc, 1u);
+                        if (g < LT_LO_TMEM_GATES) {
+                            umma_f16_ts(d, tmem_base + LT_LO_COL + (uint32_t)(g * 64 + ks * 8), bh, idesc, 1u);
+                        } else {
+                            const uint64_t ad = make_smem_desc(wl + g * LT_WLO_GATE + ks * 2 * (RL_H * 16), RL_H * 16, 128);
+                            umma_f16(d, ad, bh, idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(acc_full);
@@ -792,6 +811,7 @@ __global__ void __launch_bounds__(LT_THREADS, 1) rl_lstm_tc_kernel(const float *
 // ---------------------------------------------------------------------------------------------- engine
 struct RlLstmLayer {
     __half *w_hi = nullptr;     // [2][4H][H] fp16 hi plane of W_hh (tensor-core kernel: -> tensor memory)
+    __half *w_lo_rm = nullptr;  // [2][4H][H] fp16 lo plane, row-major (gates i, f: -> tensor memory)
     uint8_t *w_lo = nullptr;    // [2][4 gates][k-group 16][row 128][8 halfs] lo plane as shared-memory A operand tiles
     float *w_ih = nullptr;      // [2 dirs * 4H][in]   (both directions stacked: one GEMM)
     float *bias = nullptr;      // [2 * 4H]  b_ih + b_hh
@@ -933,7 +953,7 @@ int rl_prepare(mdk_rl_engine *e) {
             (rc = rl_upload(e, w3t, &e->lstm[l].w3t)) || (rc = rl_upload(e, wo, &e->lstm[l].wo)))
             return rc;
         // tensor-core operands: hi plane row-major (torch's [4H][H] as it is), lo plane as K-major tiles per gate
-        std::vector<__half> hi((size_t)2 * RL_G4 * RL_H), lo_t((size_t)2 * RL_G4 * RL_H);
+        std::vector<__half> hi((size_t)2 * RL_G4 * RL_H), lo_t((size_t)2 * RL_G4 * RL_H), lo_rm((size_t)2 * RL_G4 * RL_H);
         for (int d = 0; d < 2; ++d) {
             const std::string sfx = "_l" + std::to_string(l) + (d ? "_reverse" : "");
             const std::vector<float> &whh = e->host["lstm.weight_hh" + sfx];
@@ -943,11 +963,16 @@ int rl_prepare(mdk_rl_engine *e) {
                     const __half h16 = __float2half_rn(v);
                     hi[((size_t)d * RL_G4 + r) * RL_H + k] = h16;
                     const int g = r / RL_H, jj = r % RL_H;
-                    lo_t[(size_t)d * RL_G4 * RL_H + (((size_t)g * (RL_H / 8) + k / 8) * RL_H + jj) * 8 + (k % 8)] =
-                        __float2half_rn(v - __half2float(h16));
+                    const __half l16 = __float2half_rn(v - __half2float(h16));
+                    lo_t[(size_t)d * RL_G4 * RL_H + (((size_t)g * (RL_H / 8) + k / 8) * RL_H + jj) * 8 + (k % 8)] = l16;
+                    lo_rm[((size_t)d * RL_G4 + r) * RL_H + k] = l16;
                 }
         }
-        void *p1 = nullptr, *p2 = nullptr;
+        void *p1 = nullptr, *p2 = nullptr, *p3 = nullptr;
+        MDK_CUDA(cudaMalloc(&p3, lo_rm.size() * sizeof(__half)));
+        e->allocs.push_back(p3);
+        MDK_CUDA(cudaMemcpy(p3, lo_rm.data(), lo_rm.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        e->lstm[l].w_lo_rm = static_cast<__half *>(p3);
         MDK_CUDA(cudaMalloc(&p1, hi.size() * sizeof(__half)));
         e->allocs.push_back(p1);
         MDK_CUDA(cudaMalloc(&p2, lo_t.size() * sizeof(__half)));
@@ -1070,8 +1095,8 @@ int mdk_rl_forward(mdk_rl_engine *e, const int8_t *x_host, int64_t B, int64_t P,
                                                                                        d_gi, BP, in, 2 * RL_G4);
         if (e->lstm_tc) {
             MDK_CUDA(cudaFuncSetAttribute(rl_lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
-            rl_lstm_tc_kernel<<<dim3((unsigned)((B + LT_N - 1) / LT_N), 2), LT_THREADS, LT_SMEM, s>>>(d_gi, e->lstm[l].w_hi, e->lstm[l].w_lo,
-                                                                                            layer_out[l], B, P);
+            rl_lstm_tc_kernel<<<dim3((unsigned)((B + LT_N - 1) / LT_N), 2), LT_THREADS, LT_SMEM, s>>>(d_gi, e->lstm[l].w_hi, e->lstm[l].w_lo_rm,
+                                                                                            e->lstm[l].w_lo, layer_out[l], B, P);
         } else {
             rl_lstm_kernel<<<dim3((unsigned)((B + RL_NB - 1) / RL_NB), 2), 256, RL_LSTM_SMEM, s>>>(d_gi, e->lstm[l].w3t, e->lstm[l].wo,
                                                                                                 layer_out[l], B, P);

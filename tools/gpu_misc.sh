@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"rl_|head_kernel" -s 8 -c 8 --csv --log-file $O/r02_rl_launches.csv python tools/rl_bench.py --windows 64 --reads 30 --cpu-windows 0 --tc-only > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none -k regex:"rl_conv17_tc|rl_lstm_tc" -s 3 -c 2 -o $O/r02_prof_rl python tools/rl_bench.py --windows 64 --reads 30 --cpu-windows 0 --tc-only > $O/r02_ncu_rl.log 2>&1
-ncu -i $O/r02_prof_rl.ncu-rep --page raw --csv > $O/r02_prof_rl_raw.csv 2>/dev/null; rm -f $O/r02_prof_rl.ncu-rep; ls -la $O/r02_prof_rl_raw.csv
+timeout 300 python -m pytest tests/test_read_level.py -x -q -m gpu > $O/misc_pytest.log 2>&1; grep -v "^  File" $O/misc_pytest.log | tail -8
+timeout 200 python tools/rl_bench.py > $O/r02k_rl_bench.json 2> $O/r02k_rl_bench.err; cat $O/r02k_rl_bench.json; tail -2 $O/r02k_rl_bench.err
+timeout 200 python tools/rl_bench.py --windows 256 --positions 1000 --reads 30 --cpu-windows 0 --tc-only > $O/r02k_rl_bench_256.json 2>> $O/r02k_rl_bench.err; cat $O/r02k_rl_bench_256.json
