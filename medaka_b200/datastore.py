@@ -358,8 +358,9 @@ class DataStore(object):
     def n_samples(self):
         return len(self.sample_registry)
 
-    def write_sample(self, sample):
-        """Queue a sample for writing unless its name is already registered."""
+    def write_sample(self, sample, copy=True):
+        """Queue a sample for writing unless its name is already registered.  ``copy=False`` hands the arrays to the
+        writer thread as they are: for callers whose arrays are not reused before the store is closed."""
         fields = {f: _to_numpy(getattr(sample, f)) for f in sample._fields if getattr(sample, f) is not None}
         if not any(isinstance(v, np.ndarray) for v in fields.values()):
             self.logger.debug('Not writing sample as it has no data.')
@@ -371,7 +372,8 @@ class DataStore(object):
                 return
             self._sample_registry.add(name)
         # copy views of pinned / reused buffers before handing them to the writer thread
-        fields = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in fields.items()}
+        if copy:
+            fields = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in fields.items()}
         self.write_futures.append(self.write_executor.submit(self._backend.write_fields, name, fields))
 
     def load_sample(self, key):

@@ -146,7 +146,9 @@ def run_prediction(output, bam, regions, model, feature_encoder, chunk_len, chun
         for i, (sample, prob, feat) in enumerate(zip(data, class_probs, batch.features)):
             feats = feat if save_features else None
             extra = {} if labels is None else {"labels": labels[i]}
-            ds.write_sample(sample.amend(label_probs=prob, features=feats, **extra))
+            # (no defensive copy: the probabilities / labels are this batch's private arrays - predict_async copies
+            # them out of its pinned slot -, positions and depth are slices of the region's arrays that nobody rewrites)
+            ds.write_sample(sample.amend(label_probs=prob, features=feats, **extra), copy=False)
 
     with datastore.DataStore(output, 'a') as ds:
         # look-ahead: enough batches are queued on the engine for it to coalesce them into device-filling groups
