@@ -239,7 +239,7 @@ def cpu_reference_rate(threads, sample_windows, cols, feats, steps=1, warmup=0, 
         cols = int(min(2000, max(40, r0 * budget_s / sample_windows)))
     x = fill_features(np.empty((sample_windows, cols, feats), dtype=np.float32), 1)
     for _ in range(warmup):
-        gru_oracle.predict_on_batch(model, x)
+        gru_oracle.predict_on_batch(model, x[:, :min(cols, 500)])      # thread pool / allocator warm-up on a short slice
     t0 = time.perf_counter()
     for _ in range(steps):
         gru_oracle.predict_on_batch(model, x)
@@ -347,7 +347,8 @@ def main():
     ap.add_argument("--precision", default="tc", choices=["tc", "fp32"])
     ap.add_argument("--cpu-windows", type=int, default=200, help="windows in the bounded CPU-baseline sample")
     ap.add_argument("--cpu-cols", type=int, default=0,
-                    help="columns per window in the CPU-baseline sample (0 = sized for ~12 s per pass)")
+                    help="columns per window in the CPU sample (0 = the full window length for the cpu_baseline of the "
+                         "default run, ~15 s; sized for ~12 s per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -619,7 +620,7 @@ def main():
     if not args.no_cpu_baseline:
         cores = host_cores()
         log("cpu baseline on %d threads" % cores)
-        rate, sec, ccols = cpu_reference_rate(cores, args.cpu_windows, args.cpu_cols, F, steps=1, warmup=1)
+        rate, sec, ccols = cpu_reference_rate(cores, args.cpu_windows, args.cpu_cols or T, F, steps=1, warmup=1)
         cpu_baseline = {"value": rate, "unit": "positions/s", "cores": cores, "kind": "port",
                         "sample": "%d windows x %d cols, 1 warm-up + 1 timed pass (%.1f s), torch %s fp32 nn.GRU oracle" % (
                             args.cpu_windows, ccols, sec, torch.__version__)}
@@ -629,13 +630,14 @@ def main():
         "metric": "pileup positions/sec (consensus inference)", "value": value, "unit": "positions/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 gate math; fp16 hi/lo split tensor-core operands, fp32 accumulate"
-        if args.precision == "tc" else "f32",
+        "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(args.config) if not (args.windows or args.cols) else
                    "synthetic %d windows x %d cols x %d feats" % (B, T, F),
                    "baseline_config": args.config, "windows_per_gpu": B, "cols": T, "features": F,
                    "precision": args.precision, "rec_mode": args.rec_mode,
+                   "arithmetic": "fp32 state, gate math and accumulation; tensor-core operands as fp16 hi/lo pairs, three "
+                                 "products per contraction (fp32-faithful)" if args.precision == "tc" else "fp32 CUDA cores",
                    "group_windows": min(group, B), "batch_windows": bw, "batches_in_flight": depth,
                    "l2_policy": "inputs larger than L2 (%d MB of features, > 3 GB of activations per step)" % (feats.nbytes >> 20),
                    "sm_count": info["sm_count"]},
