@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_pipeline.py tests/test_read_level.py -x -q -m gpu 2>&1 | tail -3
-timeout 300 python tools/pipeline_bench.py --mb 100 > gpurun_out/r02_pipeline_1gpu_100mb.json 2> gpurun_out/r02_pipeline_100mb.err; cat gpurun_out/r02_pipeline_1gpu_100mb.json
+timeout 600 python bench.py > gpurun_out/r02w_bench_default.json 2> gpurun_out/r02w_bench_default.err; python -c "
+import json; d=json.loads(open('gpurun_out/r02w_bench_default.json').read().strip().splitlines()[-1]); print('value %.3e e2e %.3e'%(d['value'], d['e2e']['value']), d['dtype'], d['cpu_baseline'], d['steps'], d['warmup'])" || tail -5 gpurun_out/r02w_bench_default.err
