@@ -270,12 +270,12 @@ class GRUModel(object):
         return _Handle()
 
     def lookahead(self, batch_size, window_len=None):
-        """How many ``predict_async`` calls of ``batch_size`` windows to keep in flight (three coalesced groups: two
-        computing, one copying in or out)."""
+        """How many ``predict_async`` calls of ``batch_size`` windows to keep in flight (four coalesced groups, one per
+        big staging lane: two computing, one copying in, one copying out)."""
         pref = self.preferred_batch_size()
         if window_len is not None and batch_size * window_len <= (1 << 18):
             return 14                                   # small forwards rotate over the engine's small lanes
-        return int(max(2, min(64, 3 * ((pref + batch_size - 1) // max(batch_size, 1)) + 1)))
+        return int(max(2, min(64, 4 * ((pref + batch_size - 1) // max(batch_size, 1)) + 1)))
 
     def reserve(self, windows, window_len):
         """Size the engine's compute lanes for coalesced groups of up to ``windows`` windows (mdk_engine_reserve)."""
